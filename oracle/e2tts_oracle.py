@@ -1,0 +1,423 @@
+"""CPU oracle for the E2-TTS flow-matching hot path — a plain PyTorch fp32 RESTATEMENT.
+
+THIS FILE IS TEST INFRASTRUCTURE. Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
+`--impl reference` legs of `bench.py` may import it; the product package never does.
+
+What it restates (all citations relative to /root/reference/e2_tts_pytorch/e2_tts.py unless noted):
+  * E2TTS.forward            :1468-1595   (flow-matching objective)
+  * transformer_with_pred_head :1250-1301, cfg_transformer_with_pred_head :1303-1330, project :113-124
+  * E2TTS.sample             :1332-1466   (fixed-grid midpoint ODE, torchdiffeq semantics)
+  * Transformer.forward      :731-952     (multistream block stack)
+  * DurationPredictor.forward :1042-1113
+  * leaves: MelSpec :248-290, DepthwiseConv :295-328, AdaLNZero :332-351, RandomFourierEmbed :355-364,
+    CharacterEmbed :390-412, TextAudioCrossCondition :486-513, mask helpers :173-235
+  * unvendored third-party leaves (x-transformers Attention/FeedForward/RMSNorm/AdaptiveRMSNorm/
+    RotaryEmbedding, hyper-connections HyperConnections, hl-gauss-pytorch HLGaussLayer) as published,
+    restated in SURVEY.md Appendix A.1-A.7.
+
+It is written functionally over a *reference-format state_dict* (SURVEY Appendix B names), so the very
+same weights can be loaded into the reference module, this oracle, and the CUDA modules.
+
+PINNING STATUS
+  * composition (everything that lives in e2_tts.py) is pinned: `tests/test_oracle_vs_reference.py`
+    runs the reference's own e2_tts.py (loaded unmodified by oracle/load_reference.py) against this
+    file in the build container, and `oracle/make_golden.py` froze reference outputs into
+    `tests/golden/*.pt`, which `tests/test_oracle_golden.py` re-checks everywhere.
+  * the third-party leaves are **parity unpinned**: the reference ships no tests/golden vectors and
+    the real packages are not installable offline, so the goldens were produced with the restated
+    leaves of `oracle/ref_leaves/`. MelSpec is pinned against the installed torchaudio 2.11.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------
+# config
+
+
+@dataclass
+class TransformerCfg:
+    dim: int
+    depth: int = 8
+    heads: int = 8
+    dim_head: int = 64
+    ff_mult: int = 4
+    dim_text: int | None = None
+    text_depth: int | None = None
+    cond_on_time: bool = True
+    kernel_size: int = 31
+    num_registers: int = 32
+    num_residual_streams: int = 4
+    softclamp: float = 50.0
+
+    def __post_init__(self):
+        self.dim_text = self.dim_text or self.dim // 2  # :566
+        self.text_depth = self.text_depth or self.depth  # :572
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers (:113-124, :173-235)
+
+
+def lens_to_mask(lens, length):  # :173-182
+    return torch.arange(length, device=lens.device)[None, :] < lens[:, None]
+
+
+def mask_from_frac_lengths(seq_len, frac_lengths, rand, max_length):  # :193-210 with `rand` injected
+    lengths = (frac_lengths * seq_len).long()
+    max_start = seq_len - lengths
+    start = (max_start * rand).long().clamp(min=0)
+    end = start + lengths
+    n = int(seq_len.max().item())
+    seq = torch.arange(n, device=start.device)
+    out = (seq[None] >= start[:, None]) & (seq[None] < end[:, None])
+    if max_length > n:
+        out = F.pad(out, (0, max_length - n), value=False)
+    return out[..., :max_length]
+
+
+def list_str_to_tensor(text):  # :128-135
+    rows = [torch.tensor([*bytes(t, 'UTF-8')], dtype=torch.long) for t in text]
+    n = max(r.numel() for r in rows)
+    return torch.stack([F.pad(r, (0, n - r.numel()), value=-1) for r in rows])
+
+
+def project(x, y):  # :113-124 (fp64)
+    shape, dtype = x.shape, x.dtype
+    x, y = x.reshape(shape[0], -1).double(), y.reshape(shape[0], -1).double()
+    unit = F.normalize(y, dim=-1)
+    par = (x * unit).sum(-1, keepdim=True) * unit
+    return par.reshape(shape).to(dtype), (x - par).reshape(shape).to(dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# leaves
+
+
+def rmsnorm(x, g):  # A.1: F.normalize(x) * sqrt(d) * g, eps 1e-12 on the norm
+    return F.normalize(x, dim=-1) * (x.shape[-1] ** 0.5) * g
+
+
+def rotary_freqs(n, dim_head, device):  # A.3: interleaved duplication
+    inv = 1.0 / (10000 ** (torch.arange(0, dim_head, 2, device=device).float() / dim_head))
+    f = torch.arange(n, device=device).float()[:, None] * inv[None]
+    return torch.stack((f, f), -1).reshape(n, dim_head)
+
+
+def apply_rotary(t, freqs):  # A.3 on (b,h,n,dh); rotate_half on interleaved pairs
+    t2 = t.reshape(*t.shape[:-1], -1, 2)
+    rot = torch.stack((-t2[..., 1], t2[..., 0]), -1).reshape(t.shape)
+    return t * freqs.cos() + rot * freqs.sin()
+
+
+def attention(sd, p, x, mask, freqs, value_residual, heads, dim_head, softclamp):
+    """A.4; returns (out, orig_values). `p` = key prefix of the Attention module."""
+    b, n, _ = x.shape
+    split = lambda t: t.reshape(b, n, heads, dim_head).permute(0, 2, 1, 3)
+    q, k, v = (split(x @ sd[p + f'.to_{c}.weight'].t()) for c in 'qkv')
+    orig_v = v
+    if value_residual is not None:
+        mix = torch.sigmoid(x @ sd[p + '.to_value_residual_mix.0.weight'].t() + sd[p + '.to_value_residual_mix.0.bias'])
+        mix = mix.permute(0, 2, 1)[..., None]
+        v = v * mix + value_residual * (1.0 - mix)
+    q, k = apply_rotary(q, freqs), apply_rotary(k, freqs)
+    sim = torch.einsum('bhid,bhjd->bhij', q, k) * dim_head ** -0.5
+    sim = torch.tanh(sim / softclamp) * softclamp
+    if mask is not None:
+        sim = sim.masked_fill(~mask[:, None, None, :], -torch.finfo(sim.dtype).max)
+    attn = torch.softmax(sim.float(), dim=-1).to(sim.dtype)
+    out = torch.einsum('bhij,bhjd->bhid', attn, v)
+    gate = torch.sigmoid(x @ sd[p + '.to_v_head_gate.weight'].t() + sd[p + '.to_v_head_gate.bias'])
+    out = out * gate.permute(0, 2, 1)[..., None]
+    out = out.permute(0, 2, 1, 3).reshape(b, n, heads * dim_head) @ sd[p + '.to_out.weight'].t()
+    if mask is not None:
+        out = out * mask[..., None]
+    return out, orig_v
+
+
+def feedforward(sd, p, x):  # A.2 GEGLU (exact erf GELU)
+    h = x @ sd[p + '.ff.0.proj.weight'].t() + sd[p + '.ff.0.proj.bias']
+    u, g = h.chunk(2, dim=-1)
+    return (u * F.gelu(g)) @ sd[p + '.ff.2.weight'].t() + sd[p + '.ff.2.bias']
+
+
+def depthwise_conv(sd, p, x, mask):  # :312-328
+    if mask is not None:
+        x = x * mask[..., None]
+    w, b = sd[p + '.dw_conv1d.0.weight'], sd[p + '.dw_conv1d.0.bias']
+    y = F.conv1d(x.transpose(1, 2), w, b, padding=w.shape[-1] // 2, groups=w.shape[0])
+    y = F.silu(y).transpose(1, 2)
+    if mask is not None:
+        y = y * mask[..., None]
+    return y
+
+
+def hyper_width(sd, p, res, S):  # A.5 width connection on (b, n, S, d)
+    d = res.shape[-1]
+    normed = F.normalize(res, dim=-1) * d ** 0.5 * (sd[p + '.norm.gamma'] + 1.0)
+    alpha = torch.tanh(normed @ sd[p + '.dynamic_alpha_fn']) * sd[p + '.dynamic_alpha_scale'] + sd[p + '.static_alpha']
+    beta = torch.tanh(normed @ sd[p + '.dynamic_beta_fn']) * sd[p + '.dynamic_beta_scale'] + sd[p + '.static_beta']
+    mix = torch.einsum('bnst,bnsd->bntd', alpha, res)
+    return mix[..., 0, :], mix[..., 1:, :], beta
+
+
+def hyper_depth(rest, beta, y):  # A.5 depth connection
+    return y[..., None, :] * beta[..., None] + rest
+
+
+# --------------------------------------------------------------------------------------------------
+# Transformer.forward (:731-952). Residual streams are held as (b, n, S, d) — the reference's
+# '(b s) n d' layout is a pure relabelling (A.5), all cross-stream ops are per token.
+
+
+def transformer_forward(sd, cfg: TransformerCfg, x, times=None, mask=None, text_embed=None, prefix='transformer'):
+    P = prefix
+    b, n, d = x.shape
+    S, R = cfg.num_residual_streams, cfg.num_registers
+    L = cfg.depth
+    dev = x.device
+    assert (times is not None) == cfg.cond_on_time  # :756
+
+    x = x + sd[P + '.abs_pos_emb.weight'][:n]  # :760-763
+    x = torch.cat((sd[P + '.registers'][None].expand(b, -1, -1), x), dim=1)  # :767-768
+    if mask is not None:
+        mask = F.pad(mask, (R, 0), value=True)  # :771
+    npr = n + R
+
+    cond = None
+    if times is not None:  # :778-789 time_cond_mlp = RandomFourierEmbed -> Linear(d+1,d) -> SiLU
+        if times.ndim == 0:
+            times = times.expand(b)
+        fr = times[:, None] * sd[P + '.time_cond_mlp.0.weights'][None] * 2 * math.pi  # :362
+        four = torch.cat((times[:, None], fr.sin(), fr.cos()), dim=-1)  # :363
+        cond = F.silu(four @ sd[P + '.time_cond_mlp.1.weight'].t() + sd[P + '.time_cond_mlp.1.bias'])
+
+    freqs = rotary_freqs(npr, cfg.dim_head, dev)  # :793 (text uses the same dim_head, :798)
+
+    has_text = text_embed is not None
+    if has_text:
+        text_embed = torch.cat((sd[P + '.text_registers'][None].expand(b, -1, -1), text_embed), dim=1)  # :800-801
+
+    xs = x[:, :, None, :].expand(b, npr, S, d).contiguous()  # :818 expand
+    ts = text_embed[:, :, None, :].expand(b, npr, S, cfg.dim_text).contiguous() if has_text else None  # :821
+
+    def norm(prefix_key, h):  # rmsnorm_klass :615 (AdaptiveRMSNorm when cond_on_time)
+        if cfg.cond_on_time:
+            gamma = cond @ sd[prefix_key + '.to_gamma.weight'].t()
+            return F.normalize(h, dim=-1) * d ** 0.5 * (gamma[:, None, :] + 1.0)
+        return rmsnorm(h, sd[prefix_key + '.g'])
+
+    def post(prefix_key, h):  # postbranch_klass :616 (AdaLNZero when cond_on_time)
+        if cfg.cond_on_time:
+            g = torch.sigmoid(cond @ sd[prefix_key + '.to_gamma.weight'].t() + sd[prefix_key + '.to_gamma.bias'])
+            return h * g[:, None, :]
+        return h
+
+    skips = []
+    attn_first, text_attn_first = None, None
+    for i in range(L):
+        lp = f'{P}.layers.{i}'
+        hp = f'{P}.hyper_conns.{i}'
+        if has_text and i < cfg.text_depth:  # :853-883
+            tp = lp + '.1'
+            br, rest, beta = hyper_width(sd, hp + '.1.0', ts, S)
+            ts = hyper_depth(rest, beta, depthwise_conv(sd, tp + '.0', br, mask))
+            br, rest, beta = hyper_width(sd, hp + '.1.1', ts, S)
+            out, vals = attention(sd, tp + '.2', rmsnorm(br, sd[tp + '.1.g']), mask, freqs, text_attn_first,
+                                  cfg.heads, cfg.dim_head, cfg.softclamp)
+            ts = hyper_depth(rest, beta, out)
+            text_attn_first = vals if text_attn_first is None else text_attn_first
+            br, rest, beta = hyper_width(sd, hp + '.1.2', ts, S)
+            ts = hyper_depth(rest, beta, feedforward(sd, tp + '.4', rmsnorm(br, sd[tp + '.3.g'])))
+            at = torch.cat((xs, ts), dim=-1)  # :508-513 on every stream
+            xs_new = xs + at @ sd[tp + '.5.text_to_audio.weight'].t()
+            if (tp + '.5.audio_to_text.weight') in sd:
+                ts = ts + at @ sd[tp + '.5.audio_to_text.weight'].t()
+            xs = xs_new
+
+        if (i + 1) <= L // 2:  # :887-896
+            skips.append(xs)
+        else:
+            xs = torch.cat((xs, skips.pop()), dim=-1) @ sd[lp + '.0.0.weight'].t()
+
+        sp = lp + '.0'
+        br, rest, beta = hyper_width(sd, hp + '.0.0', xs, S)  # :900-902
+        xs = hyper_depth(rest, beta, depthwise_conv(sd, sp + '.1', br, mask))
+        br, rest, beta = hyper_width(sd, hp + '.0.1', xs, S)  # :906-916
+        out, vals = attention(sd, sp + '.3', norm(sp + '.2', br), mask, freqs, attn_first,
+                              cfg.heads, cfg.dim_head, cfg.softclamp)
+        xs = hyper_depth(rest, beta, post(sp + '.5', out))
+        attn_first = vals if attn_first is None else attn_first
+        br, rest, beta = hyper_width(sd, hp + '.0.2', xs, S)  # :936-939
+        xs = hyper_depth(rest, beta, post(sp + '.8', feedforward(sd, sp + '.7', norm(sp + '.6', br))))
+
+    assert not skips
+    out = xs[:, R:].sum(dim=2)  # :943-947 drop registers, reduce streams
+    return rmsnorm(out, sd[P + '.final_norm.g'])  # :952
+
+
+# --------------------------------------------------------------------------------------------------
+# E2TTS
+
+
+def character_embed(sd, text, max_seq_len, prefix='embed_text'):  # :400-412
+    text = text + 1
+    text = text[:, :max_seq_len]
+    if text.shape[1] < max_seq_len:
+        text = F.pad(text, (0, max_seq_len - text.shape[1]), value=0)
+    return sd[prefix + '.embed.weight'][text]
+
+
+def transformer_with_pred_head(sd, cfg, x, cond, times, mask, text, drop_text_cond):  # :1250-1301
+    n = x.shape[1]
+    h = x @ sd['proj_in.weight'].t() + sd['proj_in.bias'] + cond @ sd['cond_proj_in.weight'].t() + sd['cond_proj_in.bias']
+    te = None
+    if text is not None and not drop_text_cond:
+        te = character_embed(sd, text, n)
+    emb = transformer_forward(sd, cfg, h, times=times, mask=mask, text_embed=te)
+    return emb @ sd['to_pred.weight'].t() + sd['to_pred.bias']
+
+
+def e2tts_forward(sd, cfg, mel, text, *, x0, times, span_mask, lens=None, drop_text_cond=False):
+    """E2TTS.forward :1468-1595 with the random draws (x0 :1519, times :1523, span mask :1504-1508)
+    injected. Returns dict(loss, cond, pred, pred_data)."""
+    b, n, _ = mel.shape
+    if lens is None:
+        lens = torch.full((b,), n, device=mel.device)
+    mask = lens_to_mask(lens, n)
+    span_mask = span_mask & mask
+    t = times[:, None, None]
+    w = (1.0 - t) * x0 + t * mel  # :1533
+    flow = mel - x0  # :1535
+    cond = torch.where(span_mask[..., None], torch.zeros_like(mel), mel)  # :1539-1543
+    pred = transformer_with_pred_head(sd, cfg, w, cond, times, mask, text, drop_text_cond)
+    loss = ((pred - flow) ** 2)[span_mask].mean()  # :1580-1582
+    return dict(loss=loss, cond=cond, pred=pred, pred_data=x0 + pred)
+
+
+def cfg_pred(sd, cfg, x, cond, times, mask, text, cfg_strength=1.0):  # :1303-1330
+    pred = transformer_with_pred_head(sd, cfg, x, cond, times, mask, text, False)
+    if cfg_strength < 1e-5:
+        return pred
+    null = transformer_with_pred_head(sd, cfg, x, cond, times, mask, text, True)
+    _, orth = project(pred - null, pred)
+    return pred + orth * cfg_strength
+
+
+@torch.no_grad()
+def e2tts_sample(sd, cfg, cond, text, *, duration, y0, steps=32, cfg_strength=1.0, lens=None, max_duration=4096):
+    """E2TTS.sample :1332-1431 (return_raw_output path) with y0 (:1418) injected and an int/tensor
+    duration. Midpoint on the grid linspace(0,1,steps) (A.7)."""
+    b, cn, _ = cond.shape
+    dev = cond.device
+    if lens is None:
+        lens = torch.full((b,), cn, device=dev, dtype=torch.long)
+    if text is not None:
+        lens = torch.maximum((text != -1).sum(-1), lens)  # :1372-1373
+    cond_mask = lens_to_mask(lens, int(lens.amax()))  # :1377
+    if isinstance(duration, int):
+        duration = torch.full((b,), duration, device=dev, dtype=torch.long)
+    duration = torch.maximum(lens + 1, duration).clamp(max=max_duration)  # :1386-1387
+    md = int(duration.amax())
+    cond = F.pad(cond, (0, 0, 0, md - cn))
+    cond_mask = F.pad(cond_mask, (0, md - cond_mask.shape[-1]), value=False)[..., None]
+    mask = lens_to_mask(duration, md)
+    step_cond = torch.where(cond_mask, cond, torch.zeros_like(cond))  # :1404
+    fn = lambda tt, y: cfg_pred(sd, cfg, y, step_cond, tt, mask, text, cfg_strength)
+    ts = torch.linspace(0, 1, steps, device=dev)
+    y = y0
+    for i in range(steps - 1):
+        t0, dt = ts[i], ts[i + 1] - ts[i]
+        half = 0.5 * dt
+        ymid = y + fn(t0, y) * half
+        y = y + dt * fn(t0 + half, ymid)
+    return torch.where(cond_mask, cond, y)  # :1426
+
+
+# --------------------------------------------------------------------------------------------------
+# DurationPredictor.forward (:1042-1113); state_dict prefix is that of the standalone module
+
+
+def duration_forward(sd, cfg, mel, text, *, lens=None, rand_frac=None, return_loss=True):
+    b, n, _ = mel.shape
+    x = mel @ sd['proj_in.weight'].t() + sd['proj_in.bias']  # :1057
+    te = character_embed(sd, text, n) if text is not None else None  # :1070
+    if lens is None:
+        lens = torch.full((b,), n, device=mel.device)
+    mask = lens_to_mask(lens, n)
+    if return_loss:  # :1081-1086
+        rand_index = (rand_frac * lens).long()
+        mask = mask & (torch.arange(n, device=mel.device)[None] < rand_index[:, None])
+    emb = transformer_forward(sd, cfg, x, mask=mask, text_embed=te)
+    num = (emb * mask[..., None]).sum(1)  # :212-224
+    den = mask.float().sum(1).clamp(min=1.0)
+    pooled = num / den[:, None]
+    pred = F.softplus(pooled @ sd['hl_gauss_layer.to_pred.0.weight'].t() + sd['hl_gauss_layer.to_pred.0.bias']).squeeze(-1)
+    if not return_loss:
+        return pred
+    return F.mse_loss(pred, lens.float())  # :1111
+
+
+# --------------------------------------------------------------------------------------------------
+# MelSpec (:248-290) = torchaudio MelSpectrogram(sr 24k, n_fft 1024, hann periodic, hop 256, center
+# reflect, power 1, HTK mel, norm None, f 0..sr/2) -> log(clamp(.,1e-5))
+
+
+def hz_to_mel_htk(f):
+    return 2595.0 * math.log10(1.0 + f / 700.0)
+
+
+def mel_filterbank(n_freqs=513, n_mels=100, sample_rate=24000, f_min=0.0, f_max=None):
+    f_max = f_max if f_max is not None else sample_rate / 2
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_pts = torch.linspace(hz_to_mel_htk(f_min), hz_to_mel_htk(f_max), n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts[None, :] - all_freqs[:, None]
+    down = -slopes[:, :-2] / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.clamp(torch.minimum(down, up), min=0.0)  # (n_freqs, n_mels)
+
+
+def melspec(wave, n_fft=1024, hop=256, n_mels=100, sample_rate=24000):
+    """wave (b, nw) -> (b, n_mels, 1 + nw // hop)"""
+    pad = n_fft // 2
+    x = F.pad(wave[:, None, :], (pad, pad), mode='reflect')[:, 0]
+    frames = x.unfold(-1, n_fft, hop)  # (b, frames, n_fft)
+    win = torch.hann_window(n_fft, periodic=True, dtype=wave.dtype, device=wave.device)
+    spec = torch.fft.rfft(frames * win, dim=-1).abs()  # power = 1
+    mel = spec @ mel_filterbank(n_fft // 2 + 1, n_mels, sample_rate).to(wave)
+    return mel.clamp(min=1e-5).log().transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------------------
+# utilities shared by tests / golden generation
+
+
+def cfg_from_kwargs(**kw):
+    return TransformerCfg(**kw)
+
+
+def randomize_zero_init(sd, seed=1234, scale=0.05):
+    """The reference zero-initialises many matrices (AdaLN/adaptive-norm gammas, cross-condition,
+    hyper-connection dynamic fns: e2_tts.py:343,495,501, A.1, A.5) which would make parity tests
+    vacuous. This perturbs every all-zero float tensor (and the constant gate biases) in place,
+    deterministically, and returns sd."""
+    g = torch.Generator().manual_seed(seed)
+    for k in sorted(sd.keys()):
+        v = sd[k]
+        if not v.is_floating_point() or v.numel() == 0:
+            continue
+        if float(v.abs().max()) == 0.0:
+            v.copy_(torch.randn(v.shape, generator=g) * scale)
+        elif k.endswith('to_v_head_gate.bias'):
+            v.copy_(torch.randn(v.shape, generator=g) * 1.0)
+        elif k.endswith('to_v_head_gate.weight') or k.endswith('norm.gamma'):
+            v.copy_(torch.randn(v.shape, generator=g) * scale)
+        elif k.endswith('dynamic_alpha_scale') or k.endswith('dynamic_beta_scale'):
+            v.fill_(0.5)
+    return sd

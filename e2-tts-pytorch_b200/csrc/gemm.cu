@@ -1,0 +1,427 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a — the tensor-core core of the E2-TTS hot path.
+//
+//   D[M,N] = epilogue( sum_k A[m,k] * B[n,k] ),  bf16 operands, fp32 accumulation in tensor memory.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0 lane 0 : TMA producer   — cp.async.bulk.tensor 2-D tiles (128B swizzle) into a kStages smem ring
+//   warp 1 lane 0 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction,
+//                                    accumulators double-buffered in TMEM (2 x BN columns)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue       — tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused
+//                                    bias / AdaLN gate / row mask / residual / GEGLU(+dropout), 16-byte stores
+// Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile loop.
+// Operands may be K-major or MN-major (transposed storage) so that the backward contractions
+// dX = dY*W and dW = dY^T*X read activations exactly as they lie in HBM — no transposes are materialised.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 bf16 = one 128-byte swizzle atom
+constexpr int kGemmThreads = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmParams {
+    int M, N, K;
+    int tiles_m, tiles_n, num_work;
+    int kb_total, kb_per_split, kb_a1;  // k-blocks; kb_a1 = number of k-blocks served by the first A source
+    void* D; long long ldd; int d_fp32;
+    void* D2; long long ldd2;
+    const float* bias;
+    const float* colscale; int rows_per_batch;
+    const unsigned char* rowmask;
+    const void* resid; long long ldr;
+    int geglu; float dropout_p; unsigned long long seed;
+    int atomic_out;
+};
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int kStages = (BN == 128) ? 6 : 4;
+    static constexpr int TILE_BYTES = kStages * STAGE_BYTES;
+    static constexpr int BAR_BYTES = (2 * kStages + 4) * 8 + 16;
+    static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + 1024;  // + slack for manual 1024B alignment
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using S = GemmSmem<BN>;
+    constexpr int kStages = S::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + kStages * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA2);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+                const int tm = w % p.tiles_m;
+                const int rest = w / p.tiles_m;
+                const int tn = rest % p.tiles_n;
+                const int sp = rest / p.tiles_n;
+                const int kb0 = sp * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    uint8_t* a_dst = smA + stage * A_STAGE_BYTES;
+                    uint8_t* b_dst = smB + stage * S::B_STAGE_BYTES;
+                    if constexpr (!A_MN) {
+                        if (kb < p.kb_a1) tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, tm * BM);
+                        else tma_load_2d(a_dst, &tmA2, &full_bar[stage], (kb - p.kb_a1) * BK, tm * BM);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_2d(a_dst + i * (BK * 128), &tmA, &full_bar[stage], tm * BM + i * 64, kb * BK);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, tn * BN);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_2d(b_dst + i * (BK * 128), &tmB, &full_bar[stage], tn * BN + i * 64, kb * BK);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            // K-major: 8-row groups 1024 B apart, one swizzle atom along K; MN-major: 64-element MN atoms
+            // BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
+            constexpr uint32_t a_lbo = A_MN ? BK * 128 : 0, b_lbo = B_MN ? BK * 128 : 0;
+            constexpr uint32_t a_adv = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;  // per UMMA_K=16 step, in 16-B units
+            constexpr uint32_t b_adv = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
+                const int sp = (w / p.tiles_m) / p.tiles_n;
+                const int kb0 = sp * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(smA + stage * A_STAGE_BYTES), a_lbo, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smB + stage * S::B_STAGE_BYTES), b_lbo, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16(tmem_d, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                                 (kb > kb0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);            // smem slot is free once these MMAs retire
+                    if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue (warps 4..7)
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int iter = 0;
+        for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
+            const int tm = w % p.tiles_m;
+            const int tn = (w / p.tiles_m) % p.tiles_n;
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const int row = tm * BM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+            const bool masked = p.rowmask && row_ok && (p.rowmask[row] == 0);
+            const float* cs = (p.colscale && row_ok) ? p.colscale + (long long)(row / p.rows_per_batch) * p.N : nullptr;
+
+            if (!p.geglu) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated tail of the previous chunk
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    const int col0 = tn * BN + c * 32;
+                    if (!row_ok || col0 >= p.N) continue;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    const int nvalid = min(32, p.N - col0);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + col0 + j);
+                    }
+                    if (cs) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] *= __ldg(cs + col0 + j);
+                    }
+                    if (masked) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+                    if (p.resid) {
+                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + (long long)row * p.ldr + col0;
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const uint4 u = *reinterpret_cast<const uint4*>(rp + g * 8);
+                                v[g * 8 + 0] += bf16_lo(u.x); v[g * 8 + 1] += bf16_hi(u.x);
+                                v[g * 8 + 2] += bf16_lo(u.y); v[g * 8 + 3] += bf16_hi(u.y);
+                                v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
+                                v[g * 8 + 6] += bf16_lo(u.w); v[g * 8 + 7] += bf16_hi(u.w);
+                            }
+                        } else {
+                            for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                    if (p.d_fp32) {
+                        float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
+                        if (p.atomic_out) {
+                            for (int j = 0; j < nvalid; ++j) atomicAdd(dp + j, v[j]);
+                        } else if (nvalid == 32 && (p.ldd & 3) == 0) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                *reinterpret_cast<float4*>(dp + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        } else {
+                            for (int j = 0; j < nvalid; ++j) dp[j] = v[j];
+                        }
+                    } else {
+                        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + col0;
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                *reinterpret_cast<uint4*>(dp + g * 8) =
+                                    make_uint4(pack_bf16(v[g * 8], v[g * 8 + 1]), pack_bf16(v[g * 8 + 2], v[g * 8 + 3]),
+                                               pack_bf16(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16(v[g * 8 + 6], v[g * 8 + 7]));
+                        } else {
+                            for (int j = 0; j < nvalid; ++j) dp[j] = __float2bfloat16(v[j]);
+                        }
+                    }
+                }
+            } else {
+                // GEGLU: tile columns [0,64) = u, [64,128) = gate of the same 64 hidden units (BN == 128 only)
+                const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t ru[32], rg[32];
+                    __syncwarp();
+                    tmem_ld32(taddr + c * 32, ru);
+                    tmem_ld32(taddr + 64 + c * 32, rg);
+                    tmem_ld_wait();
+                    const int colp = tn * BN + c * 32;         // packed column of u
+                    if (!row_ok || colp >= p.N) continue;
+                    const int hcol0 = tn * 64 + c * 32;        // hidden-unit column
+                    float u[32], g[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        u[j] = __uint_as_float(ru[j]) + (p.bias ? __ldg(p.bias + colp + j) : 0.f);
+                        g[j] = __uint_as_float(rg[j]) + (p.bias ? __ldg(p.bias + colp + 64 + j) : 0.f);
+                    }
+                    if (p.D2) {
+                        __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + (long long)row * p.ldd2 + colp;
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) {
+                            *reinterpret_cast<uint4*>(d2 + gq * 8) =
+                                make_uint4(pack_bf16(u[gq * 8], u[gq * 8 + 1]), pack_bf16(u[gq * 8 + 2], u[gq * 8 + 3]),
+                                           pack_bf16(u[gq * 8 + 4], u[gq * 8 + 5]), pack_bf16(u[gq * 8 + 6], u[gq * 8 + 7]));
+                            *reinterpret_cast<uint4*>(d2 + 64 + gq * 8) =
+                                make_uint4(pack_bf16(g[gq * 8], g[gq * 8 + 1]), pack_bf16(g[gq * 8 + 2], g[gq * 8 + 3]),
+                                           pack_bf16(g[gq * 8 + 4], g[gq * 8 + 5]), pack_bf16(g[gq * 8 + 6], g[gq * 8 + 7]));
+                        }
+                    }
+                    float h[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        // the backward pass recomputes from the bf16-rounded pre-activations: use them here too
+                        const float ub = __bfloat162float(__float2bfloat16(u[j]));
+                        const float gb = __bfloat162float(__float2bfloat16(g[j]));
+                        h[j] = ub * gelu_erf(gb);
+                    }
+                    if (p.dropout_p > 0.f) {
+                        const unsigned long long base = (unsigned long long)row * (unsigned long long)(p.N / 2) + hcol0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) h[j] = dropout_keep(p.seed, base + j, p.dropout_p) ? h[j] * keep_scale : 0.f;
+                    }
+                    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + hcol0;
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq)
+                        *reinterpret_cast<uint4*>(dp + gq * 8) =
+                            make_uint4(pack_bf16(h[gq * 8], h[gq * 8 + 1]), pack_bf16(h[gq * 8 + 2], h[gq * 8 + 3]),
+                                       pack_bf16(h[gq * 8 + 4], h[gq * 8 + 5]), pack_bf16(h[gq * 8 + 6], h[gq * 8 + 7]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements; box = 64 x box_outer, 128B swizzle.
+static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+    PFN_encodeTiled enc = get_encode_fn();
+    B200_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
+    B200_REQUIRE((ld % 8) == 0, "gemm: row pitch %lld not a multiple of 8 elements", (long long)ld);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm: operand not 16-byte aligned");
+    cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const GemmParams& p, cudaStream_t st) {
+    using S = GemmSmem<BN>;
+    auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+    static bool configured = false;  // idempotent attribute; racing first calls set the same value
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        B200_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int grid = p.num_work < num_sms() ? p.num_work : num_sms();
+    kern<<<grid, kGemmThreads, S::TOTAL, st>>>(tA, tA2, tB, p);
+    return check_launch("gemm_tcgen05_kernel");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B200_REQUIRE(a && a->A && a->B && a->D, "gemm: null operand");
+    B200_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem %lldx%lldx%lld", (long long)a->M, (long long)a->N, (long long)a->K);
+    B200_REQUIRE(a->M < (1ll << 31) && a->N < (1ll << 31) && a->K < (1ll << 31), "gemm: dimension too large");
+    const bool a_mn = a->a_mn_major != 0, b_mn = a->b_mn_major != 0;
+    GemmParams p{};
+    p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
+    const int BN = 128;
+    p.tiles_m = (p.M + BM - 1) / BM;
+    p.tiles_n = (p.N + BN - 1) / BN;
+    p.kb_total = (p.K + BK - 1) / BK;
+    p.kb_a1 = p.kb_total;
+    if (a->A2) {
+        B200_REQUIRE(!a_mn, "gemm: two-source A requires K-major A");
+        B200_REQUIRE(a->K1 > 0 && a->K1 < a->K && (a->K1 % BK) == 0, "gemm: K1=%lld must be a multiple of %d inside (0,K)", (long long)a->K1, BK);
+        p.kb_a1 = (int)(a->K1 / BK);
+    }
+    int split = a->split_k > 1 ? a->split_k : 1;
+    if (split > p.kb_total) split = p.kb_total;
+    p.kb_per_split = (p.kb_total + split - 1) / split;
+    split = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.num_work = p.tiles_m * p.tiles_n * split;
+    p.atomic_out = split > 1;
+    p.D = a->D; p.ldd = a->ldd; p.d_fp32 = a->d_fp32;
+    p.D2 = a->D2; p.ldd2 = a->ldd2;
+    p.bias = a->bias; p.colscale = a->colscale; p.rows_per_batch = (int)(a->rows_per_batch > 0 ? a->rows_per_batch : 1);
+    p.rowmask = a->rowmask; p.resid = a->resid; p.ldr = a->ldr;
+    p.geglu = a->geglu; p.dropout_p = a->dropout_p; p.seed = a->seed;
+    if (p.atomic_out) {
+        B200_REQUIRE(a->d_fp32, "gemm: split-K requires an fp32 output");
+        B200_REQUIRE(!a->bias && !a->colscale && !a->rowmask && !a->resid && !a->geglu, "gemm: split-K supports no epilogue");
+        cudaError_t e = cudaMemset2DAsync(a->D, (size_t)a->ldd * 4, 0, (size_t)a->N * 4, (size_t)a->M, st);
+        B200_REQUIRE(e == cudaSuccess, "gemm: memset: %s", cudaGetErrorString(e));
+    }
+    if (a->geglu) {
+        B200_REQUIRE((a->N % 128) == 0 && !a->d_fp32 && !a->colscale && !a->rowmask && !a->resid, "gemm: GEGLU needs N %% 128 == 0, bf16 out, no other epilogue");
+        B200_REQUIRE((a->ldd % 8) == 0 && (!a->D2 || (a->ldd2 % 8) == 0), "gemm: GEGLU output pitch must be a multiple of 8");
+    }
+    if (!a->d_fp32) B200_REQUIRE((a->ldd % 8) == 0, "gemm: bf16 output pitch must be a multiple of 8");
+    if (a->resid) B200_REQUIRE((a->ldr % 8) == 0, "gemm: residual pitch must be a multiple of 8");
+
+    CUtensorMap tA, tA2, tB;
+    int rc;
+    const int64_t KA = a->A2 ? a->K1 : a->K;
+    if (!a_mn) rc = make_map(&tA, a->A, KA, a->M, a->lda, BM);
+    else rc = make_map(&tA, a->A, a->M, a->K, a->lda, BK);
+    if (rc) return rc;
+    if (a->A2) {
+        rc = make_map(&tA2, a->A2, a->K - a->K1, a->M, a->lda2, BM);
+        if (rc) return rc;
+    } else {
+        tA2 = tA;
+    }
+    if (!b_mn) rc = make_map(&tB, a->B, a->K, a->N, a->ldb, BN);
+    else rc = make_map(&tB, a->B, a->N, a->K, a->ldb, BK);
+    if (rc) return rc;
+
+    if (!a_mn && !b_mn) return launch_gemm<128, false, false>(tA, tA2, tB, p, st);
+    if (!a_mn && b_mn) return launch_gemm<128, false, true>(tA, tA2, tB, p, st);
+    if (a_mn && !b_mn) return launch_gemm<128, true, false>(tA, tA2, tB, p, st);
+    return launch_gemm<128, true, true>(tA, tA2, tB, p, st);
+}

@@ -1,0 +1,721 @@
+// HBM-bound fused kernels around the GEMM/attention core of the E2-TTS block: weight packing, the
+// flow-matching stem (noise interpolation + cond masking), residual-stream assembly (abs-pos, registers,
+// stream expand), rotary + value-residual + head-gate post-processing of the QKV projection, GEGLU backward,
+// bias column sums, the final stream-reduce + RMSNorm, and the masked-MSE flow loss.
+// All loads/stores are 16-byte vectorised and coalesced along the feature dimension.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// One launch casts/permutes every fp32 nn.Parameter that feeds a tensor-core GEMM into its packed bf16 slot.
+__device__ __forceinline__ int pack_row(const b200_pack_desc& d, int r) {
+    if (d.mode != 1) return r;  // mode 1 = GEGLU interleave: [u(inner) ; gate(inner)] -> per 64 hidden units [u(64) | gate(64)]
+    const int inner = d.rows >> 1;
+    return r < inner ? (r >> 6) * 128 + (r & 63) : ((r - inner) >> 6) * 128 + 64 + ((r - inner) & 63);
+}
+__global__ void __launch_bounds__(256) pack_weights_kernel(const b200_pack_desc* descs) {
+    const b200_pack_desc d = descs[blockIdx.y];
+    if ((d.cols & 3) || (d.col_off & 3) || (d.ld_dst & 3)) {  // scalar path (1-D biases, odd widths)
+        const long long total = (long long)d.rows * d.cols;
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+            const int r = (int)(i / d.cols), c = (int)(i % d.cols);
+            const float v = d.src[i];
+            const size_t off = (size_t)(d.row_off + pack_row(d, r)) * d.ld_dst + d.col_off + c;
+            if (d.out_fp32) reinterpret_cast<float*>(d.dst)[off] = v;
+            else reinterpret_cast<__nv_bfloat16*>(d.dst)[off] = __float2bfloat16(v);
+        }
+        return;
+    }
+    const long long total4 = ((long long)d.rows * d.cols) >> 2;
+    const int c4 = d.cols >> 2;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total4; i += (long long)gridDim.x * 256) {
+        const int r = (int)(i / c4), c = (int)(i % c4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(d.src + (size_t)r * d.cols + c);
+        const size_t off = (size_t)(d.row_off + pack_row(d, r)) * d.ld_dst + d.col_off + c;
+        if (d.out_fp32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.dst) + off) = v;
+        else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.dst) + off) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stem
+// A[row, 0:C] = w = (1-t) x0 + t x1 (or x given), A[row, Cp:Cp+C] = cond = span ? 0 : x1 (or cond given); pads are zero.
+struct StemP {
+    const float *x1, *x0, *times, *xin, *condin;
+    const unsigned char* span;
+    __nv_bfloat16* A;
+    float* cond_out;
+    int B, N, C, Cp;
+};
+__global__ void __launch_bounds__(256) stem_prepare_kernel(const StemP p) {
+    const long long total = (long long)p.B * p.N * p.Cp * 2;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int col = (int)(i % (2 * p.Cp));
+        const long long row = i / (2 * p.Cp);
+        const int half = col / p.Cp, c = col % p.Cp;
+        float v = 0.f;
+        if (c < p.C) {
+            const size_t src = (size_t)row * p.C + c;
+            if (p.xin) {
+                v = half == 0 ? p.xin[src] : p.condin[src];
+            } else {
+                const float a = p.x1[src];
+                if (half == 0) {
+                    const float t = p.times[row / p.N];
+                    v = (1.f - t) * p.x0[src] + t * a;
+                } else {
+                    v = p.span[row] ? 0.f : a;
+                    if (p.cond_out) p.cond_out[src] = v;
+                }
+            }
+        }
+        p.A[i] = __float2bfloat16(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ assemble
+struct AsmP {
+    const __nv_bfloat16* h;      // [B*N, D] or null
+    const int* ids;              // [B, N] or null (embedding gather, fp32 table)
+    const float *emb, *abs_pos, *registers;
+    __nv_bfloat16* out;          // [B, R+N, S, D]
+    int B, N, R, D, S;
+    const __nv_bfloat16* d_out;
+    __nv_bfloat16* d_h;
+    float *d_tok, *d_abs_pos, *d_registers;
+};
+__global__ void __launch_bounds__(256) assemble_fwd_kernel(const AsmP p) {
+    const int nchunk = p.D >> 3;
+    const long long total = (long long)p.B * (p.R + p.N) * nchunk;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i % nchunk);
+        const long long tok = i / nchunk;
+        const int n = (int)(tok % (p.R + p.N));
+        const int b = (int)(tok / (p.R + p.N));
+        float v[8];
+        if (n < p.R) {
+            const float4 a = *reinterpret_cast<const float4*>(p.registers + (size_t)n * p.D + c * 8);
+            const float4 bq = *reinterpret_cast<const float4*>(p.registers + (size_t)n * p.D + c * 8 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+        } else {
+            const int nn = n - p.R;
+            if (p.h) {
+                unpack8(*reinterpret_cast<const uint4*>(p.h + ((size_t)b * p.N + nn) * p.D + c * 8), v);
+            } else {
+                const int id = p.ids[(size_t)b * p.N + nn];
+                const float* e = p.emb + (size_t)id * p.D + c * 8;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = e[k];
+            }
+            if (p.abs_pos) {
+                const float* a = p.abs_pos + (size_t)nn * p.D + c * 8;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += a[k];
+            }
+        }
+        const uint4 u = pack8(v);
+        for (int s = 0; s < p.S; ++s) *reinterpret_cast<uint4*>(p.out + ((size_t)tok * p.S + s) * p.D + c * 8) = u;
+    }
+}
+// thread per (position, chunk): loops over batch; sums the S stream gradients
+__global__ void __launch_bounds__(256) assemble_bwd_kernel(const AsmP p) {
+    const int nchunk = p.D >> 3;
+    const long long total = (long long)(p.R + p.N) * nchunk;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % nchunk), n = (int)(i / nchunk);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < p.B; ++b) {
+        float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const size_t tok = (size_t)b * (p.R + p.N) + n;
+        for (int s = 0; s < p.S; ++s) {
+            float v[8];
+            unpack8(*reinterpret_cast<const uint4*>(p.d_out + (tok * p.S + s) * p.D + c * 8), v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum[k] += v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += sum[k];
+        if (n >= p.R) {
+            const size_t row = (size_t)b * p.N + (n - p.R);
+            if (p.d_h) *reinterpret_cast<uint4*>(p.d_h + row * p.D + c * 8) = pack8(sum);
+            if (p.d_tok) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p.d_tok[row * p.D + c * 8 + k] = sum[k];
+            }
+        }
+    }
+    float* dst = n < p.R ? (p.d_registers ? p.d_registers + (size_t)n * p.D + c * 8 : nullptr)
+                         : (p.d_abs_pos ? p.d_abs_pos + (size_t)(n - p.R) * p.D + c * 8 : nullptr);
+    if (dst) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[k] = acc[k];
+    }
+}
+// embedding gradient: one block per vocabulary row, deterministic (no atomics on the hot filler id 0)
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* d_tok, const int* ids, float* d_emb, int ntok, int D) {
+    const int v = blockIdx.x;
+    for (int c = threadIdx.x; c < D; c += 256) {
+        float acc = 0.f;
+        for (int t = 0; t < ntok; ++t)
+            if (ids[t] == v) acc += d_tok[(size_t)t * D + c];
+        d_emb[(size_t)v * D + c] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ rotary table
+__global__ void rotary_table_kernel(float* cs, float* sn, int Np, int half) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np * half) return;
+    const int n = i / half, j = i % half;
+    const float inv = powf(10000.f, -(float)(2 * j) / (float)(2 * half));
+    float s, c;
+    sincosf((float)n * inv, &s, &c);
+    cs[i] = c; sn[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ qkv post
+// qkvg [T, ld] = [q(I) | k(I) | v(I) | gate(h) | mix(h)] (raw GEMM output). Produces rotated q,k and the
+// value-residual-mixed v in [B,H,Np,64] (A.3, A.4 steps 1-3), plus sigmoid(head gate) [T,H] fp32.
+struct QkvP {
+    const __nv_bfloat16* qkvg; int ld;
+    const float *gate_b, *mix_b, *cs, *sn;
+    const __nv_bfloat16* v_first;
+    __nv_bfloat16 *q, *k, *v;
+    float* gate;
+    int B, H, Np;
+    // backward
+    const __nv_bfloat16 *dq, *dk, *dv;
+    const float* d_gate;
+    __nv_bfloat16 *d_qkvg, *d_vfirst;
+};
+__global__ void __launch_bounds__(256) qkv_post_fwd_kernel(const QkvP p) {
+    const long long total = (long long)p.B * p.Np * p.H * 8;
+    const int I = p.H * 64;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i & 7);
+        const int hh = (int)((i >> 3) % p.H);
+        const long long tok = (i >> 3) / p.H;
+        const int n = (int)(tok % p.Np), b = (int)(tok / p.Np);
+        const __nv_bfloat16* row = p.qkvg + (size_t)tok * p.ld;
+        const size_t dst = (((size_t)b * p.H + hh) * p.Np + n) * 64 + c * 8;
+        float cs[4], sn[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cs[j] = p.cs[n * 32 + c * 4 + j]; sn[j] = p.sn[n * 32 + c * 4 + j]; }
+        float x[8], y[8];
+        unpack8(*reinterpret_cast<const uint4*>(row + hh * 64 + c * 8), x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { y[2 * j] = x[2 * j] * cs[j] - x[2 * j + 1] * sn[j]; y[2 * j + 1] = x[2 * j + 1] * cs[j] + x[2 * j] * sn[j]; }
+        *reinterpret_cast<uint4*>(p.q + dst) = pack8(y);
+        unpack8(*reinterpret_cast<const uint4*>(row + I + hh * 64 + c * 8), x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { y[2 * j] = x[2 * j] * cs[j] - x[2 * j + 1] * sn[j]; y[2 * j + 1] = x[2 * j + 1] * cs[j] + x[2 * j] * sn[j]; }
+        *reinterpret_cast<uint4*>(p.k + dst) = pack8(y);
+        unpack8(*reinterpret_cast<const uint4*>(row + 2 * I + hh * 64 + c * 8), x);
+        if (p.v_first) {
+            const float mix = sigmoidf_(__bfloat162float(row[3 * I + p.H + hh]) + p.mix_b[hh]);
+            float vf[8];
+            unpack8(*reinterpret_cast<const uint4*>(p.v_first + dst), vf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = x[j] * mix + vf[j] * (1.f - mix);
+        }
+        *reinterpret_cast<uint4*>(p.v + dst) = pack8(x);
+        if (c == 0) p.gate[(size_t)tok * p.H + hh] = sigmoidf_(__bfloat162float(row[3 * I + hh]) + p.gate_b[hh]);
+    }
+}
+__global__ void __launch_bounds__(256) qkv_post_bwd_kernel(const QkvP p) {
+    const long long total = (long long)p.B * p.Np * p.H * 8;
+    const int I = p.H * 64;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const bool ok = i < total;
+    float dmix = 0.f, mix = 0.f;
+    int c = 0, hh = 0;
+    long long tok = 0;
+    if (ok) {
+        c = (int)(i & 7);
+        hh = (int)((i >> 3) % p.H);
+        tok = (i >> 3) / p.H;
+        const int n = (int)(tok % p.Np), b = (int)(tok / p.Np);
+        const __nv_bfloat16* row = p.qkvg + (size_t)tok * p.ld;
+        __nv_bfloat16* drow = p.d_qkvg + (size_t)tok * p.ld;
+        const size_t src = (((size_t)b * p.H + hh) * p.Np + n) * 64 + c * 8;
+        float cs[4], sn[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cs[j] = p.cs[n * 32 + c * 4 + j]; sn[j] = p.sn[n * 32 + c * 4 + j]; }
+        float x[8], y[8];
+        unpack8(*reinterpret_cast<const uint4*>(p.dq + src), x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { y[2 * j] = x[2 * j] * cs[j] + x[2 * j + 1] * sn[j]; y[2 * j + 1] = x[2 * j + 1] * cs[j] - x[2 * j] * sn[j]; }
+        *reinterpret_cast<uint4*>(drow + hh * 64 + c * 8) = pack8(y);
+        unpack8(*reinterpret_cast<const uint4*>(p.dk + src), x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { y[2 * j] = x[2 * j] * cs[j] + x[2 * j + 1] * sn[j]; y[2 * j + 1] = x[2 * j + 1] * cs[j] - x[2 * j] * sn[j]; }
+        *reinterpret_cast<uint4*>(drow + I + hh * 64 + c * 8) = pack8(y);
+        unpack8(*reinterpret_cast<const uint4*>(p.dv + src), x);
+        if (p.v_first) {
+            mix = sigmoidf_(__bfloat162float(row[3 * I + p.H + hh]) + p.mix_b[hh]);
+            float vr[8], vf[8], o[8];
+            unpack8(*reinterpret_cast<const uint4*>(row + 2 * I + hh * 64 + c * 8), vr);
+            unpack8(*reinterpret_cast<const uint4*>(p.v_first + src), vf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { dmix += x[j] * (vr[j] - vf[j]); o[j] = x[j] * (1.f - mix); x[j] *= mix; }
+            *reinterpret_cast<uint4*>(p.d_vfirst + src) = pack8(o);
+        }
+        *reinterpret_cast<uint4*>(drow + 2 * I + hh * 64 + c * 8) = pack8(x);
+    }
+    dmix += __shfl_xor_sync(0xffffffffu, dmix, 1);
+    dmix += __shfl_xor_sync(0xffffffffu, dmix, 2);
+    dmix += __shfl_xor_sync(0xffffffffu, dmix, 4);
+    if (ok && c == 0) {
+        __nv_bfloat16* drow = p.d_qkvg + (size_t)tok * p.ld;
+        const float g = p.gate[(size_t)tok * p.H + hh];
+        drow[3 * I + hh] = __float2bfloat16(p.d_gate[(size_t)tok * p.H + hh] * g * (1.f - g));
+        if (p.v_first) drow[3 * I + p.H + hh] = __float2bfloat16(dmix * mix * (1.f - mix));
+        // zero the pad columns (ld may exceed 3I + 2H) so that dW / colsum of the packed matrix stay clean
+        if (hh == 0) {
+            const int used = 3 * I + (p.v_first ? 2 : 1) * p.H;
+            for (int j = used; j < p.ld; ++j) drow[j] = __float2bfloat16(0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GEGLU backward
+// ug packed [T, 2*inner] ([u(64)|gate(64)] per 128 columns), dh [T, inner] -> dug packed
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh, const __nv_bfloat16* ug, __nv_bfloat16* dug, long long T,
+                                                         int inner, float dropout_p, unsigned long long seed) {
+    const int nchunk = inner >> 3;
+    const long long total = T * nchunk;
+    const float ks = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i % nchunk);
+        const long long row = i / nchunk;
+        const int hcol = c * 8;
+        const size_t pu = (size_t)row * 2 * inner + (hcol >> 6) * 128 + (hcol & 63);
+        float d[8], u[8], g[8], du[8], dg[8];
+        unpack8(*reinterpret_cast<const uint4*>(dh + (size_t)row * inner + hcol), d);
+        unpack8(*reinterpret_cast<const uint4*>(ug + pu), u);
+        unpack8(*reinterpret_cast<const uint4*>(ug + pu + 64), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float dd = d[j];
+            if (dropout_p > 0.f) dd = dropout_keep(seed, (unsigned long long)row * inner + hcol + j, dropout_p) ? dd * ks : 0.f;
+            const float cdf = 0.5f * (1.f + erff(g[j] * 0.70710678118654752440f));
+            const float pdf = 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
+            du[j] = dd * g[j] * cdf;
+            dg[j] = dd * u[j] * (cdf + g[j] * pdf);
+        }
+        *reinterpret_cast<uint4*>(dug + pu) = pack8(du);
+        *reinterpret_cast<uint4*>(dug + pu + 64) = pack8(dg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums (bias grads)
+// out[n] += sum_t X[t, n]  (X bf16 [T, ld]); out must be zeroed by the caller
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* X, long long T, int ncols, int ld, float* out, int rows_per_block) {
+    __shared__ float red[8][32 * 8 + 1];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int col0 = (blockIdx.x * 32 + cg) * 8;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(T, r0 + rows_per_block);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (col0 < ncols) {
+        for (long long r = r0 + rl; r < r1; r += 8) {
+            float v[8];
+            if (col0 + 8 <= ncols) {
+                unpack8(*reinterpret_cast<const uint4*>(X + (size_t)r * ld + col0), v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = col0 + j < ncols ? __bfloat162float(X[(size_t)r * ld + col0 + j]) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+    __syncthreads();
+    const int t = threadIdx.x;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][t];
+    const int col = blockIdx.x * 256 + t;
+    if (col < ncols) atomicAdd(out + col, s);
+}
+
+// ------------------------------------------------------------------------------------------------ final norm (head)
+// y[b*N+n, :] = RMSNorm_g( sum_s x[b, R+n, s, :] )   (e2_tts.py:943-952); one warp per token
+struct FnP {
+    const __nv_bfloat16* xres; const float* g; __nv_bfloat16* y;
+    int B, N, R, D, S;
+    const __nv_bfloat16* dy; __nv_bfloat16* d_xres; float* g_g;
+};
+template <int VPT>
+__global__ void __launch_bounds__(256) final_norm_fwd_kernel(const FnP p) {
+    const int lane = threadIdx.x & 31, nchunk = p.D >> 3;
+    const long long ntok = (long long)p.B * p.N;
+    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < ntok; row += (long long)gridDim.x * 8) {
+        const long long b = row / p.N, n = row % p.N;
+        const size_t tok = (size_t)b * (p.R + p.N) + p.R + n;
+        float x[VPT][8];
+        float ss = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const int c = lane + 32 * v;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[v][e] = 0.f;
+            if (c < nchunk) {
+                for (int s = 0; s < p.S; ++s) {
+                    float t[8];
+                    unpack8(*reinterpret_cast<const uint4*>(p.xres + (tok * p.S + s) * p.D + c * 8), t);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[v][e] += t[e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss += x[v][e] * x[v][e];
+        }
+        const float cn = sqrtf((float)p.D) / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const int c = lane + 32 * v;
+            if (c < nchunk) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = x[v][e] * cn * __ldg(p.g + c * 8 + e);
+                *reinterpret_cast<uint4*>(p.y + (size_t)row * p.D + c * 8) = pack8(o);
+            }
+        }
+    }
+}
+template <int VPT>
+__global__ void __launch_bounds__(256) final_norm_bwd_kernel(const FnP p) {
+    extern __shared__ float sg[];  // [D]
+    for (int i = threadIdx.x; i < p.D; i += 256) sg[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, nchunk = p.D >> 3;
+    const long long ntok = (long long)p.B * (p.R + p.N);
+    const float invD = 1.f / (float)p.D;
+    for (long long tokl = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tokl < ntok; tokl += (long long)gridDim.x * 8) {
+        const long long b = tokl / (p.R + p.N), n = tokl % (p.R + p.N);
+        const size_t tok = (size_t)tokl;
+        if (n < p.R) {  // register rows are dropped before the reduce: zero gradient
+            for (int c = lane; c < nchunk * p.S; c += 32) *reinterpret_cast<uint4*>(p.d_xres + tok * p.S * p.D + (size_t)c * 8) = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        const size_t row = (size_t)b * p.N + (n - p.R);
+        float x[VPT][8], dy[VPT][8];
+        float ss = 0.f, dot = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const int c = lane + 32 * v;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { x[v][e] = 0.f; dy[v][e] = 0.f; }
+            if (c < nchunk) {
+                for (int s = 0; s < p.S; ++s) {
+                    float t[8];
+                    unpack8(*reinterpret_cast<const uint4*>(p.xres + (tok * p.S + s) * p.D + c * 8), t);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[v][e] += t[e];
+                }
+                unpack8(*reinterpret_cast<const uint4*>(p.dy + row * p.D + c * 8), dy[v]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dot += __ldg(p.g + c * 8 + e) * dy[v][e] * x[v][e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss += x[v][e] * x[v][e];
+        }
+        const float cn = sqrtf((float)p.D) / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+        dot = warp_sum(dot);
+        const float k2 = cn * cn * cn * invD * dot;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const int c = lane + 32 * v;
+            if (c < nchunk) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    atomicAdd(&sg[c * 8 + e], dy[v][e] * x[v][e] * cn);
+                    o[e] = cn * __ldg(p.g + c * 8 + e) * dy[v][e] - x[v][e] * k2;
+                }
+                const uint4 u = pack8(o);
+                for (int s = 0; s < p.S; ++s) *reinterpret_cast<uint4*>(p.d_xres + (tok * p.S + s) * p.D + c * 8) = u;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.D; i += 256) atomicAdd(p.g_g + i, sg[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ masked MSE flow loss
+// sums[0] += sum_{span} (pred - (x1 - x0))^2, sums[1] += #span rows; pred_data = x0 + pred  (e2_tts.py:1580-1595)
+struct LossP {
+    const float *pred, *x1, *x0; const unsigned char* span; float* sums; float* pred_data;
+    long long rows; int C;
+    const float* dloss; __nv_bfloat16* dpred; int ldp;
+};
+__global__ void __launch_bounds__(256) flow_loss_fwd_kernel(const LossP p) {
+    float acc = 0.f, cnt = 0.f;
+    const long long total = p.rows * p.C;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long row = i / p.C;
+        const float pr = p.pred[i], a0 = p.x0[i];
+        if (p.pred_data) p.pred_data[i] = a0 + pr;
+        if (p.span[row]) {
+            const float d = pr - (p.x1[i] - a0);
+            acc += d * d;
+            if (i % p.C == 0) cnt += 1.f;
+        }
+    }
+    acc = warp_sum(acc); cnt = warp_sum(cnt);
+    __shared__ float sa[8], sc[8];
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = acc; sc[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, c = 0.f;
+        for (int k = 0; k < 8; ++k) { a += sa[k]; c += sc[k]; }
+        atomicAdd(p.sums, a);
+        atomicAdd(p.sums + 1, c);
+    }
+}
+__global__ void flow_loss_finalize_kernel(const float* sums, float* loss, int C) { *loss = sums[0] / (sums[1] * (float)C); }
+__global__ void __launch_bounds__(256) flow_loss_bwd_kernel(const LossP p) {
+    const float scale = 2.f * (*p.dloss) / (p.sums[1] * (float)p.C);
+    const long long total = p.rows * p.ldp;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long row = i / p.ldp;
+        const int c = (int)(i % p.ldp);
+        float v = 0.f;
+        if (c < p.C && p.span[row]) {
+            const size_t s = (size_t)row * p.C + c;
+            v = (p.pred[s] - (p.x1[s] - p.x0[s])) * scale;
+        }
+        p.dpred[i] = __float2bfloat16(v);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ gate / mask backward
+// Forward epilogue was y = mask * cs[b,:] * z. Given dy and y: dz = dy * mask * cs, d_cs[b,:] += sum_rows dy * y / cs.
+__global__ void __launch_bounds__(256) rowgate_bwd_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* y, const float* cs,
+                                                           const unsigned char* mask, __nv_bfloat16* dz, float* d_cs,
+                                                           int rows_per_batch, int D, int rows_per_block) {
+    extern __shared__ float sacc[];  // [D]
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows_per_batch, r0 + rows_per_block);
+    if (cs) {
+        for (int i = threadIdx.x; i < D; i += 256) sacc[i] = 0.f;
+        __syncthreads();
+    }
+    const int nchunk = D >> 3;
+    const int total = (r1 - r0) * nchunk;
+    for (int idx = threadIdx.x; idx < total; idx += 256) {
+        const int r = r0 + idx / nchunk, c = idx % nchunk;
+        const size_t row = (size_t)b * rows_per_batch + r;
+        float g[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + row * D + c * 8), g);
+        const bool keep = !mask || mask[row];
+        if (cs) {
+            float yv[8];
+            unpack8(*reinterpret_cast<const uint4*>(y + row * D + c * 8), yv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float s = __ldg(cs + (size_t)b * D + c * 8 + j);
+                o[j] = keep ? g[j] * s : 0.f;
+                if (keep) atomicAdd(&sacc[c * 8 + j], g[j] * yv[j] / s);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = keep ? g[j] : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dz + row * D + c * 8) = pack8(o);
+    }
+    if (cs) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < D; i += 256) atomicAdd(d_cs + (size_t)b * D + i, sacc[i]);
+    }
+}
+
+// fp32 -> bf16 cast with row pitch (used for small host-provided matrices)
+__global__ void cast_rows_kernel(const float* src, __nv_bfloat16* dst, long long rows, int cols, int ld) {
+    const long long total = rows * ld;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i % ld);
+        dst[i] = __float2bfloat16(c < cols ? src[(i / ld) * cols + c] : 0.f);
+    }
+}
+
+static inline int grid_for(long long total, int per_block = 256) {
+    long long g = (total + per_block - 1) / per_block;
+    const long long cap = (long long)num_sms() * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_pack_weights(const b200_pack_desc* descs_dev, int32_t n, b200_stream_t stream) {
+    B200_REQUIRE(descs_dev && n > 0, "pack_weights: empty table");
+    pack_weights_kernel<<<dim3(32, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(descs_dev);
+    return check_launch("pack_weights_kernel");
+}
+
+extern "C" int b200_stem_prepare(const b200_stem_args* a, b200_stream_t stream) {
+    B200_REQUIRE(a && a->A && ((a->x1 && a->x0 && a->times && a->span) || (a->x_in && a->cond_in)), "stem_prepare: null pointer");
+    B200_REQUIRE(a->C > 0 && a->Cp >= a->C && (a->Cp % 64) == 0, "stem_prepare: Cp must be a multiple of 64 >= C");
+    StemP p{a->x1, a->x0, a->times, a->x_in, a->cond_in, a->span, (__nv_bfloat16*)a->A, a->cond_out, a->B, a->N, a->C, a->Cp};
+    stem_prepare_kernel<<<grid_for((long long)a->B * a->N * a->Cp * 2), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("stem_prepare_kernel");
+}
+
+static int fill_asm(AsmP& p, const b200_assemble_args* a) {
+    B200_REQUIRE(a && (a->h || (a->ids && a->emb)) && a->registers, "assemble: null pointer");
+    B200_REQUIRE(a->D % 8 == 0 && a->S >= 1 && a->B > 0 && a->N > 0 && a->R >= 0, "assemble: unsupported shape");
+    p.h = (const __nv_bfloat16*)a->h; p.ids = a->ids; p.emb = a->emb; p.abs_pos = a->abs_pos; p.registers = a->registers;
+    p.B = a->B; p.N = a->N; p.R = a->R; p.D = a->D; p.S = a->S;
+    return 0;
+}
+extern "C" int b200_assemble_fwd(const b200_assemble_args* a, b200_stream_t stream) {
+    AsmP p{};
+    if (fill_asm(p, a)) return -1;
+    B200_REQUIRE(a->out, "assemble_fwd: null output");
+    p.out = (__nv_bfloat16*)a->out;
+    assemble_fwd_kernel<<<grid_for((long long)a->B * (a->R + a->N) * (a->D / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("assemble_fwd_kernel");
+}
+extern "C" int b200_assemble_bwd(const b200_assemble_args* a, b200_stream_t stream) {
+    AsmP p{};
+    if (fill_asm(p, a)) return -1;
+    B200_REQUIRE(a->d_out, "assemble_bwd: null d_out");
+    p.d_out = (const __nv_bfloat16*)a->d_out; p.d_h = (__nv_bfloat16*)a->d_h; p.d_tok = a->d_tok; p.d_abs_pos = a->d_abs_pos; p.d_registers = a->d_registers;
+    const long long total = (long long)(a->R + a->N) * (a->D / 8);
+    assemble_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("assemble_bwd_kernel");
+}
+extern "C" int b200_embed_bwd(const float* d_tok, const int32_t* ids, float* d_emb, int32_t ntok, int32_t D, int32_t vocab, b200_stream_t stream) {
+    B200_REQUIRE(d_tok && ids && d_emb && ntok > 0 && D > 0 && vocab > 0, "embed_bwd: bad arguments");
+    embed_bwd_kernel<<<vocab, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_tok, ids, d_emb, ntok, D);
+    return check_launch("embed_bwd_kernel");
+}
+extern "C" int b200_rotary_table(float* cos_out, float* sin_out, int32_t Np, int32_t dim_head, b200_stream_t stream) {
+    B200_REQUIRE(cos_out && sin_out && Np > 0 && dim_head == 64, "rotary_table: only dim_head 64 is built");
+    rotary_table_kernel<<<(Np * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cos_out, sin_out, Np, 32);
+    return check_launch("rotary_table_kernel");
+}
+
+static int fill_qkv(QkvP& p, const b200_qkv_post_args* a) {
+    B200_REQUIRE(a && a->qkvg && a->gate_bias && a->rot_cos && a->rot_sin && a->gate, "qkv_post: null pointer");
+    B200_REQUIRE(a->dim_head == 64, "qkv_post: only dim_head 64 is built");
+    B200_REQUIRE(a->ld % 8 == 0 && a->ld >= 3 * a->H * 64 + (a->v_first ? 2 : 1) * a->H, "qkv_post: bad row pitch %d", a->ld);
+    B200_REQUIRE(!a->v_first || a->mix_bias, "qkv_post: value residual needs the mix bias");
+    p.qkvg = (const __nv_bfloat16*)a->qkvg; p.ld = a->ld; p.gate_b = a->gate_bias; p.mix_b = a->mix_bias; p.cs = a->rot_cos; p.sn = a->rot_sin;
+    p.v_first = (const __nv_bfloat16*)a->v_first; p.gate = a->gate; p.B = a->B; p.H = a->H; p.Np = a->Np;
+    return 0;
+}
+extern "C" int b200_qkv_post_fwd(const b200_qkv_post_args* a, b200_stream_t stream) {
+    QkvP p{};
+    if (fill_qkv(p, a)) return -1;
+    B200_REQUIRE(a->q && a->k && a->v, "qkv_post_fwd: null output");
+    p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
+    qkv_post_fwd_kernel<<<grid_for((long long)a->B * a->Np * a->H * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("qkv_post_fwd_kernel");
+}
+extern "C" int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stream) {
+    QkvP p{};
+    if (fill_qkv(p, a)) return -1;
+    B200_REQUIRE(a->dq && a->dk && a->dv && a->d_gate && a->d_qkvg && (!a->v_first || a->d_vfirst), "qkv_post_bwd: null pointer");
+    p.dq = (const __nv_bfloat16*)a->dq; p.dk = (const __nv_bfloat16*)a->dk; p.dv = (const __nv_bfloat16*)a->dv; p.d_gate = a->d_gate;
+    p.d_qkvg = (__nv_bfloat16*)a->d_qkvg; p.d_vfirst = (__nv_bfloat16*)a->d_vfirst;
+    const long long total = (long long)a->B * a->Np * a->H * 8;
+    qkv_post_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("qkv_post_bwd_kernel");
+}
+
+extern "C" int b200_geglu_bwd(const void* dh, const void* ug, void* dug, int64_t T, int32_t inner, float dropout_p, uint64_t seed, b200_stream_t stream) {
+    B200_REQUIRE(dh && ug && dug && T > 0 && inner > 0 && (inner % 64) == 0, "geglu_bwd: inner must be a multiple of 64");
+    geglu_bwd_kernel<<<grid_for(T * (inner / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __nv_bfloat16*)dh, (const __nv_bfloat16*)ug, (__nv_bfloat16*)dug, T, inner, dropout_p, seed);
+    return check_launch("geglu_bwd_kernel");
+}
+
+extern "C" int b200_colsum(const void* X, int64_t T, int32_t ncols, int32_t ld, float* out, b200_stream_t stream) {
+    B200_REQUIRE(X && out && T > 0 && ncols > 0 && ld >= ncols && (ld % 8) == 0, "colsum: bad arguments");
+    const int rows_per_block = 512;
+    dim3 grid((ncols + 255) / 256, (unsigned)((T + rows_per_block - 1) / rows_per_block));
+    colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)X, T, ncols, ld, out, rows_per_block);
+    return check_launch("colsum_kernel");
+}
+
+extern "C" int b200_final_norm_fwd(const b200_final_norm_args* a, b200_stream_t stream) {
+    B200_REQUIRE(a && a->xres && a->g && a->y, "final_norm_fwd: null pointer");
+    B200_REQUIRE(a->D % 8 == 0 && a->D <= 1024 && a->S >= 1, "final_norm: D must be a multiple of 8 and <= 1024");
+    FnP p{(const __nv_bfloat16*)a->xres, a->g, (__nv_bfloat16*)a->y, a->B, a->N, a->R, a->D, a->S, nullptr, nullptr, nullptr};
+    const int grid = (int)min(((long long)a->B * a->N + 7) / 8, (long long)num_sms() * 8);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->D <= 256) final_norm_fwd_kernel<1><<<grid, 256, 0, st>>>(p);
+    else if (a->D <= 512) final_norm_fwd_kernel<2><<<grid, 256, 0, st>>>(p);
+    else final_norm_fwd_kernel<4><<<grid, 256, 0, st>>>(p);
+    return check_launch("final_norm_fwd_kernel");
+}
+extern "C" int b200_final_norm_bwd(const b200_final_norm_args* a, b200_stream_t stream) {
+    B200_REQUIRE(a && a->xres && a->g && a->dy && a->d_xres && a->g_g, "final_norm_bwd: null pointer");
+    B200_REQUIRE(a->D % 8 == 0 && a->D <= 1024 && a->S >= 1, "final_norm: D must be a multiple of 8 and <= 1024");
+    FnP p{(const __nv_bfloat16*)a->xres, a->g, nullptr, a->B, a->N, a->R, a->D, a->S, (const __nv_bfloat16*)a->dy, (__nv_bfloat16*)a->d_xres, a->g_g};
+    const int grid = (int)min(((long long)a->B * (a->N + a->R) + 7) / 8, (long long)num_sms() * 4);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)a->D * 4;
+    if (a->D <= 256) final_norm_bwd_kernel<1><<<grid, 256, smem, st>>>(p);
+    else if (a->D <= 512) final_norm_bwd_kernel<2><<<grid, 256, smem, st>>>(p);
+    else final_norm_bwd_kernel<4><<<grid, 256, smem, st>>>(p);
+    return check_launch("final_norm_bwd_kernel");
+}
+
+extern "C" int b200_flow_loss_fwd(const b200_flow_loss_args* a, b200_stream_t stream) {
+    B200_REQUIRE(a && a->pred && a->x1 && a->x0 && a->span && a->sums && a->loss, "flow_loss_fwd: null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(a->sums, 0, 2 * sizeof(float), st);
+    B200_REQUIRE(e == cudaSuccess, "flow_loss_fwd: memset: %s", cudaGetErrorString(e));
+    LossP p{a->pred, a->x1, a->x0, a->span, a->sums, a->pred_data, a->rows, a->C, nullptr, nullptr, 0};
+    flow_loss_fwd_kernel<<<grid_for(a->rows * a->C), 256, 0, st>>>(p);
+    if (int rc = check_launch("flow_loss_fwd_kernel")) return rc;
+    flow_loss_finalize_kernel<<<1, 1, 0, st>>>(a->sums, a->loss, a->C);
+    return check_launch("flow_loss_finalize_kernel");
+}
+extern "C" int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t stream) {
+    B200_REQUIRE(a && a->pred && a->x1 && a->x0 && a->span && a->sums && a->dloss && a->dpred && a->ldp >= a->C && (a->ldp % 8) == 0, "flow_loss_bwd: bad arguments");
+    LossP p{a->pred, a->x1, a->x0, a->span, a->sums, nullptr, a->rows, a->C, a->dloss, (__nv_bfloat16*)a->dpred, a->ldp};
+    flow_loss_bwd_kernel<<<grid_for(a->rows * a->ldp), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("flow_loss_bwd_kernel");
+}
+
+extern "C" int b200_rowgate_bwd(const void* dy, const void* y, const float* cs, const uint8_t* mask, void* dz, float* d_cs,
+                                int32_t B, int32_t rows_per_batch, int32_t D, b200_stream_t stream) {
+    B200_REQUIRE(dy && dz && B > 0 && B <= 65535 && rows_per_batch > 0 && D % 8 == 0, "rowgate_bwd: bad arguments");
+    B200_REQUIRE(!cs || (y && d_cs), "rowgate_bwd: gate backward needs y and d_cs");
+    const int rpb = 64;
+    dim3 grid((rows_per_batch + rpb - 1) / rpb, B);
+    rowgate_bwd_kernel<<<grid, 256, (size_t)D * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, cs, mask, (__nv_bfloat16*)dz, d_cs, rows_per_batch, D, rpb);
+    return check_launch("rowgate_bwd_kernel");
+}
+
+extern "C" int b200_cast_rows(const float* src, void* dst, int64_t rows, int32_t cols, int32_t ld, b200_stream_t stream) {
+    B200_REQUIRE(src && dst && rows > 0 && cols > 0 && ld >= cols, "cast_rows: bad arguments");
+    cast_rows_kernel<<<grid_for(rows * ld), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, (__nv_bfloat16*)dst, rows, cols, ld);
+    return check_launch("cast_rows_kernel");
+}

@@ -1,0 +1,453 @@
+// Conditioning-path and convolution kernels: small-batch fp32 linears (time MLP, every AdaptiveRMSNorm /
+// AdaLNZero gamma projection batched into one launch, duration head), Fourier time features, the masked
+// depthwise conv + SiLU positional module, and the masked mean pool of the duration predictor.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ float sl_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float sl_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ size_t yidx(const b200_small_linear_args& a, int b, int n) {
+    return a.seg_major ? ((size_t)(n / a.seg) * a.B + b) * a.seg + (n % a.seg) : (size_t)b * a.N + n;
+}
+__device__ __forceinline__ int act_of(int act, int seg, int n) { return act == 5 ? (((n / seg) & 1) ? 2 : 3) : act; }
+__device__ __forceinline__ float act_fwd(int a, float z) {
+    switch (a) {
+        case 1: return z * sl_sigmoid(z);
+        case 2: return sl_sigmoid(z);
+        case 3: return 1.f + z;
+        case 4: return z > 20.f ? z : log1pf(expf(z));
+        default: return z;
+    }
+}
+__device__ __forceinline__ float act_bwd(int a, float z) {
+    switch (a) {
+        case 1: { const float s = sl_sigmoid(z); return s * (1.f + z * (1.f - s)); }
+        case 2: { const float s = sl_sigmoid(z); return s * (1.f - s); }
+        case 4: return sl_sigmoid(z);
+        default: return 1.f;
+    }
+}
+
+constexpr int SL_MAXB = 64;
+
+// one warp per output feature n: Z[b,n] for all b
+__global__ void __launch_bounds__(256) small_linear_fwd_kernel(const b200_small_linear_args a) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    const float* w = a.W + (size_t)n * a.K;
+    const float bias = a.bias ? a.bias[n] : 0.f;
+    const int ac = act_of(a.act, a.seg, n);
+    for (int b0 = 0; b0 < a.B; b0 += 8) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = lane; k < a.K; k += 32) {
+            const float wv = __ldg(w + k);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (b0 + j < a.B) acc[j] += wv * __ldg(a.X + (size_t)(b0 + j) * a.K + k);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float s = sl_warp_sum(acc[j]);
+            if (lane == 0 && b0 + j < a.B) {
+                const float z = s + bias;
+                if (a.Z) a.Z[yidx(a, b0 + j, n)] = z;
+                a.Y[yidx(a, b0 + j, n)] = act_fwd(ac, z);
+            }
+        }
+    }
+}
+// one warp per output feature n: dZ[:,n], dbias[n], dW[n,:]
+__global__ void __launch_bounds__(256) small_linear_bwd_w_kernel(const b200_small_linear_args a) {
+    __shared__ float sdz[8][SL_MAXB];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int n = blockIdx.x * 8 + wl;
+    if (n >= a.N) return;
+    const int ac = act_of(a.act, a.seg, n);
+    float db = 0.f;
+    for (int b = lane; b < a.B; b += 32) {
+        const float dz = a.dY[yidx(a, b, n)] * act_bwd(ac, a.Z[yidx(a, b, n)]);
+        sdz[wl][b] = dz;
+        a.dZ[yidx(a, b, n)] = dz;
+        db += dz;
+    }
+    db = sl_warp_sum(db);
+    if (lane == 0 && a.dbias) a.dbias[n] = db;
+    __syncwarp();
+    for (int k = lane; k < a.K; k += 32) {
+        float acc = 0.f;
+        for (int b = 0; b < a.B; ++b) acc += sdz[wl][b] * __ldg(a.X + (size_t)b * a.K + k);
+        a.dW[(size_t)n * a.K + k] = acc;
+    }
+}
+// dX[b,k] += sum_{n in block range} dZ[b,n] W[n,k]   (dX zeroed by the host wrapper)
+__global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_small_linear_args a, int n_per_block) {
+    const int n0 = blockIdx.x * n_per_block, n1 = min(a.N, n0 + n_per_block);
+    for (int k = threadIdx.x; k < a.K; k += 256) {
+        for (int b0 = 0; b0 < a.B; b0 += 8) {
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int n = n0; n < n1; ++n) {
+                const float wv = __ldg(a.W + (size_t)n * a.K + k);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (b0 + j < a.B) acc[j] += wv * a.dZ[yidx(a, b0 + j, n)];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (b0 + j < a.B) atomicAdd(a.dX + (size_t)(b0 + j) * a.K + k, acc[j]);
+        }
+    }
+}
+
+__global__ void fourier_embed_kernel(const float* times, const float* w, float* out, int B, int half) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, j = i % half;
+    const float t = times[b];
+    const float f = t * w[j] * 2.f * 3.14159265358979323846f;
+    float s, c;
+    sincosf(f, &s, &c);
+    float* o = out + (size_t)b * (2 * half + 1);
+    if (j == 0) o[0] = t;
+    o[1 + j] = s;
+    o[1 + half + j] = c;
+}
+
+// ------------------------------------------------------------------------------------------------ depthwise conv
+constexpr int CV_TN = 64, CV_TC = 64, CV_HALO = 15;
+
+__device__ __forceinline__ bool tok_ok(const unsigned char* mask, int b, int n, int Np) {
+    return n >= 0 && n < Np && (!mask || mask[(size_t)b * Np + n]);
+}
+
+__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const b200_dwconv_args a) {
+    __shared__ float xs[CV_TN + 2 * CV_HALO][CV_TC];
+    __shared__ float ws[31][CV_TC];
+    const int n0 = blockIdx.x * CV_TN, c0 = blockIdx.y * CV_TC, b = blockIdx.z;
+    const int pad = a.ksize / 2;
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
+    for (int i = threadIdx.x; i < (CV_TN + 2 * CV_HALO) * (CV_TC / 8); i += 256) {
+        const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
+        const int n = n0 - CV_HALO + r;
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (tok_ok(a.mask, b, n, a.Np) && c0 + ch < a.D) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + n) * a.D + c0 + ch);
+            v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+            v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xs[r][ch + j] = v[j];
+    }
+    for (int i = threadIdx.x; i < a.ksize * CV_TC; i += 256) {
+        const int k = i / CV_TC, c = i % CV_TC;
+        ws[k][c] = (c0 + c < a.D) ? a.weight[(size_t)(c0 + c) * a.ksize + k] : 0.f;
+    }
+    __syncthreads();
+    const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
+    if (c0 + cl >= a.D) return;
+    const float bias = a.bias[c0 + cl];
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y);
+    for (int jj = 0; jj < 16; ++jj) {
+        const int r = tg * 16 + jj, n = n0 + r;
+        if (n >= a.Np) break;
+        float acc = bias;
+        for (int k = 0; k < a.ksize; ++k) acc += ws[k][cl] * xs[r + CV_HALO - pad + k][cl];
+        const float o = tok_ok(a.mask, b, n, a.Np) ? acc / (1.f + __expf(-acc)) : 0.f;
+        y[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(o);
+    }
+}
+
+__global__ void __launch_bounds__(256) dwconv_bwd_kernel(const b200_dwconv_args a) {
+    extern __shared__ float sm[];
+    float (*xs)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm);                                  // [TN + 4 HALO]
+    float (*dps)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (CV_TN + 4 * CV_HALO) * CV_TC);  // [TN + 2 HALO]
+    float (*ws)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (2 * CV_TN + 6 * CV_HALO) * CV_TC);  // [31]
+    float (*sdw)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (2 * CV_TN + 6 * CV_HALO + 31) * CV_TC);  // [32] (31 taps + bias)
+    const int n0 = blockIdx.x * CV_TN, c0 = blockIdx.y * CV_TC, b = blockIdx.z;
+    const int pad = a.ksize / 2;
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
+    const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy);
+    for (int i = threadIdx.x; i < (CV_TN + 4 * CV_HALO) * (CV_TC / 8); i += 256) {
+        const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
+        const int n = n0 - 2 * CV_HALO + r;
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (tok_ok(a.mask, b, n, a.Np) && c0 + ch < a.D) {
+            const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + n) * a.D + c0 + ch);
+            v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+            v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xs[r][ch + j] = v[j];
+    }
+    for (int i = threadIdx.x; i < 32 * CV_TC; i += 256) {
+        const int k = i / CV_TC, c = i % CV_TC;
+        if (k < 31) ws[k][c] = (k < a.ksize && c0 + c < a.D) ? a.weight[(size_t)(c0 + c) * a.ksize + k] : 0.f;
+        sdw[k][c] = 0.f;
+    }
+    __syncthreads();
+    const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
+    const bool cok = c0 + cl < a.D;
+    const float bias = cok ? a.bias[c0 + cl] : 0.f;
+    // phase 1: d(pre-activation) on the tile plus a HALO on each side
+    for (int r = tg; r < CV_TN + 2 * CV_HALO; r += 4) {
+        const int n = n0 - CV_HALO + r;
+        float d = 0.f;
+        if (cok && tok_ok(a.mask, b, n, a.Np)) {
+            float pre = bias;
+            for (int k = 0; k < a.ksize; ++k) pre += ws[k][cl] * xs[r + CV_HALO - pad + k][cl];
+            const float s = 1.f / (1.f + __expf(-pre));
+            d = __bfloat162float(dy[((size_t)b * a.Np + n) * a.D + c0 + cl]) * s * (1.f + pre * (1.f - s));
+        }
+        dps[r][cl] = d;
+    }
+    __syncthreads();
+    // phase 2: dx and the weight / bias partial sums
+    __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(a.dx);
+    float db = 0.f;
+    for (int jj = 0; cok && jj < 16; ++jj) {
+        const int r = tg * 16 + jj, n = n0 + r;
+        if (n >= a.Np) break;
+        float acc = 0.f;
+        for (int k = 0; k < a.ksize; ++k) acc += ws[k][cl] * dps[r + CV_HALO + pad - k][cl];
+        dx[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(tok_ok(a.mask, b, n, a.Np) ? acc : 0.f);
+        db += dps[r + CV_HALO][cl];
+    }
+    for (int k = 0; cok && k < a.ksize; ++k) {
+        float acc = 0.f;
+        for (int jj = 0; jj < 16; ++jj) {
+            const int r = tg * 16 + jj;
+            if (n0 + r >= a.Np) break;
+            acc += dps[r + CV_HALO][cl] * xs[r + 2 * CV_HALO - pad + k][cl];
+        }
+        atomicAdd(&sdw[k][cl], acc);
+    }
+    if (cok) atomicAdd(&sdw[31][cl], db);
+    __syncthreads();
+    if (cok && tg == 0) {
+        for (int k = 0; k < a.ksize; ++k) atomicAdd(a.dweight + (size_t)(c0 + cl) * a.ksize + k, sdw[k][cl]);
+        atomicAdd(a.dbias + c0 + cl, sdw[31][cl]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ masked mean
+__global__ void __launch_bounds__(256) masked_mean_fwd_kernel(const __nv_bfloat16* x, const unsigned char* mask, float* out, int N, int D) {
+    const int b = blockIdx.y, d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= D) return;
+    float acc = 0.f, den = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const bool m = !mask || mask[(size_t)b * N + n];
+        if (m) { acc += __bfloat162float(x[((size_t)b * N + n) * D + d]); den += 1.f; }
+    }
+    out[(size_t)b * D + d] = acc / fmaxf(den, 1.f);
+}
+__global__ void __launch_bounds__(256) masked_mean_bwd_kernel(const float* dout, const unsigned char* mask, __nv_bfloat16* dx, int N, int D) {
+    __shared__ float sden;
+    const int b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        float den = 0.f;
+        for (int n = 0; n < N; ++n) den += (!mask || mask[(size_t)b * N + n]) ? 1.f : 0.f;
+        sden = fmaxf(den, 1.f);
+    }
+    __syncthreads();
+    const long long total = (long long)N * D;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int n = (int)(i / D), d = (int)(i % D);
+        const bool m = !mask || mask[(size_t)b * N + n];
+        dx[(size_t)b * N * D + i] = __float2bfloat16(m ? dout[(size_t)b * D + d] / sden : 0.f);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ ODE / CFG helpers
+// out = y + a * f  (fixed-grid midpoint / Euler update, torchdiffeq semantics A.7)
+__global__ void __launch_bounds__(256) axpy_kernel(const float* y, const float* f, float a, float* out, long long n) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = y[i] + a * f[i];
+}
+// per-sample fp64 reductions for the APG projection (e2_tts.py:113-124): red[b] = (<pred - null, pred>, <pred, pred>)
+__global__ void __launch_bounds__(256) cfg_reduce_kernel(const float* pred, const float* null_pred, double* red, long long per) {
+    const int b = blockIdx.y;
+    const float* p = pred + (size_t)b * per;
+    const float* q = null_pred + (size_t)b * per;
+    double d0 = 0.0, d1 = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < per; i += (long long)gridDim.x * 256) {
+        const double pv = p[i], uv = (double)p[i] - (double)q[i];
+        d0 += uv * pv; d1 += pv * pv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+    __shared__ double s0[8], s1[8];
+    if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = d0; s1[threadIdx.x >> 5] = d1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0;
+        for (int k = 0; k < 8; ++k) { a += s0[k]; c += s1[k]; }
+        atomicAdd(red + 2 * b, a);
+        atomicAdd(red + 2 * b + 1, c);
+    }
+}
+// out = pred + (orth + par * keep) * strength, par = (<upd, unit>) unit, unit = pred / max(||pred||, 1e-12)
+__global__ void __launch_bounds__(256) cfg_apply_kernel(const float* pred, const float* null_pred, const double* red, float* out, long long per,
+                                                         float strength, int remove_parallel, float keep) {
+    const int b = blockIdx.y;
+    const double nrm = fmax(sqrt(red[2 * b + 1]), 1e-12);
+    const double coef = red[2 * b] / (nrm * nrm);   // <upd, unit> / ||pred||
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < per; i += (long long)gridDim.x * 256) {
+        const size_t j = (size_t)b * per + i;
+        const double pv = pred[j], uv = pv - (double)null_pred[j];
+        double upd = uv;
+        if (remove_parallel) {
+            const float par = (float)(coef * pv);            // reference casts parallel/orthogonal back to fp32 (:124)
+            const float orth = (float)(uv - coef * pv);
+            upd = (double)(orth + par * keep);
+        }
+        out[j] = (float)(pv + upd * strength);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ MelSpec
+// torchaudio MelSpectrogram(n_fft = win, hop, center/reflect, power 1, HTK fb) -> log(clamp(., 1e-5)) (e2_tts.py:248-290).
+// One block per (frame, batch): windowed frame in smem, direct 1024-point real DFT with an smem twiddle table
+// (index (k*n) mod n_fft), magnitude, dense mel filterbank, log. Output [B, n_mels, frames] like the reference.
+__global__ void __launch_bounds__(256) melspec_kernel(const float* wave, const float* window, const float* fb, float* out, int nw, int n_fft,
+                                                       int hop, int n_mels, int frames) {
+    extern __shared__ float msm[];
+    float* xs = msm;                 // [n_fft]
+    float* cs = xs + n_fft;          // [n_fft]
+    float* sn = cs + n_fft;          // [n_fft]
+    float* mag = sn + n_fft;         // [n_fft/2 + 1]
+    const int f = blockIdx.x, b = blockIdx.y;
+    const int pad = n_fft / 2, nbins = n_fft / 2 + 1;
+    for (int n = threadIdx.x; n < n_fft; n += 256) {
+        int j = f * hop + n - pad;
+        if (j < 0) j = -j;
+        if (j >= nw) j = 2 * (nw - 1) - j;
+        xs[n] = wave[(size_t)b * nw + j] * window[n];
+        float s, c;
+        sincospif(2.f * (float)n / (float)n_fft, &s, &c);
+        cs[n] = c; sn[n] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nbins; k += 256) {
+        float re = 0.f, im = 0.f;
+        int idx = 0;
+        for (int n = 0; n < n_fft; ++n) {
+            re += xs[n] * cs[idx];
+            im -= xs[n] * sn[idx];
+            idx = (idx + k) & (n_fft - 1);
+        }
+        mag[k] = sqrtf(re * re + im * im);
+    }
+    __syncthreads();
+    for (int m = threadIdx.x; m < n_mels; m += 256) {
+        float acc = 0.f;
+        for (int k = 0; k < nbins; ++k) acc += mag[k] * __ldg(fb + (size_t)k * n_mels + m);
+        out[((size_t)b * n_mels + m) * frames + f] = logf(fmaxf(acc, 1e-5f));
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_small_linear_fwd(const b200_small_linear_args* a, b200_stream_t stream) {
+    B200_REQUIRE(a && a->X && a->W && a->Y, "small_linear_fwd: null pointer");
+    B200_REQUIRE(a->B > 0 && a->B <= SL_MAXB && a->N > 0 && a->K > 0, "small_linear: batch must be 1..%d", SL_MAXB);
+    B200_REQUIRE(a->act >= 0 && a->act <= 5 && (a->act != 5 || a->seg > 0), "small_linear: bad activation");
+    B200_REQUIRE(!a->seg_major || (a->seg > 0 && a->N % a->seg == 0), "small_linear: seg_major needs N %% seg == 0");
+    small_linear_fwd_kernel<<<(a->N + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    return check_launch("small_linear_fwd_kernel");
+}
+extern "C" int b200_small_linear_bwd(const b200_small_linear_args* a, b200_stream_t stream) {
+    B200_REQUIRE(a && a->X && a->W && a->Z && a->dY && a->dZ && a->dW, "small_linear_bwd: null pointer");
+    B200_REQUIRE(a->B > 0 && a->B <= SL_MAXB && a->N > 0 && a->K > 0, "small_linear: batch must be 1..%d", SL_MAXB);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    small_linear_bwd_w_kernel<<<(a->N + 7) / 8, 256, 0, st>>>(*a);
+    if (int rc = check_launch("small_linear_bwd_w_kernel")) return rc;
+    if (a->dX) {
+        cudaError_t e = cudaMemsetAsync(a->dX, 0, (size_t)a->B * a->K * sizeof(float), st);
+        B200_REQUIRE(e == cudaSuccess, "small_linear_bwd: memset: %s", cudaGetErrorString(e));
+        const int npb = 64;
+        small_linear_bwd_x_kernel<<<(a->N + npb - 1) / npb, 256, 0, st>>>(*a, npb);
+        return check_launch("small_linear_bwd_x_kernel");
+    }
+    return 0;
+}
+extern "C" int b200_fourier_embed(const float* times, const float* weights, float* out, int32_t B, int32_t half, b200_stream_t stream) {
+    B200_REQUIRE(times && weights && out && B > 0 && half > 0, "fourier_embed: bad arguments");
+    fourier_embed_kernel<<<(B * half + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(times, weights, out, B, half);
+    return check_launch("fourier_embed_kernel");
+}
+
+static int check_conv(const b200_dwconv_args* a) {
+    B200_REQUIRE(a && a->x && a->weight && a->bias, "dwconv: null pointer");
+    B200_REQUIRE((a->ksize & 1) && a->ksize >= 1 && a->ksize <= 31, "dwconv: kernel_size must be odd and <= 31 (got %d)", a->ksize);
+    B200_REQUIRE(a->D % 8 == 0 && a->B > 0 && a->B <= 65535 && a->Np > 0, "dwconv: unsupported shape");
+    return 0;
+}
+extern "C" int b200_dwconv_fwd(const b200_dwconv_args* a, b200_stream_t stream) {
+    if (check_conv(a)) return -1;
+    B200_REQUIRE(a->y, "dwconv_fwd: null output");
+    dim3 grid((a->Np + CV_TN - 1) / CV_TN, (a->D + CV_TC - 1) / CV_TC, a->B);
+    dwconv_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    return check_launch("dwconv_fwd_kernel");
+}
+extern "C" int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream) {
+    if (check_conv(a)) return -1;
+    B200_REQUIRE(a->dy && a->dx && a->dweight && a->dbias, "dwconv_bwd: null pointer");
+    const size_t smem = (size_t)(2 * CV_TN + 6 * CV_HALO + 31 + 32) * CV_TC * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid((a->Np + CV_TN - 1) / CV_TN, (a->D + CV_TC - 1) / CV_TC, a->B);
+    dwconv_bwd_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    return check_launch("dwconv_bwd_kernel");
+}
+
+extern "C" int b200_masked_mean_fwd(const void* x, const uint8_t* mask, float* out, int32_t B, int32_t N, int32_t D, b200_stream_t stream) {
+    B200_REQUIRE(x && out && B > 0 && N > 0 && D > 0, "masked_mean_fwd: bad arguments");
+    masked_mean_fwd_kernel<<<dim3((D + 255) / 256, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)x, mask, out, N, D);
+    return check_launch("masked_mean_fwd_kernel");
+}
+extern "C" int b200_masked_mean_bwd(const float* dout, const uint8_t* mask, void* dx, int32_t B, int32_t N, int32_t D, b200_stream_t stream) {
+    B200_REQUIRE(dout && dx && B > 0 && N > 0 && D > 0, "masked_mean_bwd: bad arguments");
+    masked_mean_bwd_kernel<<<dim3(64, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, mask, (__nv_bfloat16*)dx, N, D);
+    return check_launch("masked_mean_bwd_kernel");
+}
+
+extern "C" int b200_axpy(const float* y, const float* f, float a, float* out, int64_t n, b200_stream_t stream) {
+    B200_REQUIRE(y && f && out && n > 0, "axpy: bad arguments");
+    const long long g = (n + 255) / 256;
+    axpy_kernel<<<(unsigned)(g > 148 * 16 ? 148 * 16 : g), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, f, a, out, n);
+    return check_launch("axpy_kernel");
+}
+extern "C" int b200_cfg_combine(const float* pred, const float* null_pred, double* ws_red, float* out, int32_t B, int64_t per_sample,
+                                float cfg_strength, int32_t remove_parallel, float keep_parallel_frac, b200_stream_t stream) {
+    B200_REQUIRE(pred && null_pred && ws_red && out && B > 0 && B <= 65535 && per_sample > 0, "cfg_combine: bad arguments");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(ws_red, 0, (size_t)B * 2 * sizeof(double), st);
+    B200_REQUIRE(e == cudaSuccess, "cfg_combine: memset: %s", cudaGetErrorString(e));
+    const int gx = (int)((per_sample + 256 * 8 - 1) / (256 * 8));
+    cfg_reduce_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, st>>>(pred, null_pred, ws_red, per_sample);
+    if (int rc = check_launch("cfg_reduce_kernel")) return rc;
+    cfg_apply_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, st>>>(pred, null_pred, ws_red, out, per_sample, cfg_strength, remove_parallel, keep_parallel_frac);
+    return check_launch("cfg_apply_kernel");
+}
+extern "C" int b200_melspec(const float* wave, const float* window, const float* fb, float* out, int32_t B, int32_t nw, int32_t n_fft,
+                            int32_t hop, int32_t n_mels, b200_stream_t stream) {
+    B200_REQUIRE(wave && window && fb && out && B > 0 && B <= 65535, "melspec: bad arguments");
+    B200_REQUIRE(n_fft >= 64 && (n_fft & (n_fft - 1)) == 0 && n_fft <= 4096 && hop > 0 && nw > n_fft / 2, "melspec: n_fft must be a power of two <= 4096 and the wave longer than n_fft/2");
+    const int frames = 1 + nw / hop;
+    const size_t smem = (size_t)(3 * n_fft + n_fft / 2 + 1) * sizeof(float);
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); configured = true; }
+    melspec_kernel<<<dim3(frames, B), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(wave, window, fb, out, nw, n_fft, hop, n_mels, frames);
+    return check_launch("melspec_kernel");
+}

@@ -1,0 +1,723 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels of libb200e2tts.so.
+
+Each Function is one fused stage of the reference's multistream block (citations: /root/reference/
+e2_tts_pytorch/e2_tts.py and SURVEY.md Appendix A). PyTorch only allocates the buffers, orders the launches on
+the current stream and carries the autograd graph; no arithmetic on the path is done by torch ops.
+Parameters stay ordinary fp32 nn.Parameters (reference-compatible state_dict); Functions receive them as
+inputs (so autograd / DDP see per-parameter gradients) next to their packed bf16 copies.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import lib
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _c(t):
+    return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def gemm(A, B, M, N, K, *, lda=None, ldb=None, A2=None, lda2=0, K1=0, a_mn=False, b_mn=False, out=None, ldd=None,
+         out_fp32=False, D2=None, ldd2=0, bias=None, colscale=None, rows_per_batch=0, rowmask=None, resid=None, ldr=0,
+         geglu=False, dropout_p=0.0, seed=0, split_k=1):
+    """D[M,N] = epilogue(sum_k A[m,k] B[n,k]) on the tcgen05 GEMM (include/b200_e2tts.h: b200_gemm)."""
+    dev = A.device
+    n_out = N // 2 if geglu else N
+    if ldd is None:
+        ldd = n_out if out_fp32 else (n_out + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((M, ldd), device=dev, dtype=F32 if out_fp32 else BF16)
+    args = lib.make_args(
+        'b200_gemm_args', A=A, lda=lda if lda is not None else (M if a_mn else K), A2=A2, lda2=lda2, K1=K1,
+        B=B, ldb=ldb if ldb is not None else (N if b_mn else K), M=M, N=N, K=K, a_mn_major=int(a_mn), b_mn_major=int(b_mn),
+        D=out, ldd=ldd, d_fp32=int(out_fp32), D2=D2, ldd2=ldd2, bias=bias, colscale=colscale, rows_per_batch=rows_per_batch,
+        rowmask=rowmask, resid=resid, ldr=ldr, geglu=int(geglu), dropout_p=float(dropout_p), seed=int(seed), split_k=int(split_k))
+    lib.call('b200_gemm', args, _stream())
+    return out
+
+
+def _split_for(M, N, K):
+    """split-K factor for weight-gradient GEMMs (few output tiles, very long K)."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    kb = (K + 63) // 64
+    return max(1, min(kb, (148 + tiles - 1) // tiles, 32))
+
+
+def grad_weight(dY, X, T, n_out, n_in, *, ldy=None, ldx=None, out=None, ldd=None):
+    """dW[n_out, n_in] = dY[T, n_out]^T X[T, n_in]  — both operands MN-major, fp32 out, split-K."""
+    return gemm(dY, X, n_out, n_in, T, lda=ldy if ldy is not None else n_out, ldb=ldx if ldx is not None else n_in,
+                a_mn=True, b_mn=True, out=out, ldd=ldd, out_fp32=True, split_k=_split_for(n_out, n_in, T))
+
+
+def colsum(X, T, ncols, ld):
+    out = torch.zeros(ncols, device=X.device, dtype=F32)
+    lib.call('b200_colsum', X, T, ncols, ld, out, _stream())
+    return out
+
+
+def pack_weights(table_dev, n):
+    lib.call('b200_pack_weights', table_dev, n, _stream())
+
+
+def rotary_table(Np, device):
+    cs = torch.empty((Np, 32), device=device, dtype=F32)
+    sn = torch.empty((Np, 32), device=device, dtype=F32)
+    lib.call('b200_rotary_table', cs, sn, Np, 64, _stream())
+    return cs, sn
+
+
+# ---------------------------------------------------------------------------------------------------- hyper-connections
+class HcWidth(Function):
+    """HyperConnections width connection + consumer (Adaptive)RMSNorm (A.5, A.1; e2_tts.py:870-882, 900-939)."""
+
+    @staticmethod
+    def forward(ctx, xres, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain, norm_mode, rows_per_batch):
+        T, S, D = xres.shape
+        branch = torch.empty((T, D), device=xres.device, dtype=BF16)
+        res = torch.empty_like(xres)
+        beta = torch.empty((T, S), device=xres.device, dtype=F32)
+        a = lib.make_args('b200_hc_width_args', xres=xres, norm_gamma=gamma, dynamic_alpha_fn=afn, dynamic_alpha_scale=ascale,
+                          static_alpha=salpha, dynamic_beta_fn=bfn, dynamic_beta_scale=bscale, static_beta=sbeta,
+                          norm_mode=norm_mode, norm_gain=norm_gain, rows_per_batch=rows_per_batch, T=T, D=D, num_streams=S,
+                          branch=branch, res_out=res, beta_out=beta)
+        lib.call('b200_hc_width_fwd', a, _stream())
+        ctx.save_for_backward(xres, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain)
+        ctx.meta = (norm_mode, rows_per_batch)
+        return branch, res, beta
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_branch, d_res, d_beta):
+        xres, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain = ctx.saved_tensors
+        norm_mode, rpb = ctx.meta
+        T, S, D = xres.shape
+        dev = xres.device
+        d_xres = torch.empty_like(xres)
+        # one zero-filled fp32 slab for all parameter-gradient accumulators
+        n_gain = 0 if norm_mode == 0 else norm_gain.numel()
+        sizes = [D, D * (S + 1), 1, S * (S + 1), D, 1, S, n_gain]
+        slab = torch.zeros(sum(sizes), device=dev, dtype=F32)
+        parts, o = [], 0
+        for n in sizes:
+            parts.append(slab[o:o + n])
+            o += n
+        g_gamma, g_afn, g_as, g_sal, g_bfn, g_bs, g_sbe, g_gain = parts
+        a = lib.make_args('b200_hc_width_args', xres=xres, norm_gamma=gamma, dynamic_alpha_fn=afn, dynamic_alpha_scale=ascale,
+                          static_alpha=salpha, dynamic_beta_fn=bfn, dynamic_beta_scale=bscale, static_beta=sbeta,
+                          norm_mode=norm_mode, norm_gain=norm_gain, rows_per_batch=rpb, T=T, D=D, num_streams=S,
+                          d_branch=_c(d_branch), d_res=_c(d_res), d_beta=_c(d_beta), d_xres=d_xres,
+                          g_norm_gamma=g_gamma, g_dynamic_alpha_fn=g_afn, g_dynamic_alpha_scale=g_as, g_static_alpha=g_sal,
+                          g_dynamic_beta_fn=g_bfn, g_dynamic_beta_scale=g_bs, g_static_beta=g_sbe,
+                          g_norm_gain=g_gain if norm_mode else None)
+        lib.call('b200_hc_width_bwd', a, _stream())
+        return (d_xres, g_gamma, g_afn.view(D, S + 1), g_as.view(()), g_sal.view(S, S + 1), g_bfn, g_bs.view(()), g_sbe,
+                g_gain.view_as(norm_gain) if norm_mode else None, None, None)
+
+
+class HcDepth(Function):
+    """HyperConnections depth connection: residual' + beta * branch_out (A.5)."""
+
+    @staticmethod
+    def forward(ctx, res, y, beta):
+        T, S, D = res.shape
+        out = torch.empty_like(res)
+        a = lib.make_args('b200_hc_depth_args', res=res, y=y, beta=beta, out=out, T=T, D=D, num_streams=S)
+        lib.call('b200_hc_depth_fwd', a, _stream())
+        ctx.save_for_backward(y, beta)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        y, beta = ctx.saved_tensors
+        d_out = _c(d_out)
+        T, S, D = d_out.shape
+        d_y = torch.empty_like(y)
+        d_beta = torch.empty_like(beta)
+        a = lib.make_args('b200_hc_depth_args', y=y, beta=beta, d_out=d_out, d_y=d_y, d_beta=d_beta, T=T, D=D, num_streams=S)
+        lib.call('b200_hc_depth_bwd', a, _stream())
+        return d_out, d_y, d_beta
+
+
+# ---------------------------------------------------------------------------------------------------- depthwise conv
+class DwConv(Function):
+    """DepthwiseConv (e2_tts.py:295-328): mask -> depthwise conv k -> SiLU -> mask, on bf16 [B, Np, D]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mask, B, Np):
+        D = x.shape[-1]
+        w2 = weight.reshape(D, -1)
+        y = torch.empty_like(x)
+        a = lib.make_args('b200_dwconv_args', x=x, mask=mask, weight=w2, bias=bias, y=y, B=B, Np=Np, D=D, ksize=w2.shape[1])
+        lib.call('b200_dwconv_fwd', a, _stream())
+        ctx.save_for_backward(x, weight, bias, mask)
+        ctx.meta = (B, Np)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight, bias, mask = ctx.saved_tensors
+        B, Np = ctx.meta
+        D = x.shape[-1]
+        w2 = weight.reshape(D, -1)
+        dx = torch.empty_like(x)
+        dw = torch.zeros_like(w2)
+        db = torch.zeros_like(bias)
+        a = lib.make_args('b200_dwconv_args', x=x, mask=mask, weight=w2, bias=bias, dy=_c(dy), dx=dx, dweight=dw, dbias=db,
+                          B=B, Np=Np, D=D, ksize=w2.shape[1])
+        lib.call('b200_dwconv_bwd', a, _stream())
+        return dx, dw.view_as(weight), db, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------- attention
+class QkvProj(Function):
+    """to_q/to_k/to_v (+ to_v_head_gate, to_value_residual_mix logits) as ONE GEMM, then rotary on q,k, value-residual
+    lerp on v and sigmoid head gate (A.3, A.4 steps 1-3/5; ctor e2_tts.py:641,689)."""
+
+    @staticmethod
+    def forward(ctx, xn, wq, wk, wv, wg, bg, wm, bm, v_first, wpack, cs, sn, B, Np, H):
+        T, Din = xn.shape
+        I = H * 64
+        ncat = 3 * I + (2 if wm is not None else 1) * H
+        ld = (ncat + 7) // 8 * 8
+        qkvg = gemm(xn, wpack, T, ncat, Din, ldd=ld)
+        q = torch.empty((B, H, Np, 64), device=xn.device, dtype=BF16)
+        k, v = torch.empty_like(q), torch.empty_like(q)
+        gate = torch.empty((T, H), device=xn.device, dtype=F32)
+        a = lib.make_args('b200_qkv_post_args', qkvg=qkvg, ld=ld, gate_bias=bg, mix_bias=bm, rot_cos=cs, rot_sin=sn, v_first=v_first,
+                          q=q, k=k, v=v, gate=gate, B=B, H=H, Np=Np, dim_head=64)
+        lib.call('b200_qkv_post_fwd', a, _stream())
+        ctx.save_for_backward(xn, qkvg, gate, v_first, wpack, cs, sn, bg, bm)
+        ctx.meta = (B, Np, H, ncat, ld, wm is not None)
+        return q, k, v, gate
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dq, dk, dv, dgate):
+        xn, qkvg, gate, v_first, wpack, cs, sn, bg, bm = ctx.saved_tensors
+        B, Np, H, ncat, ld, has_mix = ctx.meta
+        T, Din = xn.shape
+        I = H * 64
+        dev = xn.device
+        if dgate is None:
+            dgate = torch.zeros_like(gate)
+        d_qkvg = torch.empty((T, ld), device=dev, dtype=BF16)
+        d_vfirst = torch.empty_like(v_first) if v_first is not None else None
+        a = lib.make_args('b200_qkv_post_args', qkvg=qkvg, ld=ld, gate_bias=bg, mix_bias=bm, rot_cos=cs, rot_sin=sn, v_first=v_first,
+                          gate=gate, dq=_c(dq), dk=_c(dk), dv=_c(dv), d_gate=_c(dgate), d_qkvg=d_qkvg, d_vfirst=d_vfirst,
+                          B=B, H=H, Np=Np, dim_head=64)
+        lib.call('b200_qkv_post_bwd', a, _stream())
+        dx = gemm(d_qkvg, wpack, T, Din, ncat, lda=ld, ldb=Din, b_mn=True)
+        dW = grad_weight(d_qkvg, xn, T, ncat, Din, ldy=ld)
+        db = colsum(d_qkvg, T, ncat, ld)
+        return (dx, dW[:I], dW[I:2 * I], dW[2 * I:3 * I], dW[3 * I:3 * I + H], db[3 * I:3 * I + H],
+                dW[3 * I + H:3 * I + 2 * H] if has_mix else None, db[3 * I + H:3 * I + 2 * H] if has_mix else None,
+                d_vfirst, None, None, None, None, None, None)
+
+
+class AttnCore(Function):
+    """Softclamped, key-masked, head-gated flash attention (A.4 steps 4-5). Returns the gated, head-merged output."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, gate, mask, dropout_p, seed, softclamp):
+        B, H, Np, dh = q.shape
+        o = torch.empty_like(q)
+        og = torch.empty((B * Np, H * dh), device=q.device, dtype=BF16)
+        lse = torch.empty((B, H, Np), device=q.device, dtype=F32)
+        a = lib.make_args('b200_attn_fwd_args', q=q, k=k, v=v, keymask=mask, gate=gate, o=o, og=og, lse=lse, B=B, H=H, Np=Np,
+                          dim_head=dh, scale=dh ** -0.5, softclamp=softclamp, dropout_p=dropout_p, seed=seed)
+        lib.call('b200_attn_fwd', a, _stream())
+        ctx.save_for_backward(q, k, v, gate, mask, o, lse)
+        ctx.meta = (dropout_p, seed, softclamp)
+        return og
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_og):
+        q, k, v, gate, mask, o, lse = ctx.saved_tensors
+        dropout_p, seed, softclamp = ctx.meta
+        B, H, Np, dh = q.shape
+        dq, dk, dv, ws_dO = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        ws_delta = torch.empty_like(lse)
+        d_gate = torch.empty_like(gate)
+        a = lib.make_args('b200_attn_bwd_args', q=q, k=k, v=v, o=o, d_og=_c(d_og), keymask=mask, gate=gate, lse=lse, ws_dO=ws_dO,
+                          ws_delta=ws_delta, d_gate=d_gate, dq=dq, dk=dk, dv=dv, B=B, H=H, Np=Np, dim_head=dh, scale=dh ** -0.5,
+                          softclamp=softclamp, dropout_p=dropout_p, seed=seed)
+        lib.call('b200_attn_bwd', a, _stream())
+        return dq, dk, dv, d_gate, None, None, None, None
+
+
+def _rowgate_bwd(dy, y, cs, mask, B, rpb, D):
+    """dz = dy * mask * cs ; d_cs (fp32 [B, D]) — backward of the fused GEMM epilogue."""
+    if cs is None and mask is None:
+        return dy, None
+    dz = torch.empty_like(dy)
+    d_cs = torch.zeros_like(cs) if cs is not None else None
+    lib.call('b200_rowgate_bwd', dy, y, cs, mask, dz, d_cs, B, rpb, D, _stream())
+    return dz, d_cs
+
+
+class OutProj(Function):
+    """Attention to_out (no bias) with the fused epilogue: zero padded rows (A.4 step 6) and AdaLNZero gate (:346-351)."""
+
+    @staticmethod
+    def forward(ctx, og, w, wpack, colscale, mask, B, Np):
+        T, I = og.shape
+        Dout = w.shape[0]
+        y = gemm(og, wpack, T, Dout, I, colscale=colscale, rows_per_batch=Np, rowmask=mask)
+        ctx.save_for_backward(og, wpack, colscale, mask, y)
+        ctx.meta = (B, Np)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        og, wpack, colscale, mask, y = ctx.saved_tensors
+        B, Np = ctx.meta
+        T, I = og.shape
+        Dout = y.shape[1]
+        dz, d_cs = _rowgate_bwd(_c(dy), y, colscale, mask, B, Np, Dout)
+        d_og = gemm(dz, wpack, T, I, Dout, b_mn=True)
+        dW = grad_weight(dz, og, T, Dout, I)
+        return d_og, dW, None, d_cs, None, None, None
+
+
+class FeedForward(Function):
+    """x-transformers FeedForward(glu=True) (A.2): GEGLU GEMM (+dropout) -> out GEMM (+bias, AdaLNZero gate)."""
+
+    @staticmethod
+    def forward(ctx, xn, w1, b1, w2, b2, w1pack, b1pack, w2pack, colscale, B, Np, dropout_p, seed):
+        T, Din = xn.shape
+        inner = w2.shape[1]
+        ug = torch.empty((T, 2 * inner), device=xn.device, dtype=BF16)
+        h = gemm(xn, w1pack, T, 2 * inner, Din, D2=ug, ldd2=2 * inner, bias=b1pack, geglu=True, dropout_p=dropout_p, seed=seed)
+        y = gemm(h, w2pack, T, Din, inner, bias=b2, colscale=colscale, rows_per_batch=Np)
+        ctx.save_for_backward(xn, ug, h, y, w1pack, w2pack, colscale)
+        ctx.meta = (B, Np, dropout_p, seed, inner)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xn, ug, h, y, w1pack, w2pack, colscale = ctx.saved_tensors
+        B, Np, dropout_p, seed, inner = ctx.meta
+        T, Din = xn.shape
+        if colscale is not None:
+            # y = cs * (h W2^T + b2): recover the pre-gate value through y / cs inside the kernel
+            dz, d_cs = _rowgate_bwd(_c(dy), y, colscale, None, B, Np, Din)
+        else:
+            dz, d_cs = _c(dy), None
+        db2 = colsum(dz, T, Din, Din)
+        dh = gemm(dz, w2pack, T, inner, Din, b_mn=True)
+        dW2 = grad_weight(dz, h, T, Din, inner)
+        dug = torch.empty_like(ug)
+        lib.call('b200_geglu_bwd', dh, ug, dug, T, inner, float(dropout_p), int(seed), _stream())
+        dx = gemm(dug, w1pack, T, Din, 2 * inner, b_mn=True)
+        dW1p = grad_weight(dug, xn, T, 2 * inner, Din)
+        db1p = colsum(dug, T, 2 * inner, 2 * inner)
+        nb = inner // 64
+        dW1 = dW1p.view(nb, 2, 64, Din).transpose(0, 1).reshape(2 * inner, Din)   # undo the GEGLU interleave (layout only)
+        db1 = db1p.view(nb, 2, 64).transpose(0, 1).reshape(2 * inner)
+        return dx, dW1, db1, dW2, db2, None, None, None, d_cs, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------- cross-stream GEMMs
+class CrossCondition(Function):
+    """TextAudioCrossCondition (e2_tts.py:486-513) on all S streams, concat never materialised (two-source K)."""
+
+    @staticmethod
+    def forward(ctx, xs, ts, w_ta, w_at, wstack):
+        T, S, D = xs.shape
+        Dt = ts.shape[-1]
+        R = T * S
+        x2, t2 = xs.view(R, D), ts.view(R, Dt)
+        xo = gemm(x2, wstack, R, D, D + Dt, lda=D, A2=t2, lda2=Dt, K1=D, ldb=D + Dt, resid=x2, ldr=D)
+        if w_at is not None:
+            to = gemm(x2, wstack[D:], R, Dt, D + Dt, lda=D, A2=t2, lda2=Dt, K1=D, ldb=D + Dt, resid=t2, ldr=Dt)
+        else:
+            to = ts.view(R, Dt)
+        ctx.save_for_backward(xs, ts, wstack)
+        ctx.has_at = w_at is not None
+        return xo.view(T, S, D), to.view(T, S, Dt)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dxo, dto):
+        xs, ts, wstack = ctx.saved_tensors
+        T, S, D = xs.shape
+        Dt = ts.shape[-1]
+        R, Kc = T * S, D + Dt
+        x2, t2 = xs.view(R, D), ts.view(R, Dt)
+        dxo2, dto2 = _c(dxo).view(R, D), _c(dto).view(R, Dt)
+        dWta = torch.empty((D, Kc), device=xs.device, dtype=F32)
+        grad_weight(dxo2, x2, R, D, D, out=dWta, ldd=Kc)
+        grad_weight(dxo2, t2, R, D, Dt, out=dWta[:, D:], ldd=Kc)
+        if ctx.has_at:
+            dx = gemm(dxo2, wstack, R, D, Kc, lda=D, A2=dto2, lda2=Dt, K1=D, ldb=Kc, b_mn=True, resid=dxo2, ldr=D)
+            dt = gemm(dxo2, wstack[:, D:], R, Dt, Kc, lda=D, A2=dto2, lda2=Dt, K1=D, ldb=Kc, b_mn=True, resid=dto2, ldr=Dt)
+            dWat = torch.empty((Dt, Kc), device=xs.device, dtype=F32)
+            grad_weight(dto2, x2, R, Dt, D, out=dWat, ldd=Kc)
+            grad_weight(dto2, t2, R, Dt, Dt, out=dWat[:, D:], ldd=Kc)
+        else:
+            dx = gemm(dxo2, wstack, R, D, D, lda=D, ldb=Kc, b_mn=True, resid=dxo2, ldr=D)
+            dt = gemm(dxo2, wstack[:, D:], R, Dt, D, lda=D, ldb=Kc, b_mn=True, resid=dto2, ldr=Dt)
+            dWat = None
+        return dx.view(T, S, D), dt.view(T, S, Dt), dWta, dWat, None
+
+
+class SkipProj(Function):
+    """U-Net skip: Linear(2d -> d, no bias) on cat(x, skip) for every stream (e2_tts.py:649, 887-896)."""
+
+    @staticmethod
+    def forward(ctx, xs, skip, w, wpack):
+        T, S, D = xs.shape
+        R = T * S
+        out = gemm(xs.view(R, D), wpack, R, D, 2 * D, lda=D, A2=skip.view(R, D), lda2=D, K1=D, ldb=2 * D)
+        ctx.save_for_backward(xs, skip, wpack)
+        return out.view(T, S, D)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xs, skip, wpack = ctx.saved_tensors
+        T, S, D = xs.shape
+        R = T * S
+        dy2 = _c(dy).view(R, D)
+        dx = gemm(dy2, wpack, R, D, D, ldb=2 * D, b_mn=True)
+        dskip = gemm(dy2, wpack[:, D:], R, D, D, ldb=2 * D, b_mn=True)
+        dW = torch.empty((D, 2 * D), device=xs.device, dtype=F32)
+        grad_weight(dy2, xs.view(R, D), R, D, D, out=dW, ldd=2 * D)
+        grad_weight(dy2, skip.view(R, D), R, D, D, out=dW[:, D:], ldd=2 * D)
+        return dx.view(T, S, D), dskip.view(T, S, D), dW, None
+
+
+# ---------------------------------------------------------------------------------------------------- stem / head
+class StemLinear(Function):
+    """proj_in(x) + cond_proj_in(cond) as ONE K = 2*Cp GEMM over the packed [w | cond] operand (e2_tts.py:1267-1277);
+    with w_cond=None it is the DurationPredictor's single proj_in (:1057)."""
+
+    @staticmethod
+    def forward(ctx, A, w_in, b_in, w_cond, b_cond, wpack):
+        T, Kp = A.shape
+        D = wpack.shape[0]
+        bias = b_in + b_cond if b_cond is not None else b_in
+        h = gemm(A, wpack, T, D, Kp, bias=bias)
+        ctx.save_for_backward(A)
+        ctx.meta = (D, w_in.shape[1], w_cond is not None)
+        return h
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_h):
+        (A,) = ctx.saved_tensors
+        D, C, has_cond = ctx.meta
+        T, Kp = A.shape
+        d_h = _c(d_h)
+        dWp = grad_weight(d_h, A, T, D, Kp)
+        db = colsum(d_h, T, D, D)
+        half = Kp // 2
+        return None, dWp[:, :C], db, (dWp[:, half:half + C] if has_cond else None), (db if has_cond else None), None
+
+
+class Assemble(Function):
+    """+ abs_pos, register prepend, expand to S residual streams (e2_tts.py:760-771, 800-801, 818-821). h bf16 [B*N, D]."""
+
+    @staticmethod
+    def forward(ctx, h, abs_pos, registers, B, N, S):
+        D = h.shape[1]
+        R = registers.shape[0]
+        out = torch.empty((B * (R + N), S, D), device=h.device, dtype=BF16)
+        a = lib.make_args('b200_assemble_args', h=h, abs_pos=abs_pos, registers=registers, out=out, B=B, N=N, R=R, D=D, S=S)
+        lib.call('b200_assemble_fwd', a, _stream())
+        ctx.save_for_backward(registers)
+        ctx.meta = (B, N, S, D, abs_pos.shape[0] if abs_pos is not None else 0)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        (registers,) = ctx.saved_tensors
+        B, N, S, D, max_len = ctx.meta
+        R = registers.shape[0]
+        dev = registers.device
+        d_h = torch.empty((B * N, D), device=dev, dtype=BF16)
+        d_abs = torch.zeros((max_len, D), device=dev, dtype=F32) if max_len else None
+        d_reg = torch.empty((R, D), device=dev, dtype=F32)
+        a = lib.make_args('b200_assemble_args', h=d_h, registers=registers, d_out=_c(d_out), d_h=d_h, d_abs_pos=d_abs, d_registers=d_reg,
+                          B=B, N=N, R=R, D=D, S=S)
+        lib.call('b200_assemble_bwd', a, _stream())
+        return d_h, d_abs, d_reg, None, None, None
+
+
+class TextStem(Function):
+    """CharacterEmbed gather + text register prepend + stream expand (e2_tts.py:400-412, 800-801, 821)."""
+
+    @staticmethod
+    def forward(ctx, ids, emb, registers, B, N, S):
+        D = emb.shape[1]
+        R = registers.shape[0]
+        out = torch.empty((B * (R + N), S, D), device=emb.device, dtype=BF16)
+        a = lib.make_args('b200_assemble_args', ids=ids, emb=emb, registers=registers, out=out, B=B, N=N, R=R, D=D, S=S)
+        lib.call('b200_assemble_fwd', a, _stream())
+        ctx.save_for_backward(ids, emb, registers)
+        ctx.meta = (B, N, S)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        ids, emb, registers = ctx.saved_tensors
+        B, N, S = ctx.meta
+        V, D = emb.shape
+        R = registers.shape[0]
+        dev = emb.device
+        d_tok = torch.empty((B * N, D), device=dev, dtype=F32)
+        d_reg = torch.empty((R, D), device=dev, dtype=F32)
+        a = lib.make_args('b200_assemble_args', ids=ids, emb=emb, registers=registers, d_out=_c(d_out), d_tok=d_tok, d_registers=d_reg,
+                          B=B, N=N, R=R, D=D, S=S)
+        lib.call('b200_assemble_bwd', a, _stream())
+        d_emb = torch.empty_like(emb)
+        lib.call('b200_embed_bwd', d_tok, ids, d_emb, B * N, D, V, _stream())
+        return None, d_emb, d_reg, None, None, None
+
+
+class FinalNorm(Function):
+    """drop registers -> sum residual streams -> final RMSNorm (e2_tts.py:943-952). -> bf16 [B*N, D]"""
+
+    @staticmethod
+    def forward(ctx, xres, g, B, N, R):
+        T, S, D = xres.shape
+        y = torch.empty((B * N, D), device=xres.device, dtype=BF16)
+        a = lib.make_args('b200_final_norm_args', xres=xres, g=g, y=y, B=B, N=N, R=R, D=D, S=S)
+        lib.call('b200_final_norm_fwd', a, _stream())
+        ctx.save_for_backward(xres, g)
+        ctx.meta = (B, N, R)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xres, g = ctx.saved_tensors
+        B, N, R = ctx.meta
+        T, S, D = xres.shape
+        d_xres = torch.empty_like(xres)
+        g_g = torch.zeros_like(g)
+        a = lib.make_args('b200_final_norm_args', xres=xres, g=g, dy=_c(dy), d_xres=d_xres, g_g=g_g, B=B, N=N, R=R, D=D, S=S)
+        lib.call('b200_final_norm_bwd', a, _stream())
+        return d_xres, g_g, None, None, None
+
+
+class PredHead(Function):
+    """to_pred Linear(d -> C) with fp32 output (e2_tts.py:1214, 1296)."""
+
+    @staticmethod
+    def forward(ctx, y, w, b, wpack):
+        T, D = y.shape
+        C = w.shape[0]
+        pred = gemm(y, wpack, T, C, D, bias=b, out_fp32=True, ldd=C)
+        ctx.save_for_backward(y, wpack)
+        ctx.C = C
+        return pred
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dpred):
+        y, wpack = ctx.saved_tensors
+        T, D = y.shape
+        C = ctx.C
+        ldp = (C + 7) // 8 * 8
+        dp = torch.empty((T, ldp), device=y.device, dtype=BF16)
+        lib.call('b200_cast_rows', _c(dpred), dp, T, C, ldp, _stream())
+        return PredHead._bwd_from_bf16(dp, ldp, y, wpack, T, D, C)
+
+    @staticmethod
+    def _bwd_from_bf16(dp, ldp, y, wpack, T, D, C):
+        dy = gemm(dp, wpack, T, D, C, lda=ldp, ldb=D, b_mn=True)
+        dW = grad_weight(dp, y, T, C, D, ldy=ldp)
+        db = colsum(dp, T, C, ldp)
+        return dy, dW, db, None
+
+
+class FlowLossHead(Function):
+    """to_pred + masked-MSE flow-matching loss fused at the output stage (e2_tts.py:1296, 1535, 1580-1582, 1595).
+    Returns (loss, pred fp32 [B,N,C], pred_data = x0 + pred); only `loss` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, y, w, b, wpack, x1, x0, span):
+        T, D = y.shape
+        C = w.shape[0]
+        pred = gemm(y, wpack, T, C, D, bias=b, out_fp32=True, ldd=C)
+        sums = torch.empty(2, device=y.device, dtype=F32)
+        loss = torch.empty((), device=y.device, dtype=F32)
+        pred_data = torch.empty_like(pred)
+        a = lib.make_args('b200_flow_loss_args', pred=pred, x1=x1, x0=x0, span=span, sums=sums, loss=loss, pred_data=pred_data, rows=T, C=C)
+        lib.call('b200_flow_loss_fwd', a, _stream())
+        ctx.save_for_backward(y, wpack, pred, x1, x0, span, sums)
+        ctx.C = C
+        ctx.mark_non_differentiable(pred, pred_data)
+        return loss, pred, pred_data
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloss, _dpred, _dpd):
+        y, wpack, pred, x1, x0, span, sums = ctx.saved_tensors
+        T, D = y.shape
+        C = ctx.C
+        ldp = (C + 7) // 8 * 8
+        dp = torch.empty((T, ldp), device=y.device, dtype=BF16)
+        a = lib.make_args('b200_flow_loss_args', pred=pred, x1=x1, x0=x0, span=span, sums=sums, dloss=_c(dloss.to(F32)), dpred=dp, ldp=ldp,
+                          rows=T, C=C)
+        lib.call('b200_flow_loss_bwd', a, _stream())
+        dy, dW, db, _ = PredHead._bwd_from_bf16(dp, ldp, y, wpack, T, D, C)
+        return dy, dW, db, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------- conditioning path
+class SmallLinear(Function):
+    """fp32 small-batch linear + activation (time_cond_mlp e2_tts.py:621-625; batched to_gamma projections A.1/:346-351;
+    HLGaussLayer head A.6). seg_major=True returns [N/seg, B, seg] so each seg block is a contiguous [B, seg] matrix."""
+
+    @staticmethod
+    def forward(ctx, X, W, bias, act, seg, seg_major):
+        Bn, K = X.shape
+        N = W.shape[0]
+        shape = (N // seg, Bn, seg) if seg_major else (Bn, N)
+        Z = torch.empty(shape, device=X.device, dtype=F32)
+        Y = torch.empty(shape, device=X.device, dtype=F32)
+        a = lib.make_args('b200_small_linear_args', X=X, W=W, bias=bias, Z=Z, Y=Y, B=Bn, N=N, K=K, act=act, seg=seg, seg_major=int(seg_major))
+        lib.call('b200_small_linear_fwd', a, _stream())
+        ctx.save_for_backward(X, W, Z)
+        ctx.meta = (act, seg, seg_major, bias is not None)
+        return Y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dY):
+        X, W, Z = ctx.saved_tensors
+        act, seg, seg_major, has_bias = ctx.meta
+        Bn, K = X.shape
+        N = W.shape[0]
+        dZ = torch.empty_like(Z)
+        dX = torch.empty_like(X)
+        dW = torch.empty_like(W)
+        db = torch.empty(N, device=X.device, dtype=F32)
+        a = lib.make_args('b200_small_linear_args', X=X, W=W, Z=Z, dY=_c(dY), dZ=dZ, dX=dX, dW=dW, dbias=db, B=Bn, N=N, K=K, act=act, seg=seg,
+                          seg_major=int(seg_major))
+        lib.call('b200_small_linear_bwd', a, _stream())
+        return dX, dW, db if has_bias else None, None, None, None
+
+
+def fourier_embed(times, weights):
+    """RandomFourierEmbed (e2_tts.py:355-364); `weights` is a buffer, times carries no gradient on the path."""
+    Bn, half = times.shape[0], weights.shape[0]
+    out = torch.empty((Bn, 2 * half + 1), device=times.device, dtype=F32)
+    lib.call('b200_fourier_embed', times, weights, out, Bn, half, _stream())
+    return out
+
+
+class MaskedMean(Function):
+    """maybe_masked_mean (e2_tts.py:212-224) over bf16 [B, N, D] -> fp32 [B, D]."""
+
+    @staticmethod
+    def forward(ctx, x, mask, B, N):
+        D = x.shape[-1]
+        out = torch.empty((B, D), device=x.device, dtype=F32)
+        lib.call('b200_masked_mean_fwd', x, mask, out, B, N, D, _stream())
+        ctx.save_for_backward(mask)
+        ctx.meta = (B, N, D)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (mask,) = ctx.saved_tensors
+        B, N, D = ctx.meta
+        dx = torch.empty((B * N, D), device=dout.device, dtype=BF16)
+        lib.call('b200_masked_mean_bwd', _c(dout), mask, dx, B, N, D, _stream())
+        return dx, None, None, None
+
+
+def stem_prepare(B, N, C, Cp, *, x1=None, x0=None, times=None, span=None, x_in=None, cond_in=None, want_cond=False):
+    """Flow-matching input stage (e2_tts.py:1519-1543): builds the bf16 GEMM operand [w | cond] (2*Cp columns)."""
+    dev = (x1 if x1 is not None else x_in).device
+    A = torch.empty((B * N, 2 * Cp), device=dev, dtype=BF16)
+    cond_out = torch.empty((B, N, C), device=dev, dtype=F32) if want_cond else None
+    a = lib.make_args('b200_stem_args', x1=x1, x0=x0, times=times, span=span, x_in=x_in, cond_in=cond_in, A=A, cond_out=cond_out,
+                      B=B, N=N, C=C, Cp=Cp)
+    lib.call('b200_stem_prepare', a, _stream())
+    return A, cond_out
+
+
+class CondPack(Function):
+    """Pack every per-layer to_gamma weight (AdaptiveRMSNorm A.1, AdaLNZero e2_tts.py:341) into one fp32 [4L*d, d] matrix
+    and the AdaLNZero biases into the odd d-wide segments of one [4L*d] vector (one launch of the pack kernel);
+    backward hands each parameter its slice of the packed gradients."""
+
+    @staticmethod
+    def forward(ctx, run_pack, W_out, b_out, d, n_w, *params):
+        run_pack()
+        ctx.meta = (d, n_w, len(params) - n_w)
+        return W_out, b_out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dW, db):
+        d, n_w, n_b = ctx.meta
+        gw = [dW[j * d:(j + 1) * d] if dW is not None else None for j in range(n_w)]
+        gb = [db[(2 * m + 1) * d:(2 * m + 2) * d] if db is not None else None for m in range(n_b)]
+        return (None, None, None, None, None, *gw, *gb)
+
+
+class CastRows(Function):
+    """fp32 [rows, cols] -> bf16 (generic Transformer.forward entry, e2_tts.py:731)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        rows, cols = x.shape
+        ctx.dtype = x.dtype
+        return cast_rows(x.to(F32), rows, cols, cols)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype)
+
+
+def cast_rows(src_f32, rows, cols, ld):
+    out = torch.empty((rows, ld), device=src_f32.device, dtype=BF16)
+    lib.call('b200_cast_rows', _c(src_f32), out, rows, cols, ld, _stream())
+    return out
+
+
+def axpy(y, f, a):
+    """y + a * f (fp32), the fixed-grid ODE update of E2TTS.sample (e2_tts.py:1421)."""
+    out = torch.empty_like(y)
+    lib.call('b200_axpy', _c(y), _c(f), float(a), out, y.numel(), _stream())
+    return out
+
+
+def cfg_combine(pred, null_pred, strength, remove_parallel, keep_frac):
+    """CFG + APG projection (e2_tts.py:1323-1330)."""
+    B = pred.shape[0]
+    pred, null_pred = _c(pred.to(F32)), _c(null_pred.to(F32))
+    ws = torch.empty(2 * B, device=pred.device, dtype=torch.float64)
+    out = torch.empty_like(pred)
+    lib.call('b200_cfg_combine', pred, null_pred, ws, out, B, pred.numel() // B, strength, int(remove_parallel), keep_frac, _stream())
+    return out
+
+
+def melspec(wave, window, fb, n_fft, hop):
+    """MelSpec front-end (e2_tts.py:248-290): fp32 [B, nw] -> [B, n_mels, frames]."""
+    B, nw = wave.shape
+    n_mels = fb.shape[1]
+    out = torch.empty((B, n_mels, 1 + nw // hop), device=wave.device, dtype=F32)
+    lib.call('b200_melspec', wave, _c(window), _c(fb), out, B, nw, n_fft, hop, n_mels, _stream())
+    return out

@@ -67,6 +67,205 @@ typedef struct {
 } b200_gemm_args;
 int b200_gemm(const b200_gemm_args* a, b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused softclamped attention, head_dim 64 (x-transformers Attend as configured by the reference: A.4
+ * steps 4-5, call sites e2_tts.py:875, :911). q,k,v,o: bf16 [B,H,Np,64]; keymask: u8 [B,Np] (1 = keep) or
+ * NULL; gate: fp32 [B*Np, H] = sigmoid(to_v_head_gate(x)) or NULL; og: bf16 [B*Np, H*64] gated, merged
+ * heads (the input of to_out); lse: fp32 [B,H,Np] (natural log of the softmax denominator of the CLAMPED
+ * logits). Dropout on P uses a counter-based hash of (seed, b,h,i,j) that backward recomputes.
+ */
+typedef struct {
+    const void *q, *k, *v;
+    const uint8_t* keymask;
+    const float* gate;
+    void *o, *og;
+    float* lse;
+    int32_t B, H, Np, dim_head;
+    float scale, softclamp, dropout_p;
+    uint64_t seed;
+} b200_attn_fwd_args;
+int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream);
+
+/* backward: d_og bf16 [B*Np, H*64] -> dq,dk,dv bf16 [B,H,Np,64], d_gate fp32 [B*Np,H] (grad wrt the sigmoid
+ * gate VALUE; may be NULL). ws_dO (bf16 [B,H,Np,64]) and ws_delta (fp32 [B,H,Np]) are caller workspaces. */
+typedef struct {
+    const void *q, *k, *v, *o, *d_og;
+    const uint8_t* keymask;
+    const float *gate, *lse;
+    void* ws_dO; float* ws_delta;
+    float* d_gate;
+    void *dq, *dk, *dv;
+    int32_t B, H, Np, dim_head;
+    float scale, softclamp, dropout_p;
+    uint64_t seed;
+} b200_attn_bwd_args;
+int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hyper-connections (A.5; e2_tts.py:607, 673-678, 709-713, 870-882, 900-939), S = 4 residual streams held
+ * as bf16 [T, S, D] (token-major), fused with the consumer's RMSNorm / AdaptiveRMSNorm (A.1; :875,881,908,937).
+ * width fwd : xres -> branch [T,D] (normalised when norm_mode != 0), res_out [T,S,D], beta_out [T,S] fp32.
+ *   norm_mode 0: none (conv sub-block); 1: * sqrt(D)/||.|| * norm_gain[D]; 2: * norm_gain[t / rows_per_batch, D]
+ *   (norm_gain = 1 + to_gamma(cond), produced by b200_small_linear).
+ * width bwd : d_branch [T,D], d_res [T,S,D], d_beta [T,S] -> d_xres [T,S,D]; parameter gradients are ADDED
+ *   (fp32 atomics) into the g_* buffers, which the caller zero-initialises: g_norm_gain is [D] (mode 1) or
+ *   [T/rows_per_batch, D] (mode 2).
+ */
+typedef struct {
+    const void* xres;
+    const float *norm_gamma, *dynamic_alpha_fn, *dynamic_alpha_scale, *static_alpha, *dynamic_beta_fn, *dynamic_beta_scale, *static_beta;
+    int32_t norm_mode; const float* norm_gain; int32_t rows_per_batch;
+    int32_t T, D, num_streams;
+    void *branch, *res_out; float* beta_out;                 /* forward outputs */
+    const void *d_branch, *d_res; const float* d_beta;       /* backward inputs */
+    void* d_xres;
+    float *g_norm_gamma, *g_dynamic_alpha_fn, *g_dynamic_alpha_scale, *g_static_alpha, *g_dynamic_beta_fn, *g_dynamic_beta_scale,
+        *g_static_beta, *g_norm_gain;
+} b200_hc_width_args;
+int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stream);
+int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stream);
+
+/* depth: out[t,s,:] = res[t,s,:] + beta[t,s] * y[t,:] (out may alias res);
+ * bwd: d_y[t,:] = sum_s beta[t,s] d_out[t,s,:], d_beta[t,s] = <d_out[t,s,:], y[t,:]> (d_res == d_out). */
+typedef struct {
+    const void *res, *y; const float* beta; void* out;
+    const void* d_out; void* d_y; float* d_beta;
+    int32_t T, D, num_streams;
+} b200_hc_depth_args;
+int b200_hc_depth_fwd(const b200_hc_depth_args* a, b200_stream_t stream);
+int b200_hc_depth_bwd(const b200_hc_depth_args* a, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight packing: ONE launch casts every fp32 nn.Parameter that feeds a tensor-core GEMM into its bf16 slot
+ * (reference keeps fp32 nn.Linear weights; names per SURVEY Appendix B). `descs_dev` is a DEVICE array.
+ *   mode 0: dst[(row_off + r) * ld_dst + col_off + c] = src[r * cols + c]
+ *   mode 1: GEGLU interleave (A.2 `proj` weight/bias: rows [u(inner); gate(inner)] -> per 64 hidden units
+ *           [u(64) | gate(64)]), so one 128-column GEMM tile holds both halves of the same hidden units.
+ *   cols, col_off, ld_dst must be multiples of 4.  out_fp32 != 0 keeps fp32 (packed biases).
+ */
+typedef struct {
+    const float* src; void* dst;
+    int32_t rows, cols, ld_dst, row_off, col_off, mode, out_fp32, _pad;
+} b200_pack_desc;
+int b200_pack_weights(const b200_pack_desc* descs_dev, int32_t n, b200_stream_t stream);
+
+/* Flow-matching stem (e2_tts.py:1519-1543 and the operand of proj_in/cond_proj_in :1267-1277):
+ *   training: A[row] = [ (1-t) x0 + t x1 | pad | where(span, 0, x1) | pad ] (bf16, 2*Cp columns), cond_out fp32
+ *   direct  : x_in / cond_in given (sampling, transformer_with_pred_head).  Cp = C rounded up to 64. */
+typedef struct {
+    const float *x1, *x0, *times; const uint8_t* span;   /* training mode */
+    const float *x_in, *cond_in;                          /* direct mode (x1 == NULL) */
+    void* A; float* cond_out;
+    int32_t B, N, C, Cp;
+} b200_stem_args;
+int b200_stem_prepare(const b200_stem_args* a, b200_stream_t stream);
+
+/* Residual-stream assembly (e2_tts.py:760-771, 800-801, 818-821; CharacterEmbed :400-412):
+ *   out[b, r, s, :]     = registers[r, :]                         r < R
+ *   out[b, R+n, s, :]   = (h[b*N+n, :] | emb[ids[b,n], :]) + abs_pos[n, :]     for every stream s
+ * bwd: d_h (bf16) or d_tok (fp32, for b200_embed_bwd), d_abs_pos [N,D], d_registers [R,D] (all overwritten). */
+typedef struct {
+    const void* h; const int32_t* ids; const float *emb, *abs_pos, *registers;
+    void* out;
+    const void* d_out; void* d_h; float *d_tok, *d_abs_pos, *d_registers;
+    int32_t B, N, R, D, S;
+} b200_assemble_args;
+int b200_assemble_fwd(const b200_assemble_args* a, b200_stream_t stream);
+int b200_assemble_bwd(const b200_assemble_args* a, b200_stream_t stream);
+int b200_embed_bwd(const float* d_tok, const int32_t* ids, float* d_emb, int32_t ntok, int32_t D, int32_t vocab, b200_stream_t stream);
+
+/* Rotary table cos/sin [Np, 32] for dim_head 64, positions 0..Np-1 including registers (A.3; e2_tts.py:793). */
+int b200_rotary_table(float* cos_out, float* sin_out, int32_t Np, int32_t dim_head, b200_stream_t stream);
+
+/* Post-processing of the fused [q|k|v|gate|mix] projection (A.4 steps 1-3, 5): interleaved-pair rotary on
+ * q,k; v = lerp(v_first, v, sigmoid(mix)) when v_first != NULL; gate = sigmoid(gate_logit + bias) fp32 [T,H];
+ * q,k,v written as [B,H,Np,64]. bwd inverts all of it into d_qkvg (same packed layout) and d_vfirst. */
+typedef struct {
+    const void* qkvg; int32_t ld;
+    const float *gate_bias, *mix_bias, *rot_cos, *rot_sin;
+    const void* v_first;
+    void *q, *k, *v; float* gate;
+    const void *dq, *dk, *dv; const float* d_gate;
+    void *d_qkvg, *d_vfirst;
+    int32_t B, H, Np, dim_head;
+} b200_qkv_post_args;
+int b200_qkv_post_fwd(const b200_qkv_post_args* a, b200_stream_t stream);
+int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stream);
+
+/* GEGLU backward on the packed pre-activations saved by b200_gemm(geglu=1) (A.2). */
+int b200_geglu_bwd(const void* dh, const void* ug, void* dug, int64_t T, int32_t inner, float dropout_p, uint64_t seed, b200_stream_t stream);
+/* out[n] += sum_t X[t,n] (bf16 X, fp32 out; caller zeroes out) — nn.Linear bias gradients. */
+int b200_colsum(const void* X, int64_t T, int32_t ncols, int32_t ld, float* out, b200_stream_t stream);
+
+/* Drop registers, sum the S streams, final RMSNorm (e2_tts.py:943-952). y bf16 [B*N, D]. */
+typedef struct {
+    const void* xres; const float* g; void* y;
+    const void* dy; void* d_xres; float* g_g;   /* bwd: d_xres [B,R+N,S,D] fully written, g_g accumulated */
+    int32_t B, N, R, D, S;
+} b200_final_norm_args;
+int b200_final_norm_fwd(const b200_final_norm_args* a, b200_stream_t stream);
+int b200_final_norm_bwd(const b200_final_norm_args* a, b200_stream_t stream);
+
+/* Masked-MSE flow-matching loss (e2_tts.py:1535, 1580-1582, 1595) without the boolean gather / host sync:
+ * loss = sum_{span}(pred - (x1 - x0))^2 / (count * C); pred_data = x0 + pred. sums is a 2-float workspace that
+ * must be kept for backward; dpred is bf16 [rows, ldp] (pad columns zero) = dloss * 2 (pred - flow) / (count*C). */
+typedef struct {
+    const float *pred, *x1, *x0; const uint8_t* span;
+    float *sums, *loss, *pred_data;
+    const float* dloss; void* dpred; int32_t ldp;
+    int64_t rows; int32_t C;
+} b200_flow_loss_args;
+int b200_flow_loss_fwd(const b200_flow_loss_args* a, b200_stream_t stream);
+int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t stream);
+
+/* Backward of the GEMM epilogue y = rowmask * colscale[b,:] * z (AdaLNZero gate :346-351, A.4 step 6):
+ * dz = dy * mask * cs (bf16), d_cs[b,:] += sum_rows dy * y / cs (fp32, caller zeroes). cs/mask may be NULL. */
+int b200_rowgate_bwd(const void* dy, const void* y, const float* cs, const uint8_t* mask, void* dz, float* d_cs,
+                     int32_t B, int32_t rows_per_batch, int32_t D, b200_stream_t stream);
+int b200_cast_rows(const float* src, void* dst, int64_t rows, int32_t cols, int32_t ld, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small-batch fp32 linear (time conditioning path: time_cond_mlp e2_tts.py:621-625, all AdaptiveRMSNorm /
+ * AdaLNZero to_gamma projections A.1 / :346-351 batched into one call, HLGaussLayer head A.6):
+ *   Z[b,n] = sum_k X[b,k] W[n,k] + bias[n];  Y = act(Z).  B <= 64 rows.
+ *   act: 0 identity, 1 SiLU, 2 sigmoid, 3 (1 + z), 4 softplus, 5 alternating per `seg` outputs: (1+z), sigmoid
+ * bwd: dX (overwritten), dW, dbias (overwritten) from dY, Z. */
+typedef struct {
+    const float *X, *W, *bias; float *Z, *Y;
+    const float* dY; float *dZ, *dX, *dW, *dbias;
+    int32_t B, N, K, act, seg;
+    int32_t seg_major;   /* != 0: Y/Z/dY/dZ are laid out [N/seg][B][seg] so every `seg`-wide output block is a contiguous [B, seg] matrix */
+} b200_small_linear_args;
+int b200_small_linear_fwd(const b200_small_linear_args* a, b200_stream_t stream);
+int b200_small_linear_bwd(const b200_small_linear_args* a, b200_stream_t stream);
+/* RandomFourierEmbed (e2_tts.py:355-364): out[b] = [t, sin(2 pi t w), cos(2 pi t w)], out [B, 2*half+1] */
+int b200_fourier_embed(const float* times, const float* weights, float* out, int32_t B, int32_t half, b200_stream_t stream);
+
+/* Masked depthwise conv k (odd, <= 31) + SiLU (DepthwiseConv e2_tts.py:295-328) on bf16 [B, Np, D]:
+ *   y = m * silu(conv1d_depthwise(m * x) + bias), weight fp32 [D, k]. bwd recomputes the pre-activation;
+ *   dweight/dbias are ADDED into zero-initialised fp32 buffers. */
+typedef struct {
+    const void* x; const uint8_t* mask; const float *weight, *bias; void* y;
+    const void* dy; void* dx; float *dweight, *dbias;
+    int32_t B, Np, D, ksize;
+} b200_dwconv_args;
+int b200_dwconv_fwd(const b200_dwconv_args* a, b200_stream_t stream);
+int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream);
+
+/* Masked mean over the sequence (maybe_masked_mean e2_tts.py:212-224): x bf16 [B,N,D] -> out fp32 [B,D]; bwd. */
+int b200_masked_mean_fwd(const void* x, const uint8_t* mask, float* out, int32_t B, int32_t N, int32_t D, b200_stream_t stream);
+int b200_masked_mean_bwd(const float* dout, const uint8_t* mask, void* dx, int32_t B, int32_t N, int32_t D, b200_stream_t stream);
+
+/* Fixed-grid ODE update out = y + a * f (torchdiffeq midpoint/euler as called at e2_tts.py:1421). */
+int b200_axpy(const float* y, const float* f, float a, float* out, int64_t n, b200_stream_t stream);
+/* Classifier-free guidance with the APG orthogonal projection in fp64 (e2_tts.py:1323-1330, project :113-124):
+ * out = pred + (orth + par * keep) * strength per sample over all n*d elements. ws_red: 2*B doubles. */
+int b200_cfg_combine(const float* pred, const float* null_pred, double* ws_red, float* out, int32_t B, int64_t per_sample,
+                     float cfg_strength, int32_t remove_parallel, float keep_parallel_frac, b200_stream_t stream);
+/* MelSpec (e2_tts.py:248-290): wave fp32 [B, nw] -> log-mel fp32 [B, n_mels, 1 + nw/hop]; window [n_fft], fb [n_fft/2+1, n_mels]. */
+int b200_melspec(const float* wave, const float* window, const float* fb, float* out, int32_t B, int32_t nw, int32_t n_fft,
+                 int32_t hop, int32_t n_mels, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/b200_e2tts.h declares (no compute calls)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope='module')
+def pkg():
+    so = os.path.join(ROOT, 'e2-tts-pytorch_b200', 'libb200e2tts.so')
+    if not os.path.isfile(so):
+        subprocess.run(['make', '-C', os.path.join(ROOT, 'e2-tts-pytorch_b200', 'csrc'), '-j8', 'all'], check=True)
+    import e2_tts_pytorch_b200 as pkg
+    return pkg
+
+
+def test_every_declared_symbol_is_exported(pkg):
+    lib = pkg.lib.load()
+    assert len(pkg.lib.FUNCTIONS) >= 30
+    for name in pkg.lib.FUNCTIONS:
+        assert hasattr(lib, name), name
+    assert lib.b200_version() >= 100
+    assert isinstance(pkg.lib.launch_count(), int)
+
+
+def test_struct_layouts_parse(pkg):
+    for name, fields in pkg.lib.STRUCT_FIELDS.items():
+        assert fields, name
+        assert ctypes.sizeof(pkg.lib.STRUCTS[name]) > 0
+    # spot check: the GEMM descriptor of the header has the documented leading fields
+    assert [f for f, _ in pkg.lib.STRUCT_FIELDS['b200_gemm_args']][:5] == ['A', 'lda', 'A2', 'lda2', 'K1']
+
+
+def test_argument_validation_without_gpu(pkg):
+    """Entry points reject bad arguments before touching the device (error string through b200_last_error)."""
+    a = pkg.lib.make_args('b200_gemm_args', M=0, N=0, K=0)
+    with pytest.raises(RuntimeError, match='gemm'):
+        pkg.lib.call('b200_gemm', a, None)
+    a = pkg.lib.make_args('b200_hc_width_args', num_streams=3)
+    with pytest.raises(RuntimeError):
+        pkg.lib.call('b200_hc_width_fwd', a, None)
+
+
+def test_state_dict_is_reference_compatible(pkg):
+    import torch
+    g = torch.load(os.path.join(ROOT, 'tests', 'golden', 'e2tts_d128_L2.pt'), weights_only=False)
+    m = pkg.E2TTS(transformer=dict(dropout=0., max_seq_len=g['max_seq_len'], **g['transformer']), use_vocos=False)
+    assert set(m.state_dict().keys()) == set(g['state_dict'].keys())
+    m.load_state_dict(g['state_dict'])
+    d = torch.load(os.path.join(ROOT, 'tests', 'golden', 'duration_d128_L2.pt'), weights_only=False)
+    dp = pkg.DurationPredictor(transformer=dict(dropout=0., max_seq_len=256, **g['transformer']))
+    assert set(dp.state_dict().keys()) == set(d['state_dict'].keys())
+
+
+def test_unsupported_switches_raise(pkg):
+    with pytest.raises(NotImplementedError):
+        pkg.Transformer(dim=128, depth=2, heads=2, attn_laser=True)
+    with pytest.raises(NotImplementedError):
+        pkg.E2TTS(transformer=dict(dim=128, depth=2, heads=2), concat_cond=True, use_vocos=False)
+
+
+def test_tokenizer_and_mask_helpers(pkg):
+    import torch
+    ids = pkg.list_str_to_tensor(['Hello', 'Goodbye'])
+    assert ids.tolist() == [[72, 101, 108, 108, 111, -1, -1], [71, 111, 111, 100, 98, 121, 101]]
+    assert pkg.lens_to_mask(torch.tensor([2, 3]), 3).tolist() == [[True, True, False], [True, True, True]]
+    m = pkg.mask_from_frac_lengths(torch.tensor([10, 6]), torch.tensor([0.7, 1.0]), 10)
+    assert m.sum(-1).tolist() == [7, 6] and not m[1, 6:].any()

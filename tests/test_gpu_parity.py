@@ -50,7 +50,7 @@ def check(name, got, want, tol=LEAF_TOL):
 def test_gemm_modes(pkg):
     torch.manual_seed(0)
     ops = pkg.ops
-    M, N, K = 300, 264, 192
+    M, N, K = 304, 264, 192
     A, B = bf(torch.randn(M, K, device=dev())), bf(torch.randn(N, K, device=dev()))
     ref = A.float() @ B.float().t()
     check('nt', ops.gemm(A, B, M, N, K)[:, :N], ref, 1e-2)

@@ -109,6 +109,7 @@ struct AttnP {
     float* lse;
     int B, H, Np;
     float scale, clamp, inv_clamp, dropout_p, keep_scale;
+    unsigned int drop_thresh; int drop_stride;
     unsigned long long seed;
     // backward
     const __nv_bfloat16 *dog, *dO;
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     uint32_t aq[4][4];
     const int qrow0 = qt * AT + warp * 16 + g, qrow1 = qrow0 + 8;
-    const unsigned long long drop_base0 = (((unsigned long long)b * p.H + hh) * p.Np + qrow0) * (unsigned long long)p.Np;
-    const unsigned long long drop_base1 = drop_base0 + 8ull * p.Np;
+    const unsigned long long drop_base0 = (((unsigned long long)b * p.H + hh) * p.Np + qrow0) * (unsigned long long)p.drop_stride;
+    const unsigned long long drop_base1 = drop_base0 + 8ull * p.drop_stride;
 
     for (int kt = 0; kt < nkt; ++kt) {
         const int buf = kt & 1;
@@ -193,8 +194,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
                 l0 += p0; l1 += p1;
                 if (p.dropout_p > 0.f) {
                     const unsigned long long key = (unsigned long long)(kt * AT + nt * 8 + 2 * t + e);
-                    p0 = dropout_keep(p.seed, drop_base0 + key, p.dropout_p) ? p0 * p.keep_scale : 0.f;
-                    p1 = dropout_keep(p.seed, drop_base1 + key, p.dropout_p) ? p1 * p.keep_scale : 0.f;
+                    p0 = dropout_keep16(p.seed, drop_base0 + key, p.drop_thresh) ? p0 * p.keep_scale : 0.f;
+                    p1 = dropout_keep16(p.seed, drop_base1 + key, p.drop_thresh) ? p1 * p.keep_scale : 0.f;
                 }
                 s[nt][e] = p0; s[nt][2 + e] = p1;
             }
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnP p) {
     const int qrow0 = qt * AT + warp * 16 + g, qrow1 = qrow0 + 8;
     const float lse0 = qrow0 < p.Np ? p.lse[bh * p.Np + qrow0] : 0.f, lse1 = qrow1 < p.Np ? p.lse[bh * p.Np + qrow1] : 0.f;
     const float dl0 = qrow0 < p.Np ? p.delta[bh * p.Np + qrow0] : 0.f, dl1 = qrow1 < p.Np ? p.delta[bh * p.Np + qrow1] : 0.f;
-    const unsigned long long drop_base0 = (bh * p.Np + qrow0) * (unsigned long long)p.Np, drop_base1 = drop_base0 + 8ull * p.Np;
+    const unsigned long long drop_base0 = (bh * p.Np + qrow0) * (unsigned long long)p.drop_stride, drop_base1 = drop_base0 + 8ull * p.drop_stride;
 
     float dq[8][4];
 #pragma unroll
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnP p) {
                 float dpe = dp[nt][e];
                 if (p.dropout_p > 0.f) {
                     const unsigned long long base = (e < 2) ? drop_base0 : drop_base1;
-                    dpe = dropout_keep(p.seed, base + (unsigned long long)key, p.dropout_p) ? dpe * p.keep_scale : 0.f;
+                    dpe = dropout_keep16(p.seed, base + (unsigned long long)key, p.drop_thresh) ? dpe * p.keep_scale : 0.f;
                 }
                 s[nt][e] = pr * (dpe - dl) * (1.f - th * th) * p.scale;
             }
@@ -420,8 +421,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnP p) {
                 float dpe = dp[nt][e];
                 float prd = pr;
                 if (p.dropout_p > 0.f) {
-                    const unsigned long long idx = (bh * p.Np + (unsigned long long)qn) * (unsigned long long)p.Np + (unsigned long long)((e < 2) ? key0 : key1);
-                    const bool keep = dropout_keep(p.seed, idx, p.dropout_p);
+                    const unsigned long long idx = (bh * p.Np + (unsigned long long)qn) * (unsigned long long)p.drop_stride + (unsigned long long)((e < 2) ? key0 : key1);
+                    const bool keep = dropout_keep16(p.seed, idx, p.drop_thresh);
                     dpe = keep ? dpe * p.keep_scale : 0.f;
                     prd = keep ? pr * p.keep_scale : 0.f;
                 }
@@ -464,7 +465,10 @@ static int fill_common(AttnP& p, int B, int H, int Np, float scale, float clamp,
     B200_REQUIRE(clamp > 0.f, "attention: softclamp value must be > 0 (reference always clamps, e2_tts.py:548-551)");
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout must be in [0,1)");
     p.B = B; p.H = H; p.Np = Np; p.scale = scale; p.clamp = clamp; p.inv_clamp = 1.f / clamp;
-    p.dropout_p = dropout_p; p.keep_scale = 1.f / (1.f - dropout_p); p.seed = seed;
+    p.dropout_p = dropout_p; p.seed = seed;
+    p.drop_thresh = (unsigned int)(dropout_p * 65536.f);
+    p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
+    p.drop_stride = (Np + 1) & ~1;
     return 0;
 }
 
@@ -472,7 +476,8 @@ static int fill_common(AttnP& p, int B, int H, int Np, float scale, float clamp,
 
 using namespace b200;
 
-extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) {
+// mma.sync forward (round-1 bring-up kernel): kept as a cross-check for the tcgen05 forward in attn_tc.cu.
+extern "C" int b200_attn_fwd_legacy(const b200_attn_fwd_args* a, b200_stream_t stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     B200_REQUIRE(a && a->q && a->k && a->v && a->o && a->og && a->lse, "attn_fwd: null pointer");
     B200_REQUIRE(a->dim_head == 64, "attn_fwd: only dim_head 64 is built (got %d)", a->dim_head);

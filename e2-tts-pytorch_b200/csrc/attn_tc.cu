@@ -1,0 +1,368 @@
+// tcgen05 / TMEM / TMA flash attention FORWARD for the softclamped, key-masked, head-gated attention of the
+// E2-TTS multistream block (x-transformers Attend as configured by the reference: SURVEY A.4 steps 4-5).
+//
+// One CTA per (128-query tile, head, batch), 192 threads, warp-specialised:
+//   warp 0 lane 0 : TMA producer  — Q once, then K_j / V_j tiles (128 keys x 64) into a 2-stage smem ring
+//   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T  (tcgen05.mma 128x128x16 x4, both operands K-major) into TMEM S[j%2]
+//                                   O_j = P_j V_j  (tcgen05.mma 128x64x16 x8, A = P from smem (K-major), B = V MN-major)
+//                                   into TMEM O[j%2]; S_{j+1} is issued before O_j so the tensor pipe never waits on softmax
+//   warps 2..5    : softmax       — one query ROW per thread (tcgen05.ld 32x32b: lane == row, no shuffles):
+//                                   pass 1 row max of the raw scores, pass 2 softclamp (tanh) + exp2 + dropout,
+//                                   P_j written as bf16 into 128B-swizzled smem (the A operand of the PV MMA),
+//                                   partial O_j read back from TMEM and folded into fp32 registers with the usual
+//                                   online-softmax rescale.
+// mbarrier pipelines: q_full, k_full/v_full/kv_empty[2], s_full/s_empty[2], p_full[2], o_full/o_empty[2].
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int TQ = 128, TKV = 128, DH = 64;
+constexpr int TILE16 = 128 * 64 * 2;          // 16 KB: Q, K or V tile
+constexpr int PTILE = 128 * 128 * 2;          // 32 KB: P tile (two 64-key swizzle atoms)
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+struct AttnTcP {
+    const unsigned int* maskbits;   // [B, words] key-validity bitmask (bit set = keep), words = ceil(Np / 32) padded to a multiple of 4
+    int mask_words;
+    const float* gate;              // [B*Np, H] or null
+    __nv_bfloat16 *o, *og;
+    float* lse;
+    int B, H, Np, nkv;
+    float scale_over_clamp, clamp, dropout_p, keep_scale;
+    unsigned int drop_thresh;       // keep iff 16-bit hash >= thresh
+    int drop_stride;                // even row pitch of the dropout counter space
+    unsigned long long seed;
+};
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// key-validity bitmask: bit (n % 32) of word n / 32 is set iff key n participates (n < Np and mask[b, n] != 0)
+__global__ void attn_maskbits_kernel(const unsigned char* mask, unsigned int* bits, int B, int Np, int words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= B * words) return;
+    const int b = w / words, w0 = (w % words) * 32;
+    unsigned int v = 0;
+    for (int i = 0; i < 32; ++i) {
+        const int n = w0 + i;
+        if (n < Np && (!mask || mask[(size_t)b * Np + n])) v |= 1u << i;
+    }
+    bits[w] = v;
+}
+
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const AttnTcP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE16;          // [2]
+    uint8_t* sV = sK + 2 * TILE16;      // [2]
+    uint8_t* sP = sV + 2 * TILE16;      // [2] x 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PTILE);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* k_full = bars + 1;        // 2
+    uint64_t* v_full = bars + 3;        // 2
+    uint64_t* kv_empty = bars + 5;      // 2
+    uint64_t* s_full = bars + 7;        // 2
+    uint64_t* s_empty = bars + 9;       // 2
+    uint64_t* p_full = bars + 11;       // 2
+    uint64_t* o_full = bars + 13;       // 2
+    uint64_t* o_empty = bars + 15;      // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+    const int bh = b * p.H + hh;
+    const int q0 = qt * TQ;
+    const int nkv = p.nkv;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tO = tmem_base + 256;   // S[2] at +0/+128, O[2] at +256/+320
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            const int row_base = bh * p.Np;
+            mbar_arrive_expect_tx(q_full, TILE16);
+            tma_load_2d(sQ, &tmQ, q_full, 0, row_base + q0);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j & 1;
+                mbar_wait(&kv_empty[st], (((j >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&k_full[st], TILE16);
+                tma_load_2d(sK + st * TILE16, &tmK, &k_full[st], 0, row_base + j * TKV);
+                mbar_arrive_expect_tx(&v_full[st], TILE16);
+                tma_load_2d(sV + st * TILE16, &tmV, &v_full[st], 0, row_base + j * TKV);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- MMA issuer
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+            mbar_wait(q_full, 0);
+            const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+            for (int j = 0; j <= nkv; ++j) {
+                if (j < nkv) {
+                    const int st = j & 1;
+                    const uint32_t ph = (j >> 1) & 1;
+                    mbar_wait(&k_full[st], ph);
+                    mbar_wait(&s_empty[st], ph ^ 1);
+                    tc_fence_after();
+                    const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + st * TILE16), 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < DH / 16; ++k) umma_f16(tS + st * 128, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit(&s_full[st]);
+                }
+                if (j >= 1) {
+                    const int jj = j - 1, st = jj & 1;
+                    const uint32_t ph = (jj >> 1) & 1;
+                    mbar_wait(&p_full[st], ph);
+                    mbar_wait(&v_full[st], ph);
+                    mbar_wait(&o_empty[st], ph ^ 1);
+                    tc_fence_after();
+                    const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + st * TILE16), 128 * 128, 1024);
+                    const uint32_t pbase = smem_u32(sP + st * PTILE);
+#pragma unroll
+                    for (int k = 0; k < TKV / 16; ++k) {
+                        const uint64_t pdesc = make_smem_desc_sw128(pbase + (k >> 2) * TILE16 + (k & 3) * 32, 0, 1024);
+                        umma_f16(tO + st * 64, pdesc, vdesc + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&o_full[st]);
+                    umma_commit(&kv_empty[st]);
+                }
+            }
+        }
+    } else {
+        // -------------------------------------------------------------------- softmax warps (row per thread)
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const int qi = q0 + row;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words;
+        const unsigned long long drop_row = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride;
+        float o_acc[DH];
+#pragma unroll
+        for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, m_ref = -INFINITY;
+        float m_hist0 = -INFINITY, m_hist1 = -INFINITY;
+
+        auto fold = [&](int t) {   // fold partial O of tile t (buffer t & 1) into o_acc
+            const int st = t & 1;
+            mbar_wait(&o_full[st], (t >> 1) & 1);
+            tc_fence_after();
+            const float mt = st ? m_hist1 : m_hist0;
+            const float c = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - mt) * LOG2E_F);
+            m_ref = mt;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                uint32_t r[32];
+                tmem_ld32(tO + st * 64 + h2 * 32 + lane_off, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[h2 * 32 + i] = o_acc[h2 * 32 + i] * c + __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[st]);
+        };
+
+        for (int j = 0; j < nkv; ++j) {
+            const int st = j & 1;
+            const uint4 mw = *reinterpret_cast<const uint4*>(mb + j * 4);
+            const unsigned int mbits[4] = {mw.x, mw.y, mw.z, mw.w};
+            mbar_wait(&s_full[st], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ts = tS + st * 128 + lane_off;
+            // pass 1: row max of the raw scores over the valid keys (tanh is monotone: clamp(max) == max(clamp))
+            float rmax = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(ts + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) rmax = ((mbits[c] >> i) & 1u) ? fmaxf(rmax, __uint_as_float(r[i])) : rmax;
+            }
+            const float m_tile = (rmax == -INFINITY) ? -INFINITY : p.clamp * tanh_approx(rmax * p.scale_over_clamp);
+            const float m_new = fmaxf(m_run, m_tile);
+            const float ms = (m_new == -INFINITY) ? 0.f : m_new;
+            l_run *= (m_run == -INFINITY) ? 0.f : ex2_approx((m_run - ms) * LOG2E_F);
+            m_run = m_new;
+            // the P buffer (and O buffer) of tile j-2 must have been consumed by its PV MMA: fold that partial now
+            if (j >= 2) fold(j - 2);
+            if (st) m_hist1 = ms; else m_hist0 = ms;
+            // pass 2: probabilities -> bf16 P tile in swizzled smem
+            uint8_t* pdst = sP + st * PTILE + row * 128;
+            const float msl = ms * LOG2E_F;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(ts + c * 32, r);
+                tmem_ld_wait();
+                float pv[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float sc = p.clamp * tanh_approx(__uint_as_float(r[i]) * p.scale_over_clamp);
+                    float e = ex2_approx(sc * LOG2E_F - msl);
+                    e = ((mbits[c] >> i) & 1u) ? e : 0.f;
+                    l_run += e;
+                    pv[i] = e;
+                }
+                if (p.dropout_p > 0.f) {
+                    const unsigned long long kbase = drop_row + (unsigned long long)(j * TKV + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const uint32_t h = hash_u32(p.seed, (kbase + i) >> 1);
+                        pv[i] = ((h & 0xffffu) >= p.drop_thresh) ? pv[i] * p.keep_scale : 0.f;
+                        pv[i + 1] = ((h >> 16) >= p.drop_thresh) ? pv[i + 1] * p.keep_scale : 0.f;
+                    }
+                }
+                uint8_t* atom = pdst + (c >> 1) * TILE16;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int chunk = (c & 1) * 4 + g;
+                    *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+                        make_uint4(pack_bf16(pv[g * 8], pv[g * 8 + 1]), pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]),
+                                   pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]));
+                }
+            }
+            tc_fence_before();          // TMEM S reads are complete
+            fence_proxy_async();        // make the generic-proxy smem writes of P visible to the tensor-core (async) proxy
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&s_empty[st]); mbar_arrive(&p_full[st]); }
+        }
+        if (nkv >= 2) fold(nkv - 2);
+        fold(nkv - 1);
+        // ---- epilogue: normalise, write O (ungated), Og (gated, head-merged) and LSE
+        if (qi < p.Np) {
+            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+            const float gt = p.gate ? p.gate[((size_t)b * p.Np + qi) * p.H + hh] : 1.f;
+            __nv_bfloat16* orow = p.o + ((size_t)bh * p.Np + qi) * DH;
+            __nv_bfloat16* grow = p.og + ((size_t)b * p.Np + qi) * (size_t)(p.H * DH) + hh * DH;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = o_acc[g * 8 + i] * inv;
+                const uint4 u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                *reinterpret_cast<uint4*>(orow + g * 8) = u;
+                // gate the bf16-rounded output (what the backward pass sees) for consistency
+                *reinterpret_cast<uint4*>(grow + g * 8) =
+                    make_uint4(pack_bf16(bf16_lo(u.x) * gt, bf16_hi(u.x) * gt), pack_bf16(bf16_lo(u.y) * gt, bf16_hi(u.y) * gt),
+                               pack_bf16(bf16_lo(u.z) * gt, bf16_hi(u.z) * gt), pack_bf16(bf16_lo(u.w) * gt, bf16_hi(u.w) * gt));
+            }
+            p.lse[(size_t)bh * p.Np + qi] = m_run + logf(l_run);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_head_map(CUtensorMap* m, const void* ptr, long long rows) {
+    static PFN_encodeTiled2 enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<PFN_encodeTiled2>(fn);
+    }
+    B200_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "attention: operand not 16-byte aligned");
+    cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {128};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" size_t b200_attn_workspace_bytes(int32_t B, int32_t Np) {
+    const int words = ((Np + 127) / 128) * 4;
+    return (size_t)B * words * sizeof(unsigned int);
+}
+
+extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B200_REQUIRE(a && a->q && a->k && a->v && a->o && a->og && a->lse && a->ws_maskbits, "attn_fwd: null pointer");
+    B200_REQUIRE(a->dim_head == 64, "attn_fwd: only dim_head 64 is built (got %d)", a->dim_head);
+    B200_REQUIRE(a->B > 0 && a->H > 0 && a->Np > 0 && a->B <= 65535 && a->H <= 65535, "attn_fwd: bad shape");
+    B200_REQUIRE(a->softclamp > 0.f, "attn_fwd: softclamp value must be > 0 (the reference always clamps, e2_tts.py:548-551)");
+    B200_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "attn_fwd: dropout must be in [0,1)");
+    AttnTcP p{};
+    p.nkv = (a->Np + TKV - 1) / TKV;
+    p.mask_words = p.nkv * 4;
+    p.maskbits = reinterpret_cast<const unsigned int*>(a->ws_maskbits);
+    {
+        const int total = a->B * p.mask_words;
+        attn_maskbits_kernel<<<(total + 127) / 128, 128, 0, st>>>(a->keymask, reinterpret_cast<unsigned int*>(a->ws_maskbits), a->B, a->Np, p.mask_words);
+        if (int rc = check_launch("attn_maskbits_kernel")) return rc;
+    }
+    p.gate = a->gate; p.o = (__nv_bfloat16*)a->o; p.og = (__nv_bfloat16*)a->og; p.lse = a->lse;
+    p.B = a->B; p.H = a->H; p.Np = a->Np;
+    p.clamp = a->softclamp; p.scale_over_clamp = a->scale / a->softclamp;
+    p.dropout_p = a->dropout_p;
+    p.drop_thresh = (unsigned int)(a->dropout_p * 65536.f);
+    p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
+    p.seed = a->seed;
+    p.drop_stride = (a->Np + 1) & ~1;
+    CUtensorMap tq, tk, tv;
+    const long long rows = (long long)a->B * a->H * a->Np;
+    if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows)) return -1;
+    const int smem = 5 * TILE16 + 2 * PTILE + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        B200_REQUIRE(e == cudaSuccess, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((a->Np + TQ - 1) / TQ, a->H, a->B);
+    attn_fwd_tc_kernel<<<grid, 192, smem, st>>>(tq, tk, tv, p);
+    return check_launch("attn_fwd_tc_kernel");
+}

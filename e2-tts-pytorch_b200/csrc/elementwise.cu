@@ -167,14 +167,26 @@ __global__ void __launch_bounds__(256) assemble_bwd_kernel(const AsmP p) {
         for (int k = 0; k < 8; ++k) dst[k] = acc[k];
     }
 }
-// embedding gradient: one block per vocabulary row, deterministic (no atomics on the hot filler id 0)
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* d_tok, const int* ids, float* d_emb, int ntok, int D) {
+// embedding gradient: grid (vocab row, token slab); a block scans its slab for its id and adds its partial row
+// (the hot filler id 0 is spread over all slabs instead of one serial block). d_emb is zeroed by the host wrapper.
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* d_tok, const int* ids, float* d_emb, int ntok, int D, int slab) {
     const int v = blockIdx.x;
-    for (int c = threadIdx.x; c < D; c += 256) {
-        float acc = 0.f;
-        for (int t = 0; t < ntok; ++t)
-            if (ids[t] == v) acc += d_tok[(size_t)t * D + c];
-        d_emb[(size_t)v * D + c] = acc;
+    const int t0 = blockIdx.y * slab, t1 = min(ntok, t0 + slab);
+    __shared__ int hits[256];
+    __shared__ int nhit;
+    for (int base = t0; base < t1; base += 256) {
+        if (threadIdx.x == 0) nhit = 0;
+        __syncthreads();
+        const int t = base + threadIdx.x;
+        if (t < t1 && ids[t] == v) hits[atomicAdd(&nhit, 1)] = t;
+        __syncthreads();
+        const int nh = nhit;
+        for (int c = threadIdx.x; c < D; c += 256) {
+            float acc = 0.f;
+            for (int j = 0; j < nh; ++j) acc += d_tok[(size_t)hits[j] * D + c];
+            if (nh) atomicAdd(d_emb + (size_t)v * D + c, acc);
+        }
+        __syncthreads();
     }
 }
 
@@ -609,7 +621,11 @@ extern "C" int b200_assemble_bwd(const b200_assemble_args* a, b200_stream_t stre
 }
 extern "C" int b200_embed_bwd(const float* d_tok, const int32_t* ids, float* d_emb, int32_t ntok, int32_t D, int32_t vocab, b200_stream_t stream) {
     B200_REQUIRE(d_tok && ids && d_emb && ntok > 0 && D > 0 && vocab > 0, "embed_bwd: bad arguments");
-    embed_bwd_kernel<<<vocab, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_tok, ids, d_emb, ntok, D);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(d_emb, 0, (size_t)vocab * D * sizeof(float), st);
+    B200_REQUIRE(e == cudaSuccess, "embed_bwd: memset: %s", cudaGetErrorString(e));
+    const int slab = 1024;
+    embed_bwd_kernel<<<dim3(vocab, (ntok + slab - 1) / slab), 256, 0, st>>>(d_tok, ids, d_emb, ntok, D, slab);
     return check_launch("embed_bwd_kernel");
 }
 extern "C" int b200_rotary_table(float* cos_out, float* sin_out, int32_t Np, int32_t dim_head, b200_stream_t stream) {

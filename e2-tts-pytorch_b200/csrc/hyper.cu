@@ -37,6 +37,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Reduce 32 per-lane values across the warp with recursive halving (31 shuffles instead of 160): on return
+// lane l holds the warp-wide sum of v[l] in v[0].
+template <int N>
+__device__ __forceinline__ void warp_halve(float (&v)[32], int lane) {
+    constexpr int o = N / 2;
+    const bool hi = lane & o;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+        const float send = hi ? v[i] : v[i + o];
+        const float keep = hi ? v[i + o] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+}
+__device__ __forceinline__ float warp_reduce32(float (&v)[32], int lane) {
+    warp_halve<32>(v, lane);
+    warp_halve<16>(v, lane);
+    warp_halve<8>(v, lane);
+    warp_halve<4>(v, lane);
+    warp_halve<2>(v, lane);
+    return v[0];
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
     f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
@@ -56,8 +77,20 @@ struct TokState {
     float beta[HS];
 };
 
+// Stage the per-feature parameters once per block: sp[i] = { (gamma_i+1) * A[i][0..4], (gamma_i+1) * b[i], gamma_i+1, 0 }
+// (two 16-byte shared loads per feature instead of seven global loads; the (gamma+1) factor is folded in).
+__device__ __forceinline__ void stage_params(const HcP& p, float4* sp) {
+    for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
+        const float g1 = __ldg(p.gamma + i) + 1.f;
+        const float* a = p.afn + i * HT;
+        sp[2 * i] = make_float4(g1 * __ldg(a), g1 * __ldg(a + 1), g1 * __ldg(a + 2), g1 * __ldg(a + 3));
+        sp[2 * i + 1] = make_float4(g1 * __ldg(a + 4), g1 * __ldg(p.bfn + i), g1, 0.f);
+    }
+    __syncthreads();
+}
+
 template <int VPT>
-__device__ __forceinline__ void token_forward(const HcP& p, long long tok, int lane, TokState<VPT>& st) {
+__device__ __forceinline__ void token_forward(const HcP& p, const float4* __restrict__ sp, long long tok, int lane, TokState<VPT>& st) {
     const int nchunk = p.D >> 3;
     float ss[HS] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -76,47 +109,51 @@ __device__ __forceinline__ void token_forward(const HcP& p, long long tok, int l
             for (int e = 0; e < 8; ++e) ss[s] += st.r[s][v][e] * st.r[s][v][e];
         }
     }
-    const float sqrtD = sqrtf((float)p.D);
+    float red[32];
 #pragma unroll
-    for (int s = 0; s < HS; ++s) st.inv[s] = sqrtD / fmaxf(sqrtf(warp_sum(ss[s])), 1e-12f);
-
-    float wc[HS][HT], dc[HS];
-#pragma unroll
-    for (int s = 0; s < HS; ++s) {
-        dc[s] = 0.f;
-#pragma unroll
-        for (int t = 0; t < HT; ++t) wc[s][t] = 0.f;
-    }
+    for (int i = 0; i < 32; ++i) red[i] = 0.f;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
         const int c = lane + 32 * v;
         if (c < nchunk) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int i = c * 8 + e;
-                const float g1 = __ldg(p.gamma + i) + 1.f;
-                const float bf = __ldg(p.bfn + i);
-                float af[HT];
-#pragma unroll
-                for (int t = 0; t < HT; ++t) af[t] = __ldg(p.afn + i * HT + t);
+                const float4 p0 = sp[2 * (c * 8 + e)], p1 = sp[2 * (c * 8 + e) + 1];
 #pragma unroll
                 for (int s = 0; s < HS; ++s) {
-                    const float nh = st.r[s][v][e] * st.inv[s] * g1;
-                    dc[s] += nh * bf;
-#pragma unroll
-                    for (int t = 0; t < HT; ++t) wc[s][t] += nh * af[t];
+                    const float rv = st.r[s][v][e];
+                    red[s * HT + 0] += rv * p0.x; red[s * HT + 1] += rv * p0.y; red[s * HT + 2] += rv * p0.z;
+                    red[s * HT + 3] += rv * p0.w; red[s * HT + 4] += rv * p1.x; red[HS * HT + s] += rv * p1.y;
                 }
             }
         }
     }
+#pragma unroll
+    for (int s = 0; s < HS; ++s) red[28 + s] = ss[s];   // the four sums of squares ride along in the same reduction
+    const float mine = warp_reduce32(red, lane);         // lane l owns total #l
+    const float sqrtD = sqrtf((float)p.D);
+    float invs[HS];
+#pragma unroll
+    for (int s = 0; s < HS; ++s) {
+        invs[s] = sqrtD / fmaxf(sqrtf(__shfl_sync(0xffffffffu, mine, 28 + s)), 1e-12f);
+        st.inv[s] = invs[s];
+    }
+    // each lane applies inv_s and tanh to the ONE dot product it owns, then the 24 results are broadcast
+    float myinv = invs[0];
+    {
+        const int s_of = lane < HS * HT ? lane / HT : lane - HS * HT;
+#pragma unroll
+        for (int s = 1; s < HS; ++s) myinv = (s_of == s) ? invs[s] : myinv;
+    }
+    const float th = tanhf(mine * myinv);
     const float sa = __ldg(p.ascale), sb = __ldg(p.bscale);
 #pragma unroll
     for (int s = 0; s < HS; ++s) {
-        st.thb[s] = tanhf(warp_sum(dc[s]));
+        st.thb[s] = __shfl_sync(0xffffffffu, th, HS * HT + s);
         st.beta[s] = st.thb[s] * sb + __ldg(p.sbeta + s);
 #pragma unroll
         for (int t = 0; t < HT; ++t) {
-            st.tha[s][t] = tanhf(warp_sum(wc[s][t]));
+            st.tha[s][t] = __shfl_sync(0xffffffffu, th, s * HT + t);
             st.alpha[s][t] = st.tha[s][t] * sa + __ldg(p.salpha + s * HT + t);
         }
     }
@@ -128,13 +165,15 @@ __device__ __forceinline__ const float* norm_gain(const HcP& p, long long tok) {
 
 template <int VPT>
 __global__ void __launch_bounds__(256) hc_width_fwd_kernel(const HcP p) {
+    extern __shared__ float4 sp[];
+    stage_params(p, sp);
     const int lane = threadIdx.x & 31;
     const long long warp_global = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * 8;
     const int nchunk = p.D >> 3;
     for (long long tok = warp_global; tok < p.T; tok += nwarps) {
         TokState<VPT> st;
-        token_forward<VPT>(p, tok, lane, st);
+        token_forward<VPT>(p, sp, tok, lane, st);
         float br[VPT][8];
         float bss = 0.f;
 #pragma unroll
@@ -163,7 +202,12 @@ __global__ void __launch_bounds__(256) hc_width_fwd_kernel(const HcP p) {
                 }
             }
         }
-        if (lane < HS) p.beta_out[(size_t)tok * HS + lane] = st.beta[lane];
+        {
+            float bsel = st.beta[0];
+#pragma unroll
+            for (int s = 1; s < HS; ++s) bsel = (lane == s) ? st.beta[s] : bsel;
+            if (lane < HS) p.beta_out[(size_t)tok * HS + lane] = bsel;
+        }
         float c_norm = 1.f;
         const float* ng = nullptr;
         if (p.norm_mode) {
@@ -183,17 +227,23 @@ __global__ void __launch_bounds__(256) hc_width_fwd_kernel(const HcP p) {
     }
 }
 
-// Backward. grid = (ceil(rows_per_batch / 64), B): a block never straddles two batch elements, so the
-// adaptive-gain gradient (B, D) can be accumulated in shared memory and flushed once per block.
+// Backward, two kernels so that no per-element atomics are needed:
+//   (1) token kernel  : one warp per token — recompute the forward scalars, produce d_xres and a 40-float per-token
+//                       record (inv[4], d_wc[20], d_dc[4], alpha[:,0][4], c_norm, pad) plus the scalar parameter grads;
+//   (2) param kernel  : one thread per pair of feature columns, marching over a slab of tokens with the records in
+//                       shared memory — accumulates d(dynamic_alpha_fn), d(dynamic_beta_fn), d(norm.gamma), d(gain)
+//                       in registers; one global atomicAdd per column per block.
+// grid.y = batch element: a block never straddles two batch elements (adaptive-gain gradient is per batch).
 constexpr int HC_TOK_PER_BLOCK = 64;
+constexpr int HC_REC = 40;
 
 template <int VPT>
-__global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
-    extern __shared__ float sacc[];  // [8][D] : afn t0..t4, bfn, gamma, ng   then [32] scalars
+__global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p, float* __restrict__ rec) {
+    extern __shared__ float4 sp[];
+    __shared__ float s_scal[32];
+    if (threadIdx.x < 32) s_scal[threadIdx.x] = 0.f;
+    stage_params(p, sp);
     const int D = p.D, nchunk = D >> 3;
-    float* s_scal = sacc + 8 * D;
-    for (int i = threadIdx.x; i < 8 * D + 32; i += 256) sacc[i] = 0.f;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * HC_TOK_PER_BLOCK;
@@ -211,10 +261,11 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
     for (int n = n0 + warp; n < n1; n += 8) {
         const long long tok = (long long)b * p.rows_per_batch + n;
         TokState<VPT> st;
-        token_forward<VPT>(p, tok, lane, st);
+        token_forward<VPT>(p, sp, tok, lane, st);
 
         // ---- branch (mix_0), its norm, and d(mix_0)
         float dm0[VPT][8];
+        float cn = 1.f;
         {
             float br[VPT][8], dy[VPT][8];
             float bss = 0.f;
@@ -233,7 +284,7 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
                 }
             }
             if (p.norm_mode) {
-                const float cn = sqrtf((float)D) / fmaxf(sqrtf(warp_sum(bss)), 1e-12f);
+                cn = sqrtf((float)D) / fmaxf(sqrtf(warp_sum(bss)), 1e-12f);
                 const float* ng = norm_gain(p, tok);
                 float dot = 0.f;
 #pragma unroll
@@ -249,17 +300,9 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
 #pragma unroll
                 for (int v = 0; v < VPT; ++v) {
                     const int c = lane + 32 * v;
-                    if (c < nchunk) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int i = c * 8 + e;
-                            atomicAdd(&sacc[7 * D + i], dy[v][e] * br[v][e] * cn);
-                            dm0[v][e] = cn * __ldg(ng + i) * dy[v][e] - br[v][e] * k2;
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) dm0[v][e] = 0.f;
-                    }
+                    for (int e = 0; e < 8; ++e)
+                        dm0[v][e] = (c < nchunk) ? cn * __ldg(ng + c * 8 + e) * dy[v][e] - br[v][e] * k2 : 0.f;
                 }
             } else {
 #pragma unroll
@@ -270,11 +313,9 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
         }
         // ---- d_alpha[s][t] = <d_mix_t, r_s>; start d_r_s = sum_t alpha[s][t] d_mix_t
         float dr[HS][VPT][8];
-        float dal[HS][HT];
+        float red[32];
 #pragma unroll
-        for (int s = 0; s < HS; ++s)
-#pragma unroll
-            for (int t = 0; t < HT; ++t) dal[s][t] = 0.f;
+        for (int i = 0; i < 32; ++i) red[i] = 0.f;
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int c = lane + 32 * v;
@@ -283,7 +324,7 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     dr[s][v][e] = st.alpha[s][0] * dm0[v][e];
-                    dal[s][0] += dm0[v][e] * st.r[s][v][e];
+                    red[s * HT] += dm0[v][e] * st.r[s][v][e];
                 }
             if (c < nchunk) {
 #pragma unroll
@@ -295,11 +336,12 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             dr[s][v][e] += st.alpha[s][t] * dm[e];
-                            dal[s][t] += dm[e] * st.r[s][v][e];
+                            red[s * HT + t] += dm[e] * st.r[s][v][e];
                         }
                 }
             }
         }
+        const float mine = warp_reduce32(red, lane);
         float dwc[HS][HT], ddc[HS];
 #pragma unroll
         for (int s = 0; s < HS; ++s) {
@@ -309,11 +351,26 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
             g_sbe[s] += dbe;
 #pragma unroll
             for (int t = 0; t < HT; ++t) {
-                const float da = warp_sum(dal[s][t]);
+                const float da = __shfl_sync(0xffffffffu, mine, s * HT + t);
                 dwc[s][t] = da * sa * (1.f - st.tha[s][t] * st.tha[s][t]);
                 g_as += da * st.tha[s][t];
                 g_sal[s][t] += da;
             }
+        }
+        // per-token record for the parameter kernel
+        {
+            float val = 0.f;
+#pragma unroll
+            for (int s = 0; s < HS; ++s) {
+                if (lane == s) val = st.inv[s];
+                if (lane == 24 + s) val = ddc[s];
+                if (lane == 28 + s) val = st.alpha[s][0];
+#pragma unroll
+                for (int t = 0; t < HT; ++t)
+                    if (lane == 4 + s * HT + t) val = dwc[s][t];
+            }
+            rec[(size_t)tok * HC_REC + lane] = val;
+            if (lane == 0) rec[(size_t)tok * HC_REC + 32] = cn;
         }
         // ---- through n^ = r * inv * (gamma+1)
         float R[HS] = {0.f, 0.f, 0.f, 0.f};
@@ -324,30 +381,13 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
             if (c < nchunk) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int i = c * 8 + e;
-                    const float g1 = __ldg(p.gamma + i) + 1.f;
-                    const float bf = __ldg(p.bfn + i);
-                    float af[HT], gaf[HT];
-#pragma unroll
-                    for (int t = 0; t < HT; ++t) { af[t] = __ldg(p.afn + i * HT + t); gaf[t] = 0.f; }
-                    float gbf = 0.f, ggam = 0.f;
+                    const float4 p0 = sp[2 * (c * 8 + e)], p1 = sp[2 * (c * 8 + e) + 1];   // already scaled by (gamma+1)
 #pragma unroll
                     for (int s = 0; s < HS; ++s) {
-                        const float rn = st.r[s][v][e] * st.inv[s];
-                        const float nh = rn * g1;
-                        float dnh = ddc[s] * bf;
-#pragma unroll
-                        for (int t = 0; t < HT; ++t) { dnh += dwc[s][t] * af[t]; gaf[t] += nh * dwc[s][t]; }
-                        gbf += nh * ddc[s];
-                        ggam += dnh * rn;
-                        const float uu = dnh * g1;
+                        const float uu = ddc[s] * p1.y + dwc[s][0] * p0.x + dwc[s][1] * p0.y + dwc[s][2] * p0.z + dwc[s][3] * p0.w + dwc[s][4] * p1.x;
                         u[s][v][e] = uu;
                         R[s] += uu * st.r[s][v][e];
                     }
-#pragma unroll
-                    for (int t = 0; t < HT; ++t) atomicAdd(&sacc[t * D + i], gaf[t]);
-                    atomicAdd(&sacc[5 * D + i], gbf);
-                    atomicAdd(&sacc[6 * D + i], ggam);
                 }
             } else {
 #pragma unroll
@@ -383,18 +423,95 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p) {
         atomicAdd(&s_scal[25], g_bs);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < D; i += 256) {
-#pragma unroll
-        for (int t = 0; t < HT; ++t) atomicAdd(p.g_afn + i * HT + t, sacc[t * D + i]);
-        atomicAdd(p.g_bfn + i, sacc[5 * D + i]);
-        atomicAdd(p.g_gamma + i, sacc[6 * D + i]);
-        if (p.norm_mode == 1) atomicAdd(p.g_ng + i, sacc[7 * D + i]);
-        else if (p.norm_mode == 2) atomicAdd(p.g_ng + (size_t)b * D + i, sacc[7 * D + i]);
-    }
     if (threadIdx.x < 20) atomicAdd(p.g_salpha + threadIdx.x, s_scal[threadIdx.x]);
     else if (threadIdx.x < 24) atomicAdd(p.g_sbeta + (threadIdx.x - 20), s_scal[threadIdx.x]);
     else if (threadIdx.x == 24) atomicAdd(p.g_ascale, s_scal[24]);
     else if (threadIdx.x == 25) atomicAdd(p.g_bscale, s_scal[25]);
+}
+
+constexpr int HC_PARAM_TOK = 128;   // tokens per block (4 groups of 32)
+constexpr int HC_PARAM_COLS = 128;  // feature columns per block (64 threads x 2)
+
+__global__ void __launch_bounds__(256) hc_width_bwd_param_kernel(const HcP p, const float* __restrict__ rec) {
+    __shared__ float srec[HC_PARAM_TOK][36];
+    __shared__ float sred[8][HC_PARAM_COLS];
+    const int D = p.D, b = blockIdx.z;
+    const int n0 = blockIdx.x * HC_PARAM_TOK;
+    const int ntok = min(p.rows_per_batch - n0, HC_PARAM_TOK);
+    const long long tok0 = (long long)b * p.rows_per_batch + n0;
+    for (int i = threadIdx.x; i < ntok * 36; i += 256) srec[i / 36][i % 36] = rec[(size_t)(tok0 + i / 36) * HC_REC + (i % 36)];
+    for (int i = threadIdx.x; i < 8 * HC_PARAM_COLS; i += 256) sred[i / HC_PARAM_COLS][i % HC_PARAM_COLS] = 0.f;
+    __syncthreads();
+    const int cp = threadIdx.x & 63, tg = threadIdx.x >> 6;
+    const int col = blockIdx.y * HC_PARAM_COLS + cp * 2;
+    if (col < D) {
+        float g1[2], bf[2], af[2][HT], gaf[2][HT], gbf[2] = {0.f, 0.f}, ggam[2] = {0.f, 0.f}, gng[2] = {0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            g1[q] = __ldg(p.gamma + col + q) + 1.f;
+            bf[q] = __ldg(p.bfn + col + q);
+#pragma unroll
+            for (int t = 0; t < HT; ++t) { af[q][t] = __ldg(p.afn + (col + q) * HT + t); gaf[q][t] = 0.f; }
+        }
+        const int nbeg = tg * 32, nend = min(ntok, nbeg + 32);
+#pragma unroll 4
+        for (int n = nbeg; n < nend; ++n) {
+            const float* rc = srec[n];
+            const size_t tok = (size_t)(tok0 + n);
+            float r[HS][2];
+#pragma unroll
+            for (int s = 0; s < HS; ++s) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(p.xres + (tok * HS + s) * D + col);
+                r[s][0] = bf16_lo(w); r[s][1] = bf16_hi(w);
+            }
+            float dy[2] = {0.f, 0.f};
+            if (p.norm_mode) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(p.d_branch + tok * D + col);
+                dy[0] = bf16_lo(w); dy[1] = bf16_hi(w);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float bmix = 0.f;
+#pragma unroll
+                for (int s = 0; s < HS; ++s) {
+                    const float rn = r[s][q] * rc[s];
+                    const float nh = rn * g1[q];
+                    const float ddc = rc[24 + s];
+                    float dnh = ddc * bf[q];
+#pragma unroll
+                    for (int t = 0; t < HT; ++t) {
+                        const float dwc = rc[4 + s * HT + t];
+                        dnh += dwc * af[q][t];
+                        gaf[q][t] += nh * dwc;
+                    }
+                    gbf[q] += nh * ddc;
+                    ggam[q] += dnh * rn;
+                    bmix += rc[28 + s] * r[s][q];
+                }
+                gng[q] += dy[q] * bmix * rc[32];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int lc = cp * 2 + q;
+#pragma unroll
+            for (int t = 0; t < HT; ++t) atomicAdd(&sred[t][lc], gaf[q][t]);
+            atomicAdd(&sred[5][lc], gbf[q]);
+            atomicAdd(&sred[6][lc], ggam[q]);
+            atomicAdd(&sred[7][lc], gng[q]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * HC_PARAM_COLS; i += 256) {
+        const int k = i / HC_PARAM_COLS, c = blockIdx.y * HC_PARAM_COLS + (i % HC_PARAM_COLS);
+        if (c >= D) continue;
+        const float v = sred[k][i % HC_PARAM_COLS];
+        if (k < HT) atomicAdd(p.g_afn + c * HT + k, v);
+        else if (k == 5) atomicAdd(p.g_bfn + c, v);
+        else if (k == 6) atomicAdd(p.g_gamma + c, v);
+        else if (p.norm_mode == 1) atomicAdd(p.g_ng + c, v);
+        else if (p.norm_mode == 2) atomicAdd(p.g_ng + (size_t)b * D + c, v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ depth
@@ -483,9 +600,10 @@ extern "C" int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stre
     if (fill_hc(p, a)) return -1;
     p.branch = (__nv_bfloat16*)a->branch; p.res_out = (__nv_bfloat16*)a->res_out; p.beta_out = a->beta_out;
     const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 8);
-    if (a->D <= 256) hc_width_fwd_kernel<1><<<grid, 256, 0, st>>>(p);
-    else if (a->D <= 512) hc_width_fwd_kernel<2><<<grid, 256, 0, st>>>(p);
-    else hc_width_fwd_kernel<4><<<grid, 256, 0, st>>>(p);
+    const size_t smem = (size_t)a->D * 2 * sizeof(float4);
+    if (a->D <= 256) hc_width_fwd_kernel<1><<<grid, 256, smem, st>>>(p);
+    else if (a->D <= 512) hc_width_fwd_kernel<2><<<grid, 256, smem, st>>>(p);
+    else hc_width_fwd_kernel<4><<<grid, 256, smem, st>>>(p);
     return check_launch("hc_width_fwd_kernel");
 }
 
@@ -500,12 +618,16 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     p.d_xres = (__nv_bfloat16*)a->d_xres;
     p.g_gamma = a->g_norm_gamma; p.g_afn = a->g_dynamic_alpha_fn; p.g_ascale = a->g_dynamic_alpha_scale; p.g_salpha = a->g_static_alpha;
     p.g_bfn = a->g_dynamic_beta_fn; p.g_bscale = a->g_dynamic_beta_scale; p.g_sbeta = a->g_static_beta; p.g_ng = a->g_norm_gain;
+    B200_REQUIRE(a->ws_records, "hc_width_bwd: missing per-token record workspace (T * 40 floats)");
     dim3 grid((a->rows_per_batch + HC_TOK_PER_BLOCK - 1) / HC_TOK_PER_BLOCK, a->T / a->rows_per_batch);
-    const size_t smem = (size_t)(8 * a->D + 32) * sizeof(float);
-    if (a->D <= 256) hc_width_bwd_kernel<1><<<grid, 256, smem, st>>>(p);
-    else if (a->D <= 512) hc_width_bwd_kernel<2><<<grid, 256, smem, st>>>(p);
-    else hc_width_bwd_kernel<4><<<grid, 256, smem, st>>>(p);
-    return check_launch("hc_width_bwd_kernel");
+    const size_t smem = (size_t)a->D * 2 * sizeof(float4);
+    if (a->D <= 256) hc_width_bwd_kernel<1><<<grid, 256, smem, st>>>(p, a->ws_records);
+    else if (a->D <= 512) hc_width_bwd_kernel<2><<<grid, 256, smem, st>>>(p, a->ws_records);
+    else hc_width_bwd_kernel<4><<<grid, 256, smem, st>>>(p, a->ws_records);
+    if (int rc = check_launch("hc_width_bwd_kernel")) return rc;
+    dim3 grid2((a->rows_per_batch + HC_PARAM_TOK - 1) / HC_PARAM_TOK, (a->D + HC_PARAM_COLS - 1) / HC_PARAM_COLS, a->T / a->rows_per_batch);
+    hc_width_bwd_param_kernel<<<grid2, 256, 0, st>>>(p, a->ws_records);
+    return check_launch("hc_width_bwd_param_kernel");
 }
 
 extern "C" int b200_hc_depth_fwd(const b200_hc_depth_args* a, b200_stream_t stream) {

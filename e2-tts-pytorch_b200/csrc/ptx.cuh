@@ -138,4 +138,11 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float 
     return (hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
+// Attention dropout: one 32-bit hash decides TWO neighbouring keys (16 bits each): keep iff half >= thresh, thresh = p * 65536.
+// idx = row_id * drop_stride + key with drop_stride even, so that (idx >> 1) pairs keys (2k, 2k+1) of one query row.
+__device__ __forceinline__ bool dropout_keep16(uint64_t seed, uint64_t idx, uint32_t thresh) {
+    const uint32_t h = hash_u32(seed, idx >> 1);
+    return ((idx & 1) ? (h >> 16) : (h & 0xffffu)) >= thresh;
+}
+
 }  // namespace b200

@@ -126,11 +126,28 @@ __device__ __forceinline__ bool tok_ok(const unsigned char* mask, int b, int n, 
     return n >= 0 && n < Np && (!mask || mask[(size_t)b * Np + n]);
 }
 
+// Both kernels keep the thread's channel weights in registers and slide a register window over the sequence, so the
+// inner loop is pure FFMA (the first version re-read weights and inputs from shared memory for every tap and was
+// LSU-bound: ncu profiles/r1_hc_conv_before.txt). KS = 31 (reference default, e2_tts.py:539) is fully unrolled;
+// other odd sizes <= 31 run the same code with zero-padded taps.
+template <int ROWS>
+__device__ __forceinline__ void conv_rows(const float (&w)[31], const float (*src)[CV_TC], int row0, int cl, float bias, float (&out)[ROWS]) {
+    float win[ROWS + 30];
+#pragma unroll
+    for (int j = 0; j < ROWS + 30; ++j) win[j] = src[row0 + j][cl];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        float acc = bias;
+#pragma unroll
+        for (int k = 0; k < 31; ++k) acc += w[k] * win[j + k];
+        out[j] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const b200_dwconv_args a) {
     __shared__ float xs[CV_TN + 2 * CV_HALO][CV_TC];
-    __shared__ float ws[31][CV_TC];
     const int n0 = blockIdx.x * CV_TN, c0 = blockIdx.y * CV_TC, b = blockIdx.z;
-    const int pad = a.ksize / 2;
+    const int pad = a.ksize / 2, shift = CV_HALO - pad;   // taps are centred inside the 31-wide register window
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
     for (int i = threadIdx.x; i < (CV_TN + 2 * CV_HALO) * (CV_TC / 8); i += 256) {
         const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
@@ -144,93 +161,113 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const b200_dwconv_args 
 #pragma unroll
         for (int j = 0; j < 8; ++j) xs[r][ch + j] = v[j];
     }
-    for (int i = threadIdx.x; i < a.ksize * CV_TC; i += 256) {
-        const int k = i / CV_TC, c = i % CV_TC;
-        ws[k][c] = (c0 + c < a.D) ? a.weight[(size_t)(c0 + c) * a.ksize + k] : 0.f;
-    }
-    __syncthreads();
     const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
-    if (c0 + cl >= a.D) return;
-    const float bias = a.bias[c0 + cl];
+    const bool cok = c0 + cl < a.D;
+    float w[31];
+#pragma unroll
+    for (int k = 0; k < 31; ++k) w[k] = (cok && k >= shift && k - shift < a.ksize) ? a.weight[(size_t)(c0 + cl) * a.ksize + (k - shift)] : 0.f;
+    __syncthreads();
+    if (!cok) return;
+    float out[16];
+    conv_rows<16>(w, xs, tg * 16, cl, a.bias[c0 + cl], out);
     __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y);
+#pragma unroll
     for (int jj = 0; jj < 16; ++jj) {
-        const int r = tg * 16 + jj, n = n0 + r;
-        if (n >= a.Np) break;
-        float acc = bias;
-        for (int k = 0; k < a.ksize; ++k) acc += ws[k][cl] * xs[r + CV_HALO - pad + k][cl];
-        const float o = tok_ok(a.mask, b, n, a.Np) ? acc / (1.f + __expf(-acc)) : 0.f;
-        y[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(o);
+        const int n = n0 + tg * 16 + jj;
+        if (n < a.Np) {
+            const float o = tok_ok(a.mask, b, n, a.Np) ? out[jj] / (1.f + __expf(-out[jj])) : 0.f;
+            y[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(o);
+        }
     }
 }
 
+constexpr int CV_TILES_PER_BLOCK = 4;   // n-tiles marched by one block: weight/bias partial sums stay in registers across them
+constexpr int CV_P1 = 96;               // phase-1 rows (tile + halo each side = 94, padded to 4 x 24)
+
 __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const b200_dwconv_args a) {
     extern __shared__ float sm[];
-    float (*xs)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm);                                  // [TN + 4 HALO]
-    float (*dps)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (CV_TN + 4 * CV_HALO) * CV_TC);  // [TN + 2 HALO]
-    float (*ws)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (2 * CV_TN + 6 * CV_HALO) * CV_TC);  // [31]
-    float (*sdw)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (2 * CV_TN + 6 * CV_HALO + 31) * CV_TC);  // [32] (31 taps + bias)
-    const int n0 = blockIdx.x * CV_TN, c0 = blockIdx.y * CV_TC, b = blockIdx.z;
-    const int pad = a.ksize / 2;
+    float (*xs)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm);                              // [CV_P1 + 30] rows, token n0 - 30 + r
+    float (*dps)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (CV_P1 + 30) * CV_TC);       // [CV_P1] rows, token n0 - 15 + r
+    float (*sdw)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (2 * CV_P1 + 30) * CV_TC);   // [32] (31 taps + bias)
+    const int c0 = blockIdx.y * CV_TC, b = blockIdx.z;
+    const int pad = a.ksize / 2, shift = CV_HALO - pad;
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
     const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy);
-    for (int i = threadIdx.x; i < (CV_TN + 4 * CV_HALO) * (CV_TC / 8); i += 256) {
-        const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
-        const int n = n0 - 2 * CV_HALO + r;
-        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (tok_ok(a.mask, b, n, a.Np) && c0 + ch < a.D) {
-            const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + n) * a.D + c0 + ch);
-            v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-            v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xs[r][ch + j] = v[j];
-    }
-    for (int i = threadIdx.x; i < 32 * CV_TC; i += 256) {
-        const int k = i / CV_TC, c = i % CV_TC;
-        if (k < 31) ws[k][c] = (k < a.ksize && c0 + c < a.D) ? a.weight[(size_t)(c0 + c) * a.ksize + k] : 0.f;
-        sdw[k][c] = 0.f;
-    }
-    __syncthreads();
+    __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(a.dx);
+    for (int i = threadIdx.x; i < 32 * CV_TC; i += 256) sdw[i / CV_TC][i % CV_TC] = 0.f;
     const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
     const bool cok = c0 + cl < a.D;
     const float bias = cok ? a.bias[c0 + cl] : 0.f;
-    // phase 1: d(pre-activation) on the tile plus a HALO on each side
-    for (int r = tg; r < CV_TN + 2 * CV_HALO; r += 4) {
-        const int n = n0 - CV_HALO + r;
-        float d = 0.f;
-        if (cok && tok_ok(a.mask, b, n, a.Np)) {
-            float pre = bias;
-            for (int k = 0; k < a.ksize; ++k) pre += ws[k][cl] * xs[r + CV_HALO - pad + k][cl];
-            const float s = 1.f / (1.f + __expf(-pre));
-            d = __bfloat162float(dy[((size_t)b * a.Np + n) * a.D + c0 + cl]) * s * (1.f + pre * (1.f - s));
-        }
-        dps[r][cl] = d;
+    float w[31], wr[31], dwk[31];
+#pragma unroll
+    for (int k = 0; k < 31; ++k) {
+        w[k] = (cok && k >= shift && k - shift < a.ksize) ? a.weight[(size_t)(c0 + cl) * a.ksize + (k - shift)] : 0.f;
+        dwk[k] = 0.f;
     }
-    __syncthreads();
-    // phase 2: dx and the weight / bias partial sums
-    __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(a.dx);
+#pragma unroll
+    for (int k = 0; k < 31; ++k) wr[k] = w[30 - k];   // flipped taps for the transposed convolution (dx)
     float db = 0.f;
-    for (int jj = 0; cok && jj < 16; ++jj) {
-        const int r = tg * 16 + jj, n = n0 + r;
-        if (n >= a.Np) break;
-        float acc = 0.f;
-        for (int k = 0; k < a.ksize; ++k) acc += ws[k][cl] * dps[r + CV_HALO + pad - k][cl];
-        dx[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(tok_ok(a.mask, b, n, a.Np) ? acc : 0.f);
-        db += dps[r + CV_HALO][cl];
-    }
-    for (int k = 0; cok && k < a.ksize; ++k) {
-        float acc = 0.f;
-        for (int jj = 0; jj < 16; ++jj) {
-            const int r = tg * 16 + jj;
-            if (n0 + r >= a.Np) break;
-            acc += dps[r + CV_HALO][cl] * xs[r + 2 * CV_HALO - pad + k][cl];
+    const int ntiles = (a.Np + CV_TN - 1) / CV_TN;
+    for (int tile = blockIdx.x * CV_TILES_PER_BLOCK; tile < min(ntiles, (int)(blockIdx.x + 1) * CV_TILES_PER_BLOCK); ++tile) {
+        const int n0 = tile * CV_TN;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (CV_P1 + 30) * (CV_TC / 8); i += 256) {
+            const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
+            const int n = n0 - 2 * CV_HALO + r;
+            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (tok_ok(a.mask, b, n, a.Np) && c0 + ch < a.D) {
+                const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + n) * a.D + c0 + ch);
+                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+                v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xs[r][ch + j] = v[j];
         }
-        atomicAdd(&sdw[k][cl], acc);
+        __syncthreads();
+        // phase 1: d(pre-activation) for tokens n0-15 .. n0+80 (24 rows per thread group)
+        {
+            float pre[24];
+            conv_rows<24>(w, xs, tg * 24, cl, bias, pre);
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+                const int r = tg * 24 + j, n = n0 - CV_HALO + r;
+                float d = 0.f;
+                if (cok && tok_ok(a.mask, b, n, a.Np)) {
+                    const float s = 1.f / (1.f + __expf(-pre[j]));
+                    d = __bfloat162float(dy[((size_t)b * a.Np + n) * a.D + c0 + cl]) * s * (1.f + pre[j] * (1.f - s));
+                }
+                dps[r][cl] = d;
+            }
+        }
+        __syncthreads();
+        // phase 2: dx = flipped conv of d_pre; weight / bias partial sums accumulate in registers across tiles
+        if (cok) {
+            float dxo[16];
+            conv_rows<16>(wr, dps, tg * 16, cl, 0.f, dxo);
+            float win[46];
+#pragma unroll
+            for (int j = 0; j < 46; ++j) win[j] = xs[tg * 16 + CV_HALO + j][cl];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int r = tg * 16 + jj, n = n0 + r;
+                if (n < a.Np) {
+                    dx[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(tok_ok(a.mask, b, n, a.Np) ? dxo[jj] : 0.f);
+                    const float dpr = dps[r + CV_HALO][cl];
+                    db += dpr;
+#pragma unroll
+                    for (int k = 0; k < 31; ++k) dwk[k] += dpr * win[jj + k];
+                }
+            }
+        }
     }
-    if (cok) atomicAdd(&sdw[31][cl], db);
+    if (cok) {
+#pragma unroll
+        for (int k = 0; k < 31; ++k) atomicAdd(&sdw[k][cl], dwk[k]);
+        atomicAdd(&sdw[31][cl], db);
+    }
     __syncthreads();
     if (cok && tg == 0) {
-        for (int k = 0; k < a.ksize; ++k) atomicAdd(a.dweight + (size_t)(c0 + cl) * a.ksize + k, sdw[k][cl]);
+        for (int k = 0; k < a.ksize; ++k) atomicAdd(a.dweight + (size_t)(c0 + cl) * a.ksize + k, sdw[k + shift][cl]);
         atomicAdd(a.dbias + c0 + cl, sdw[31][cl]);
     }
 }
@@ -400,13 +437,14 @@ extern "C" int b200_dwconv_fwd(const b200_dwconv_args* a, b200_stream_t stream) 
 extern "C" int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream) {
     if (check_conv(a)) return -1;
     B200_REQUIRE(a->dy && a->dx && a->dweight && a->dbias, "dwconv_bwd: null pointer");
-    const size_t smem = (size_t)(2 * CV_TN + 6 * CV_HALO + 31 + 32) * CV_TC * sizeof(float);
+    const size_t smem = (size_t)(2 * CV_P1 + 30 + 32) * CV_TC * sizeof(float);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    dim3 grid((a->Np + CV_TN - 1) / CV_TN, (a->D + CV_TC - 1) / CV_TC, a->B);
+    const int ntiles = (a->Np + CV_TN - 1) / CV_TN;
+    dim3 grid((ntiles + CV_TILES_PER_BLOCK - 1) / CV_TILES_PER_BLOCK, (a->D + CV_TC - 1) / CV_TC, a->B);
     dwconv_bwd_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
     return check_launch("dwconv_bwd_kernel");
 }

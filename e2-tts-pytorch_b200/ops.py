@@ -15,6 +15,7 @@ from torch.autograd.function import once_differentiable
 from . import lib
 
 BF16, F32 = torch.bfloat16, torch.float32
+ATTN_FWD_ENTRY = 'b200_attn_fwd'   # tests may point this at 'b200_attn_fwd_legacy' to cross-check the two forward kernels
 
 
 def _stream():
@@ -116,7 +117,7 @@ class HcWidth(Function):
                           d_branch=_c(d_branch), d_res=_c(d_res), d_beta=_c(d_beta), d_xres=d_xres,
                           g_norm_gamma=g_gamma, g_dynamic_alpha_fn=g_afn, g_dynamic_alpha_scale=g_as, g_static_alpha=g_sal,
                           g_dynamic_beta_fn=g_bfn, g_dynamic_beta_scale=g_bs, g_static_beta=g_sbe,
-                          g_norm_gain=g_gain if norm_mode else None)
+                          g_norm_gain=g_gain if norm_mode else None, ws_records=torch.empty((T, 40), device=dev, dtype=F32))
         lib.call('b200_hc_width_bwd', a, _stream())
         return (d_xres, g_gamma, g_afn.view(D, S + 1), g_as.view(()), g_sal.view(S, S + 1), g_bfn, g_bs.view(()), g_sbe,
                 g_gain.view_as(norm_gain) if norm_mode else None, None, None)
@@ -233,9 +234,10 @@ class AttnCore(Function):
         o = torch.empty_like(q)
         og = torch.empty((B * Np, H * dh), device=q.device, dtype=BF16)
         lse = torch.empty((B, H, Np), device=q.device, dtype=F32)
+        ws = torch.empty(((Np + 127) // 128) * 4 * B, device=q.device, dtype=torch.int32)
         a = lib.make_args('b200_attn_fwd_args', q=q, k=k, v=v, keymask=mask, gate=gate, o=o, og=og, lse=lse, B=B, H=H, Np=Np,
-                          dim_head=dh, scale=dh ** -0.5, softclamp=softclamp, dropout_p=dropout_p, seed=seed)
-        lib.call('b200_attn_fwd', a, _stream())
+                          dim_head=dh, scale=dh ** -0.5, softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws)
+        lib.call(ATTN_FWD_ENTRY, a, _stream())
         ctx.save_for_backward(q, k, v, gate, mask, o, lse)
         ctx.meta = (dropout_p, seed, softclamp)
         return og

@@ -83,8 +83,11 @@ typedef struct {
     int32_t B, H, Np, dim_head;
     float scale, softclamp, dropout_p;
     uint64_t seed;
+    void* ws_maskbits;   /* workspace of b200_attn_workspace_bytes(B, Np) bytes (key-validity bitmask built by the call) */
 } b200_attn_fwd_args;
-int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream);
+size_t b200_attn_workspace_bytes(int32_t B, int32_t Np);
+int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream);        /* tcgen05 / TMEM / TMA kernel */
+int b200_attn_fwd_legacy(const b200_attn_fwd_args* a, b200_stream_t stream); /* mma.sync bring-up kernel, kept for cross-checks */
 
 /* backward: d_og bf16 [B*Np, H*64] -> dq,dk,dv bf16 [B,H,Np,64], d_gate fp32 [B*Np,H] (grad wrt the sigmoid
  * gate VALUE; may be NULL). ws_dO (bf16 [B,H,Np,64]) and ws_delta (fp32 [B,H,Np]) are caller workspaces. */
@@ -121,6 +124,7 @@ typedef struct {
     void* d_xres;
     float *g_norm_gamma, *g_dynamic_alpha_fn, *g_dynamic_alpha_scale, *g_static_alpha, *g_dynamic_beta_fn, *g_dynamic_beta_scale,
         *g_static_beta, *g_norm_gain;
+    float* ws_records;   /* bwd workspace: T * 40 floats (per-token scalars handed from the token kernel to the parameter kernel) */
 } b200_hc_width_args;
 int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stream);
 int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stream);

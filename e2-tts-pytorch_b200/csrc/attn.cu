@@ -490,7 +490,20 @@ extern "C" int b200_attn_fwd_legacy(const b200_attn_fwd_args* a, b200_stream_t s
     return check_launch("attn_fwd_kernel");
 }
 
-extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) {
+namespace b200 {
+int launch_attn_bwd_prep(const b200_attn_bwd_args* a, cudaStream_t st) {
+    AttnP p{};
+    if (fill_common(p, a->B, a->H, a->Np, a->scale, a->softclamp, a->dropout_p, a->seed)) return -1;
+    p.gate = a->gate; p.o = (__nv_bfloat16*)a->o; p.dog = (const __nv_bfloat16*)a->d_og; p.dO_out = (__nv_bfloat16*)a->ws_dO;
+    p.delta_out = a->ws_delta; p.dgate = a->d_gate;
+    const long long rows = (long long)a->B * a->H * a->Np;
+    attn_bwd_prep_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(p);
+    return check_launch("attn_bwd_prep_kernel");
+}
+}  // namespace b200
+
+// mma.sync backward (round-1 bring-up kernels, dq/dk/dv all bf16): kept as a cross-check for the tcgen05 backward.
+extern "C" int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     B200_REQUIRE(a && a->q && a->k && a->v && a->o && a->d_og && a->lse && a->ws_dO && a->ws_delta && a->dq && a->dk && a->dv, "attn_bwd: null pointer");
     B200_REQUIRE(a->dim_head == 64, "attn_bwd: only dim_head 64 is built (got %d)", a->dim_head);

@@ -294,6 +294,263 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 }
 
+// ================================================================================================ backward
+// One CTA per (128-key tile, head, batch), 320 threads:
+//   warp 0 lane 0 : TMA producer — K, V once; Q_i / dO_i tiles (128 queries) through a 2-stage ring
+//   warp 1 lane 0 : MMA issuer   — per query tile i:  S = Q_i K^T, dP = dO_i V^T           (128x128x16 x4 each, K-major operands)
+//                                   then, once the math warps have written P and dS (bf16) to swizzled smem:
+//                                   dV += P^T dO_i, dK += dS^T Q_i (A MN-major from the P / dS tiles, B MN-major)
+//                                   dQ_i = dS K                    (A K-major dS tile, B = K tile MN-major)
+//   warps 2..9    : math         — row r = 32*(warp%4)+lane, key half = (warp-2)/4: recompute softclamp + softmax from the
+//                                   saved LSE, dS = P (dP - delta)(1 - tanh^2) scale, write P_drop / dS tiles, flush dQ_i
+//                                   from TMEM with fp32 global atomics, finally store dK, dV.
+// TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
+struct AttnBwdTcP {
+    const unsigned int* maskbits; int mask_words;
+    const float *lse, *delta;
+    float* dq_acc;                  // fp32 [B,H,Np,64], zeroed by the host wrapper
+    __nv_bfloat16 *dk, *dv;
+    int B, H, Np, nq;
+    float scale, scale_over_clamp, clamp, dropout_p, keep_scale;
+    unsigned int drop_thresh; int drop_stride;
+    unsigned long long seed;
+};
+
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmDO, const AttnBwdTcP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + TILE16;
+    uint8_t* sQ = sV + TILE16;           // [2]
+    uint8_t* sDO = sQ + 2 * TILE16;      // [2]
+    uint8_t* sP = sDO + 2 * TILE16;      // 32 KB
+    uint8_t* sDS = sP + PTILE;           // 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + PTILE);
+    uint64_t* kv_full = bars;            // 1
+    uint64_t* qdo_full = bars + 1;       // 2
+    uint64_t* qdo_empty = bars + 3;      // 2
+    uint64_t* sdp_full = bars + 5;       // 1
+    uint64_t* sdp_empty = bars + 6;      // 1 (8 arrivals)
+    uint64_t* pds_full = bars + 7;       // 1 (8 arrivals)
+    uint64_t* mma3_done = bars + 8;      // 1
+    uint64_t* dq_empty = bars + 9;       // 1 (8 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+    const int bh = b * p.H + hh;
+    const int k0 = kt * TKV;
+    const int nq = p.nq;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 8); mbar_init(pds_full, 8); mbar_init(mma3_done, 1); mbar_init(dq_empty, 8);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int row_base = bh * p.Np;
+            mbar_arrive_expect_tx(kv_full, 2 * TILE16);
+            tma_load_2d(sK, &tmK, kv_full, 0, row_base + k0);
+            tma_load_2d(sV, &tmV, kv_full, 0, row_base + k0);
+            for (int i = 0; i < nq; ++i) {
+                const int st = i & 1;
+                mbar_wait(&qdo_empty[st], (((i >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&qdo_full[st], 2 * TILE16);
+                tma_load_2d(sQ + st * TILE16, &tmQ, &qdo_full[st], 0, row_base + i * TQ);
+                tma_load_2d(sDO + st * TILE16, &tmDO, &qdo_full[st], 0, row_base + i * TQ);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);   // S, dP
+            constexpr uint32_t id_t = make_idesc_bf16(128, 64, 1, 1);    // dV, dK (A^T from smem, B MN-major)
+            constexpr uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);    // dQ
+            mbar_wait(kv_full, 0);
+            const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 0, 1024);             // K-major (B of S)
+            const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 0, 1024);             // K-major (B of dP)
+            const uint64_t kmn = make_smem_desc_sw128(smem_u32(sK), 128 * 128, 1024);        // MN-major (B of dQ)
+            const uint64_t pT = make_smem_desc_sw128(smem_u32(sP), 128 * 128, 1024);         // MN-major A (P^T)
+            const uint64_t dsT = make_smem_desc_sw128(smem_u32(sDS), 128 * 128, 1024);       // MN-major A (dS^T)
+            for (int i = 0; i < nq; ++i) {
+                const int st = i & 1;
+                const uint32_t ph = i & 1;
+                mbar_wait(&qdo_full[st], (i >> 1) & 1);
+                mbar_wait(sdp_empty, ph ^ 1);
+                tc_fence_after();
+                const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + st * TILE16), 0, 1024);
+                const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sDO + st * TILE16), 0, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), id_s, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tDP, dodesc + (uint64_t)(k * 2), vdesc + (uint64_t)(k * 2), id_s, k > 0 ? 1u : 0u);
+                umma_commit(sdp_full);
+                mbar_wait(pds_full, ph);
+                mbar_wait(dq_empty, ph ^ 1);
+                tc_fence_after();
+                const uint64_t qmn = make_smem_desc_sw128(smem_u32(sQ + st * TILE16), 128 * 128, 1024);
+                const uint64_t domn = make_smem_desc_sw128(smem_u32(sDO + st * TILE16), 128 * 128, 1024);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) umma_f16(tDV, pT + (uint64_t)(k * 128), domn + (uint64_t)(k * 128), id_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) umma_f16(tDK, dsT + (uint64_t)(k * 128), qmn + (uint64_t)(k * 128), id_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t dsk = make_smem_desc_sw128(smem_u32(sDS) + (k >> 2) * TILE16 + (k & 3) * 32, 0, 1024);
+                    umma_f16(tDQ, dsk, kmn + (uint64_t)(k * 128), id_q, k > 0 ? 1u : 0u);
+                }
+                umma_commit(mma3_done);
+                umma_commit(&qdo_empty[st]);
+            }
+        }
+    } else {
+        // -------------------------------------------------------------------- math warps
+        const int mw = warp - 2;
+        const int qd = warp & 3, half = mw >> 2;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + kt * 4 + half * 2;
+        const unsigned int mbits[2] = {mb[0], mb[1]};
+        const float keep_scale = p.keep_scale;
+
+        auto flush_dq = [&](int i) {   // dQ_i (TMEM) -> fp32 global atomics; this thread owns 32 of the 64 columns of its row
+            uint32_t r[32];
+            tmem_ld32(tDQ + half * 32 + lane_off, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            const int qi = i * TQ + row;
+            if (qi < p.Np) {
+                float* dst = p.dq_acc + ((size_t)bh * p.Np + qi) * DH + half * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(r[c]));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
+        };
+
+        for (int i = 0; i < nq; ++i) {
+            const uint32_t ph = i & 1;
+            const int qi = i * TQ + row;
+            const bool rvalid = qi < p.Np;
+            const float lse = rvalid ? p.lse[(size_t)bh * p.Np + qi] : 0.f;
+            const float dl = rvalid ? p.delta[(size_t)bh * p.Np + qi] : 0.f;
+            const float lse2 = lse * LOG2E_F;
+            mbar_wait(sdp_full, ph);
+            tc_fence_after();
+            float pv[2][32], dsv[2][32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t rs[32], rd[32];
+                tmem_ld32(tS + half * 64 + c * 32 + lane_off, rs);
+                tmem_ld32(tDP + half * 64 + c * 32 + lane_off, rd);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float th = tanh_approx(__uint_as_float(rs[e]) * p.scale_over_clamp);
+                    float pr = ex2_approx(p.clamp * LOG2E_F * th - lse2);
+                    pr = (rvalid && ((mbits[c] >> e) & 1u)) ? pr : 0.f;
+                    pv[c][e] = pr;
+                    dsv[c][e] = __uint_as_float(rd[e]);
+                    rs[e] = __float_as_uint(th);
+                }
+                if (p.dropout_p > 0.f) {
+                    const unsigned long long kbase = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride +
+                                                     (unsigned long long)(k0 + half * 64 + c * 32);
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        const uint32_t h = hash_u32(p.seed, (kbase + e) >> 1);
+                        const bool k0_ = (h & 0xffffu) >= p.drop_thresh, k1_ = (h >> 16) >= p.drop_thresh;
+                        dsv[c][e] = k0_ ? dsv[c][e] * keep_scale : 0.f;
+                        dsv[c][e + 1] = k1_ ? dsv[c][e + 1] * keep_scale : 0.f;
+                        const float p0 = pv[c][e], p1 = pv[c][e + 1];
+                        // dS uses the un-dropped probability, dV the dropped one
+                        const float th0 = __uint_as_float(rs[e]), th1 = __uint_as_float(rs[e + 1]);
+                        dsv[c][e] = p0 * (dsv[c][e] - dl) * (1.f - th0 * th0) * p.scale;
+                        dsv[c][e + 1] = p1 * (dsv[c][e + 1] - dl) * (1.f - th1 * th1) * p.scale;
+                        pv[c][e] = k0_ ? p0 * keep_scale : 0.f;
+                        pv[c][e + 1] = k1_ ? p1 * keep_scale : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float th = __uint_as_float(rs[e]);
+                        dsv[c][e] = pv[c][e] * (dsv[c][e] - dl) * (1.f - th * th) * p.scale;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sdp_empty);
+            // P / dS smem tiles and the dQ accumulator of the previous query tile must have been consumed by its MMAs
+            if (i > 0) {
+                mbar_wait(mma3_done, (i - 1) & 1);
+                tc_fence_after();
+                flush_dq(i - 1);
+            }
+            uint8_t* prow = sP + half * TILE16 + row * 128;
+            uint8_t* drow = sDS + half * TILE16 + row * 128;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int chunk = c * 4 + g;
+                    const int off = (chunk ^ (row & 7)) << 4;
+                    *reinterpret_cast<uint4*>(prow + off) =
+                        make_uint4(pack_bf16(pv[c][g * 8], pv[c][g * 8 + 1]), pack_bf16(pv[c][g * 8 + 2], pv[c][g * 8 + 3]),
+                                   pack_bf16(pv[c][g * 8 + 4], pv[c][g * 8 + 5]), pack_bf16(pv[c][g * 8 + 6], pv[c][g * 8 + 7]));
+                    *reinterpret_cast<uint4*>(drow + off) =
+                        make_uint4(pack_bf16(dsv[c][g * 8], dsv[c][g * 8 + 1]), pack_bf16(dsv[c][g * 8 + 2], dsv[c][g * 8 + 3]),
+                                   pack_bf16(dsv[c][g * 8 + 4], dsv[c][g * 8 + 5]), pack_bf16(dsv[c][g * 8 + 6], dsv[c][g * 8 + 7]));
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
+        }
+        mbar_wait(mma3_done, (nq - 1) & 1);
+        tc_fence_after();
+        flush_dq(nq - 1);
+        // ---- dV, dK (TMEM lanes = keys): this thread stores 32 of the 64 columns of key row `row`
+        const int key = k0 + row;
+        {
+            uint32_t rv[32], rk[32];
+            tmem_ld32(tDV + half * 32 + lane_off, rv);
+            tmem_ld32(tDK + half * 32 + lane_off, rk);
+            tmem_ld_wait();
+            if (key < p.Np) {
+                __nv_bfloat16* dvp = p.dv + ((size_t)bh * p.Np + key) * DH + half * 32;
+                __nv_bfloat16* dkp = p.dk + ((size_t)bh * p.Np + key) * DH + half * 32;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    *reinterpret_cast<uint4*>(dvp + g * 8) =
+                        make_uint4(pack_bf16(__uint_as_float(rv[g * 8]), __uint_as_float(rv[g * 8 + 1])), pack_bf16(__uint_as_float(rv[g * 8 + 2]), __uint_as_float(rv[g * 8 + 3])),
+                                   pack_bf16(__uint_as_float(rv[g * 8 + 4]), __uint_as_float(rv[g * 8 + 5])), pack_bf16(__uint_as_float(rv[g * 8 + 6]), __uint_as_float(rv[g * 8 + 7])));
+                    *reinterpret_cast<uint4*>(dkp + g * 8) =
+                        make_uint4(pack_bf16(__uint_as_float(rk[g * 8]), __uint_as_float(rk[g * 8 + 1])), pack_bf16(__uint_as_float(rk[g * 8 + 2]), __uint_as_float(rk[g * 8 + 3])),
+                                   pack_bf16(__uint_as_float(rk[g * 8 + 4]), __uint_as_float(rk[g * 8 + 5])), pack_bf16(__uint_as_float(rk[g * 8 + 6]), __uint_as_float(rk[g * 8 + 7])));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host
 typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -365,4 +622,51 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     dim3 grid((a->Np + TQ - 1) / TQ, a->H, a->B);
     attn_fwd_tc_kernel<<<grid, 192, smem, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd_tc_kernel");
+}
+
+// dO = dOg * gate, delta = <dO, O>, d_gate — defined in attn.cu
+namespace b200 { int launch_attn_bwd_prep(const b200_attn_bwd_args* a, cudaStream_t st); }
+
+extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B200_REQUIRE(a && a->q && a->k && a->v && a->o && a->d_og && a->lse && a->ws_dO && a->ws_delta && a->dq && a->dk && a->dv && a->ws_maskbits,
+                 "attn_bwd: null pointer");
+    B200_REQUIRE(a->dim_head == 64, "attn_bwd: only dim_head 64 is built (got %d)", a->dim_head);
+    B200_REQUIRE(a->B > 0 && a->H > 0 && a->Np > 0 && a->B <= 65535 && a->H <= 65535, "attn_bwd: bad shape");
+    B200_REQUIRE(a->softclamp > 0.f && a->dropout_p >= 0.f && a->dropout_p < 1.f, "attn_bwd: bad softclamp / dropout");
+    if (int rc = launch_attn_bwd_prep(a, st)) return rc;
+    AttnBwdTcP p{};
+    p.nq = (a->Np + TQ - 1) / TQ;
+    p.mask_words = p.nq * 4;
+    p.maskbits = reinterpret_cast<const unsigned int*>(a->ws_maskbits);
+    {
+        const int total = a->B * p.mask_words;
+        attn_maskbits_kernel<<<(total + 127) / 128, 128, 0, st>>>(a->keymask, reinterpret_cast<unsigned int*>(a->ws_maskbits), a->B, a->Np, p.mask_words);
+        if (int rc = check_launch("attn_maskbits_kernel")) return rc;
+    }
+    const size_t nelem = (size_t)a->B * a->H * a->Np * DH;
+    cudaError_t e = cudaMemsetAsync(a->dq, 0, nelem * sizeof(float), st);
+    B200_REQUIRE(e == cudaSuccess, "attn_bwd: memset: %s", cudaGetErrorString(e));
+    p.lse = a->lse; p.delta = a->ws_delta; p.dq_acc = reinterpret_cast<float*>(a->dq);
+    p.dk = (__nv_bfloat16*)a->dk; p.dv = (__nv_bfloat16*)a->dv;
+    p.B = a->B; p.H = a->H; p.Np = a->Np;
+    p.scale = a->scale; p.clamp = a->softclamp; p.scale_over_clamp = a->scale / a->softclamp;
+    p.dropout_p = a->dropout_p;
+    p.drop_thresh = (unsigned int)(a->dropout_p * 65536.f);
+    p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
+    p.drop_stride = (a->Np + 1) & ~1;
+    p.seed = a->seed;
+    CUtensorMap tq, tk, tv, tdo;
+    const long long rows = (long long)a->B * a->H * a->Np;
+    if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows) || make_head_map(&tdo, a->ws_dO, rows)) return -1;
+    const int smem = 6 * TILE16 + 2 * PTILE + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        B200_REQUIRE(e2 == cudaSuccess, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
+        configured = true;
+    }
+    dim3 grid(p.nq, a->H, a->B);
+    attn_bwd_tc_kernel<<<grid, 320, smem, st>>>(tq, tk, tv, tdo, p);
+    return check_launch("attn_bwd_tc_kernel");
 }

@@ -212,9 +212,10 @@ struct QkvP {
     float* gate;
     int B, H, Np;
     // backward
-    const __nv_bfloat16 *dq, *dk, *dv;
+    const __nv_bfloat16 *dq, *dk, *dv, *dv_extra;
     const float* d_gate;
     __nv_bfloat16 *d_qkvg, *d_vfirst;
+    int dq_fp32;
 };
 __global__ void __launch_bounds__(256) qkv_post_fwd_kernel(const QkvP p) {
     const long long total = (long long)p.B * p.Np * p.H * 8;
@@ -270,7 +271,13 @@ __global__ void __launch_bounds__(256) qkv_post_bwd_kernel(const QkvP p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { cs[j] = p.cs[n * 32 + c * 4 + j]; sn[j] = p.sn[n * 32 + c * 4 + j]; }
         float x[8], y[8];
-        unpack8(*reinterpret_cast<const uint4*>(p.dq + src), x);
+        if (p.dq_fp32) {
+            const float4 a0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dq) + src);
+            const float4 a1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dq) + src + 4);
+            x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+        } else {
+            unpack8(*reinterpret_cast<const uint4*>(p.dq + src), x);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) { y[2 * j] = x[2 * j] * cs[j] + x[2 * j + 1] * sn[j]; y[2 * j + 1] = x[2 * j + 1] * cs[j] - x[2 * j] * sn[j]; }
         *reinterpret_cast<uint4*>(drow + hh * 64 + c * 8) = pack8(y);
@@ -279,6 +286,12 @@ __global__ void __launch_bounds__(256) qkv_post_bwd_kernel(const QkvP p) {
         for (int j = 0; j < 4; ++j) { y[2 * j] = x[2 * j] * cs[j] + x[2 * j + 1] * sn[j]; y[2 * j + 1] = x[2 * j + 1] * cs[j] - x[2 * j] * sn[j]; }
         *reinterpret_cast<uint4*>(drow + I + hh * 64 + c * 8) = pack8(y);
         unpack8(*reinterpret_cast<const uint4*>(p.dv + src), x);
+        if (p.dv_extra) {
+            float xe[8];
+            unpack8(*reinterpret_cast<const uint4*>(p.dv_extra + src), xe);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] += xe[j];
+        }
         if (p.v_first) {
             mix = sigmoidf_(__bfloat162float(row[3 * I + p.H + hh]) + p.mix_b[hh]);
             float vr[8], vf[8], o[8];
@@ -656,7 +669,7 @@ extern "C" int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stre
     if (fill_qkv(p, a)) return -1;
     B200_REQUIRE(a->dq && a->dk && a->dv && a->d_gate && a->d_qkvg && (!a->v_first || a->d_vfirst), "qkv_post_bwd: null pointer");
     p.dq = (const __nv_bfloat16*)a->dq; p.dk = (const __nv_bfloat16*)a->dk; p.dv = (const __nv_bfloat16*)a->dv; p.d_gate = a->d_gate;
-    p.d_qkvg = (__nv_bfloat16*)a->d_qkvg; p.d_vfirst = (__nv_bfloat16*)a->d_vfirst;
+    p.d_qkvg = (__nv_bfloat16*)a->d_qkvg; p.d_vfirst = (__nv_bfloat16*)a->d_vfirst; p.dq_fp32 = a->dq_fp32; p.dv_extra = (const __nv_bfloat16*)a->dv_extra;
     const long long total = (long long)a->B * a->Np * a->H * 8;
     qkv_post_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("qkv_post_bwd_kernel");

@@ -451,11 +451,10 @@ class Transformer(Module):
         def sub_attn(res, hcm, gain, mode, attn, pk, vf, colscale):
             br, rest, beta = ops.HcWidth.apply(res, *hcm.params(), gain, mode, Np)
             mix = attn.to_value_residual_mix
-            q, k, v, gate = ops.QkvProj.apply(br, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_v_head_gate.weight,
-                                              attn.to_v_head_gate.bias, mix[0].weight if mix is not None else None,
-                                              mix[0].bias if mix is not None else None, vf if mix is not None else None,
-                                              pk['qkv'], cs, sn, B, Np, H)
-            og = ops.AttnCore.apply(q, k, v, gate, mask_u8, p_drop, next_seed(), SOFTCLAMP)
+            og, v = ops.Attention.apply(br, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_v_head_gate.weight,
+                                        attn.to_v_head_gate.bias, mix[0].weight if mix is not None else None,
+                                        mix[0].bias if mix is not None else None, vf if mix is not None else None,
+                                        pk['qkv'], cs, sn, mask_u8, B, Np, H, p_drop, next_seed(), SOFTCLAMP)
             y = ops.OutProj.apply(og, attn.to_out.weight, pk['out'], colscale, mask_u8, B, Np)
             return ops.HcDepth.apply(rest, y, beta), (v if vf is None else vf)
 

@@ -15,7 +15,8 @@ from torch.autograd.function import once_differentiable
 from . import lib
 
 BF16, F32 = torch.bfloat16, torch.float32
-ATTN_FWD_ENTRY = 'b200_attn_fwd'   # tests may point this at 'b200_attn_fwd_legacy' to cross-check the two forward kernels
+ATTN_FWD_ENTRY = 'b200_attn_fwd'   # tests may point these at the '*_legacy' (mma.sync) entry points to cross-check the kernels
+ATTN_BWD_ENTRY = 'b200_attn_bwd'
 
 
 def _stream():
@@ -215,7 +216,7 @@ class QkvProj(Function):
         d_vfirst = torch.empty_like(v_first) if v_first is not None else None
         a = lib.make_args('b200_qkv_post_args', qkvg=qkvg, ld=ld, gate_bias=bg, mix_bias=bm, rot_cos=cs, rot_sin=sn, v_first=v_first,
                           gate=gate, dq=_c(dq), dk=_c(dk), dv=_c(dv), d_gate=_c(dgate), d_qkvg=d_qkvg, d_vfirst=d_vfirst,
-                          B=B, H=H, Np=Np, dim_head=64)
+                          B=B, H=H, Np=Np, dim_head=64, dq_fp32=int(dq.dtype == F32))
         lib.call('b200_qkv_post_bwd', a, _stream())
         dx = gemm(d_qkvg, wpack, T, Din, ncat, lda=ld, ldb=Din, b_mn=True)
         dW = grad_weight(d_qkvg, xn, T, ncat, Din, ldy=ld)
@@ -248,14 +249,80 @@ class AttnCore(Function):
         q, k, v, gate, mask, o, lse = ctx.saved_tensors
         dropout_p, seed, softclamp = ctx.meta
         B, H, Np, dh = q.shape
-        dq, dk, dv, ws_dO = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        legacy = ATTN_BWD_ENTRY.endswith('legacy')
+        dq = torch.empty(q.shape, device=q.device, dtype=BF16 if legacy else F32)   # tcgen05 backward accumulates dq in fp32
+        dk, dv, ws_dO = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
         ws_delta = torch.empty_like(lse)
         d_gate = torch.empty_like(gate)
+        ws = torch.empty(((Np + 127) // 128) * 4 * B, device=q.device, dtype=torch.int32)
         a = lib.make_args('b200_attn_bwd_args', q=q, k=k, v=v, o=o, d_og=_c(d_og), keymask=mask, gate=gate, lse=lse, ws_dO=ws_dO,
                           ws_delta=ws_delta, d_gate=d_gate, dq=dq, dk=dk, dv=dv, B=B, H=H, Np=Np, dim_head=dh, scale=dh ** -0.5,
-                          softclamp=softclamp, dropout_p=dropout_p, seed=seed)
-        lib.call('b200_attn_bwd', a, _stream())
+                          softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws)
+        lib.call(ATTN_BWD_ENTRY, a, _stream())
         return dq, dk, dv, d_gate, None, None, None, None
+
+
+class Attention(Function):
+    """Fused attention stage: ONE GEMM for to_q/to_k/to_v (+ head-gate and value-residual-mix logits), rotary + value
+    residual + gate post-processing, tcgen05 flash attention (softclamp, key mask, dropout, head gate). Returns the gated
+    head-merged output (input of to_out) and this layer's values (the first layer's feed every later layer, e2_tts.py:878,916).
+    One autograd node: q/k/v never enter the graph, and dq stays fp32 from the attention backward into the rotary inverse."""
+
+    @staticmethod
+    def forward(ctx, xn, wq, wk, wv, wg, bg, wm, bm, v_first, wpack, cs, sn, mask, B, Np, H, dropout_p, seed, softclamp):
+        T, Din = xn.shape
+        I = H * 64
+        dev = xn.device
+        has_mix = wm is not None
+        ncat = 3 * I + (2 if has_mix else 1) * H
+        ld = (ncat + 7) // 8 * 8
+        qkvg = gemm(xn, wpack, T, ncat, Din, ldd=ld)
+        q = torch.empty((B, H, Np, 64), device=dev, dtype=BF16)
+        k, v, o = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        gate = torch.empty((T, H), device=dev, dtype=F32)
+        a = lib.make_args('b200_qkv_post_args', qkvg=qkvg, ld=ld, gate_bias=bg, mix_bias=bm, rot_cos=cs, rot_sin=sn, v_first=v_first,
+                          q=q, k=k, v=v, gate=gate, B=B, H=H, Np=Np, dim_head=64)
+        lib.call('b200_qkv_post_fwd', a, _stream())
+        og = torch.empty((T, I), device=dev, dtype=BF16)
+        lse = torch.empty((B, H, Np), device=dev, dtype=F32)
+        ws = torch.empty(((Np + 127) // 128) * 4 * B, device=dev, dtype=torch.int32)
+        a = lib.make_args('b200_attn_fwd_args', q=q, k=k, v=v, keymask=mask, gate=gate, o=o, og=og, lse=lse, B=B, H=H, Np=Np,
+                          dim_head=64, scale=0.125, softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws)
+        lib.call(ATTN_FWD_ENTRY, a, _stream())
+        ctx.save_for_backward(xn, qkvg, gate, v_first, wpack, cs, sn, bg, bm, q, k, v, o, lse, mask)
+        ctx.meta = (B, Np, H, ncat, ld, has_mix, dropout_p, seed, softclamp)
+        return og, v
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_og, d_v_extra):
+        xn, qkvg, gate, v_first, wpack, cs, sn, bg, bm, q, k, v, o, lse, mask = ctx.saved_tensors
+        B, Np, H, ncat, ld, has_mix, dropout_p, seed, softclamp = ctx.meta
+        T, Din = xn.shape
+        I = H * 64
+        dev = xn.device
+        legacy = ATTN_BWD_ENTRY.endswith('legacy')
+        dq = torch.empty(q.shape, device=dev, dtype=BF16 if legacy else F32)
+        dk, dv, ws_dO = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        ws_delta = torch.empty_like(lse)
+        d_gate = torch.empty_like(gate)
+        ws = torch.empty(((Np + 127) // 128) * 4 * B, device=dev, dtype=torch.int32)
+        a = lib.make_args('b200_attn_bwd_args', q=q, k=k, v=v, o=o, d_og=_c(d_og), keymask=mask, gate=gate, lse=lse, ws_dO=ws_dO,
+                          ws_delta=ws_delta, d_gate=d_gate, dq=dq, dk=dk, dv=dv, B=B, H=H, Np=Np, dim_head=64, scale=0.125,
+                          softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws)
+        lib.call(ATTN_BWD_ENTRY, a, _stream())
+        d_qkvg = torch.empty((T, ld), device=dev, dtype=BF16)
+        d_vfirst = torch.empty_like(v_first) if v_first is not None else None
+        a = lib.make_args('b200_qkv_post_args', qkvg=qkvg, ld=ld, gate_bias=bg, mix_bias=bm, rot_cos=cs, rot_sin=sn, v_first=v_first,
+                          gate=gate, dq=dq, dk=dk, dv=dv, dv_extra=_c(d_v_extra), d_gate=d_gate, d_qkvg=d_qkvg, d_vfirst=d_vfirst,
+                          B=B, H=H, Np=Np, dim_head=64, dq_fp32=int(dq.dtype == F32))
+        lib.call('b200_qkv_post_bwd', a, _stream())
+        dx = gemm(d_qkvg, wpack, T, Din, ncat, lda=ld, ldb=Din, b_mn=True)
+        dW = grad_weight(d_qkvg, xn, T, ncat, Din, ldy=ld)
+        db = colsum(d_qkvg, T, ncat, ld)
+        return (dx, dW[:I], dW[I:2 * I], dW[2 * I:3 * I], dW[3 * I:3 * I + H], db[3 * I:3 * I + H],
+                dW[3 * I + H:3 * I + 2 * H] if has_mix else None, db[3 * I + H:3 * I + 2 * H] if has_mix else None,
+                d_vfirst, None, None, None, None, None, None, None, None, None, None)
 
 
 def _rowgate_bwd(dy, y, cs, mask, B, rpb, D):

@@ -89,8 +89,9 @@ size_t b200_attn_workspace_bytes(int32_t B, int32_t Np);
 int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream);        /* tcgen05 / TMEM / TMA kernel */
 int b200_attn_fwd_legacy(const b200_attn_fwd_args* a, b200_stream_t stream); /* mma.sync bring-up kernel, kept for cross-checks */
 
-/* backward: d_og bf16 [B*Np, H*64] -> dq,dk,dv bf16 [B,H,Np,64], d_gate fp32 [B*Np,H] (grad wrt the sigmoid
- * gate VALUE; may be NULL). ws_dO (bf16 [B,H,Np,64]) and ws_delta (fp32 [B,H,Np]) are caller workspaces. */
+/* backward: d_og bf16 [B*Np, H*64] -> dk,dv bf16 [B,H,Np,64], dq FP32 [B,H,Np,64] (accumulated with atomics across key
+ * tiles by the tcgen05 kernel; the legacy kernel writes bf16 dq), d_gate fp32 [B*Np,H] (grad wrt the sigmoid gate VALUE;
+ * may be NULL). ws_dO (bf16 [B,H,Np,64]), ws_delta (fp32 [B,H,Np]) and ws_maskbits are caller workspaces. */
 typedef struct {
     const void *q, *k, *v, *o, *d_og;
     const uint8_t* keymask;
@@ -101,8 +102,10 @@ typedef struct {
     int32_t B, H, Np, dim_head;
     float scale, softclamp, dropout_p;
     uint64_t seed;
+    void* ws_maskbits;
 } b200_attn_bwd_args;
-int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream);
+int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream);         /* tcgen05 / TMEM / TMA kernel, dq fp32 */
+int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t stream);  /* mma.sync bring-up kernels, dq bf16 */
 
 /* ------------------------------------------------------------------------------------------------
  * Hyper-connections (A.5; e2_tts.py:607, 673-678, 709-713, 870-882, 900-939), S = 4 residual streams held
@@ -190,8 +193,10 @@ typedef struct {
     const void* v_first;
     void *q, *k, *v; float* gate;
     const void *dq, *dk, *dv; const float* d_gate;
+    const void* dv_extra;   /* optional bf16 [B,H,Np,64] added to dv (value-residual gradients of later layers into layer 0) */
     void *d_qkvg, *d_vfirst;
     int32_t B, H, Np, dim_head;
+    int32_t dq_fp32;   /* bwd: dq is fp32 (tcgen05 attention backward) instead of bf16 */
 } b200_qkv_post_args;
 int b200_qkv_post_fwd(const b200_qkv_post_args* a, b200_stream_t stream);
 int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stream);

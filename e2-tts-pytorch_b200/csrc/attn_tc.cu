@@ -1,12 +1,13 @@
 // tcgen05 / TMEM / TMA flash attention FORWARD for the softclamped, key-masked, head-gated attention of the
 // E2-TTS multistream block (x-transformers Attend as configured by the reference: SURVEY A.4 steps 4-5).
 //
-// One CTA per (128-query tile, head, batch), 192 threads, warp-specialised:
+// One CTA per (128-query tile, head, batch), 320 threads, warp-specialised:
 //   warp 0 lane 0 : TMA producer  — Q once, then K_j / V_j tiles (128 keys x 64) into a 2-stage smem ring
 //   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T  (tcgen05.mma 128x128x16 x4, both operands K-major) into TMEM S[j%2]
 //                                   O_j = P_j V_j  (tcgen05.mma 128x64x16 x8, A = P from smem (K-major), B = V MN-major)
 //                                   into TMEM O[j%2]; S_{j+1} is issued before O_j so the tensor pipe never waits on softmax
-//   warps 2..5    : softmax       — one query ROW per thread (tcgen05.ld 32x32b: lane == row, no shuffles):
+//   warps 2..9    : softmax       — thread = (query row, key half): 64 of the 128 scores of its row (tcgen05.ld 32x32b:
+//                                   lane == row), row max exchanged between the two halves through smem;
 //                                   pass 1 row max of the raw scores, pass 2 softclamp (tanh) + exp2 + dropout,
 //                                   P_j written as bf16 into 128B-swizzled smem (the A operand of the PV MMA),
 //                                   partial O_j read back from TMEM and folded into fp32 registers with the usual
@@ -66,7 +67,7 @@ __global__ void attn_maskbits_kernel(const unsigned char* mask, unsigned int* bi
     bits[w] = v;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const AttnTcP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -86,6 +87,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* o_full = bars + 13;       // 2
     uint64_t* o_empty = bars + 15;      // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    float* s_xch = reinterpret_cast<float*>(bars + 20);   // [2 parities][2 halves][128 rows] row-max exchange, then row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
@@ -98,9 +100,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
-            mbar_init(&p_full[i], 4);
-            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+            mbar_init(&p_full[i], 8);
+            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8);
         }
         fence_barrier_init();
     }
@@ -165,34 +167,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else {
-        // -------------------------------------------------------------------- softmax warps (row per thread)
-        const int qd = warp & 3;
+        // -------------------------------------------------------------------- softmax warps: thread = (row, key half)
+        const int qd = warp & 3, half = (warp - 2) >> 2;
         const int row = qd * 32 + lane;
         const int qi = q0 + row;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words;
+        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + half * 2;
+        const uint32_t seedmix = seed_mix32(p.seed);
         const unsigned long long drop_row = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride;
-        float o_acc[DH];
+        float o_acc[32];
 #pragma unroll
-        for (int i = 0; i < DH; ++i) o_acc[i] = 0.f;
+        for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f, m_ref = -INFINITY;
         float m_hist0 = -INFINITY, m_hist1 = -INFINITY;
 
-        auto fold = [&](int t) {   // fold partial O of tile t (buffer t & 1) into o_acc
+        auto fold = [&](int t) {   // fold this thread's 32 columns of the partial O of tile t (buffer t & 1) into o_acc
             const int st = t & 1;
             mbar_wait(&o_full[st], (t >> 1) & 1);
             tc_fence_after();
             const float mt = st ? m_hist1 : m_hist0;
             const float c = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - mt) * LOG2E_F);
             m_ref = mt;
+            uint32_t r[32];
+            tmem_ld32(tO + st * 64 + half * 32 + lane_off, r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                uint32_t r[32];
-                tmem_ld32(tO + st * 64 + h2 * 32 + lane_off, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[h2 * 32 + i] = o_acc[h2 * 32 + i] * c + __uint_as_float(r[i]);
-            }
+            for (int i = 0; i < 32; ++i) o_acc[i] = o_acc[i] * c + __uint_as_float(r[i]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[st]);
@@ -200,21 +200,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
         for (int j = 0; j < nkv; ++j) {
             const int st = j & 1;
-            const uint4 mw = *reinterpret_cast<const uint4*>(mb + j * 4);
-            const unsigned int mbits[4] = {mw.x, mw.y, mw.z, mw.w};
+            const unsigned int mbits[2] = {mb[j * 4], mb[j * 4 + 1]};
+            const bool all_valid = (mbits[0] & mbits[1]) == 0xffffffffu;
             mbar_wait(&s_full[st], (j >> 1) & 1);
             tc_fence_after();
-            const uint32_t ts = tS + st * 128 + lane_off;
-            // pass 1: row max of the raw scores over the valid keys (tanh is monotone: clamp(max) == max(clamp))
+            const uint32_t ts = tS + st * 128 + half * 64 + lane_off;
+            // pass 1: max of the raw scores over this thread's 64 keys (tanh is monotone: clamp(max) == max(clamp))
             float rmax = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
                 tmem_ld32(ts + c * 32, r);
                 tmem_ld_wait();
+                if (all_valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) rmax = ((mbits[c] >> i) & 1u) ? fmaxf(rmax, __uint_as_float(r[i])) : rmax;
+                    for (int i = 0; i < 32; ++i) rmax = fmaxf(rmax, __uint_as_float(r[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) rmax = ((mbits[c] >> i) & 1u) ? fmaxf(rmax, __uint_as_float(r[i])) : rmax;
+                }
             }
+            float* xch = s_xch + st * 256;
+            xch[half * 128 + row] = rmax;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            rmax = fmaxf(rmax, xch[(half ^ 1) * 128 + row]);
             const float m_tile = (rmax == -INFINITY) ? -INFINITY : p.clamp * tanh_approx(rmax * p.scale_over_clamp);
             const float m_new = fmaxf(m_run, m_tile);
             const float ms = (m_new == -INFINITY) ? 0.f : m_new;
@@ -223,37 +232,40 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // the P buffer (and O buffer) of tile j-2 must have been consumed by its PV MMA: fold that partial now
             if (j >= 2) fold(j - 2);
             if (st) m_hist1 = ms; else m_hist0 = ms;
-            // pass 2: probabilities -> bf16 P tile in swizzled smem
-            uint8_t* pdst = sP + st * PTILE + row * 128;
+            // pass 2: probabilities -> bf16 P tile in swizzled smem (this half = one 64-key swizzle atom)
+            uint8_t* pdst = sP + st * PTILE + half * TILE16 + row * 128;
             const float msl = ms * LOG2E_F;
+            const float cl2 = p.clamp * LOG2E_F;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
                 tmem_ld32(ts + c * 32, r);
                 tmem_ld_wait();
                 float pv[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float sc = p.clamp * tanh_approx(__uint_as_float(r[i]) * p.scale_over_clamp);
-                    float e = ex2_approx(sc * LOG2E_F - msl);
-                    e = ((mbits[c] >> i) & 1u) ? e : 0.f;
-                    l_run += e;
+                    const float e = ex2_approx(cl2 * tanh_approx(__uint_as_float(r[i]) * p.scale_over_clamp) - msl);
                     pv[i] = e;
                 }
+                if (!all_valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) pv[i] = ((mbits[c] >> i) & 1u) ? pv[i] : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) l_run += pv[i];
                 if (p.dropout_p > 0.f) {
-                    const unsigned long long kbase = drop_row + (unsigned long long)(j * TKV + c * 32);
+                    const uint32_t pbase = (uint32_t)((drop_row + (unsigned long long)(j * TKV + half * 64 + c * 32)) >> 1);
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const uint32_t h = hash_u32(p.seed, (kbase + i) >> 1);
+                        const uint32_t h = hash_pair32(seedmix, pbase + (i >> 1));
                         pv[i] = ((h & 0xffffu) >= p.drop_thresh) ? pv[i] * p.keep_scale : 0.f;
                         pv[i + 1] = ((h >> 16) >= p.drop_thresh) ? pv[i + 1] * p.keep_scale : 0.f;
                     }
                 }
-                uint8_t* atom = pdst + (c >> 1) * TILE16;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const int chunk = (c & 1) * 4 + g;
-                    *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) =
+                    const int chunk = c * 4 + g;
+                    *reinterpret_cast<uint4*>(pdst + ((chunk ^ (row & 7)) << 4)) =
                         make_uint4(pack_bf16(pv[g * 8], pv[g * 8 + 1]), pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]),
                                    pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]));
                 }
@@ -265,14 +277,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         if (nkv >= 2) fold(nkv - 2);
         fold(nkv - 1);
-        // ---- epilogue: normalise, write O (ungated), Og (gated, head-merged) and LSE
+        // ---- epilogue: total row sum over both halves, normalise, write O (ungated), Og (gated, head-merged) and LSE
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        s_xch[half * 128 + row] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float l_tot = l_run + s_xch[(half ^ 1) * 128 + row];
         if (qi < p.Np) {
-            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+            const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
             const float gt = p.gate ? p.gate[((size_t)b * p.Np + qi) * p.H + hh] : 1.f;
-            __nv_bfloat16* orow = p.o + ((size_t)bh * p.Np + qi) * DH;
-            __nv_bfloat16* grow = p.og + ((size_t)b * p.Np + qi) * (size_t)(p.H * DH) + hh * DH;
+            __nv_bfloat16* orow = p.o + ((size_t)bh * p.Np + qi) * DH + half * 32;
+            __nv_bfloat16* grow = p.og + ((size_t)b * p.Np + qi) * (size_t)(p.H * DH) + hh * DH + half * 32;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = o_acc[g * 8 + i] * inv;
@@ -283,7 +299,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     make_uint4(pack_bf16(bf16_lo(u.x) * gt, bf16_hi(u.x) * gt), pack_bf16(bf16_lo(u.y) * gt, bf16_hi(u.y) * gt),
                                pack_bf16(bf16_lo(u.z) * gt, bf16_hi(u.z) * gt), pack_bf16(bf16_lo(u.w) * gt, bf16_hi(u.w) * gt));
             }
-            p.lse[(size_t)bh * p.Np + qi] = m_run + logf(l_run);
+            if (half == 0) p.lse[(size_t)bh * p.Np + qi] = m_run + logf(l_tot);
         }
     }
     tc_fence_before();
@@ -422,6 +438,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + kt * 4 + half * 2;
         const unsigned int mbits[2] = {mb[0], mb[1]};
+        const bool all_valid = (mbits[0] & mbits[1]) == 0xffffffffu;
+        const uint32_t seedmix = seed_mix32(p.seed);
         const float keep_scale = p.keep_scale;
 
         auto flush_dq = [&](int i) {   // dQ_i (TMEM) -> fp32 global atomics; this thread owns 32 of the 64 columns of its row
@@ -448,45 +466,42 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float lse2 = lse * LOG2E_F;
             mbar_wait(sdp_full, ph);
             tc_fence_after();
-            float pv[2][32], dsv[2][32];
+            uint32_t ppk[2][16], dpk[2][16];   // bf16-packed P_drop and dS of this thread's 64 keys
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t rs[32], rd[32];
                 tmem_ld32(tS + half * 64 + c * 32 + lane_off, rs);
                 tmem_ld32(tDP + half * 64 + c * 32 + lane_off, rd);
                 tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float th = tanh_approx(__uint_as_float(rs[e]) * p.scale_over_clamp);
-                    float pr = ex2_approx(p.clamp * LOG2E_F * th - lse2);
-                    pr = (rvalid && ((mbits[c] >> e) & 1u)) ? pr : 0.f;
-                    pv[c][e] = pr;
-                    dsv[c][e] = __uint_as_float(rd[e]);
-                    rs[e] = __float_as_uint(th);
-                }
+                uint32_t pbase = 0;
                 if (p.dropout_p > 0.f) {
                     const unsigned long long kbase = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride +
                                                      (unsigned long long)(k0 + half * 64 + c * 32);
+                    pbase = (uint32_t)(kbase >> 1);
+                }
 #pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        const uint32_t h = hash_u32(p.seed, (kbase + e) >> 1);
+                for (int e = 0; e < 32; e += 2) {
+                    float pr[2], ds[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float th = tanh_approx(__uint_as_float(rs[e + u]) * p.scale_over_clamp);
+                        float pe = ex2_approx(p.clamp * LOG2E_F * th - lse2);
+                        pe = (rvalid && (all_valid || ((mbits[c] >> (e + u)) & 1u))) ? pe : 0.f;
+                        pr[u] = pe;
+                        ds[u] = (1.f - th * th) * p.scale;           // d(clamped logit)/d(raw logit) * scale
+                    }
+                    float dp0 = __uint_as_float(rd[e]), dp1 = __uint_as_float(rd[e + 1]);
+                    float pd0 = pr[0], pd1 = pr[1];
+                    if (p.dropout_p > 0.f) {
+                        const uint32_t h = hash_pair32(seedmix, pbase + (e >> 1));
                         const bool k0_ = (h & 0xffffu) >= p.drop_thresh, k1_ = (h >> 16) >= p.drop_thresh;
-                        dsv[c][e] = k0_ ? dsv[c][e] * keep_scale : 0.f;
-                        dsv[c][e + 1] = k1_ ? dsv[c][e + 1] * keep_scale : 0.f;
-                        const float p0 = pv[c][e], p1 = pv[c][e + 1];
-                        // dS uses the un-dropped probability, dV the dropped one
-                        const float th0 = __uint_as_float(rs[e]), th1 = __uint_as_float(rs[e + 1]);
-                        dsv[c][e] = p0 * (dsv[c][e] - dl) * (1.f - th0 * th0) * p.scale;
-                        dsv[c][e + 1] = p1 * (dsv[c][e + 1] - dl) * (1.f - th1 * th1) * p.scale;
-                        pv[c][e] = k0_ ? p0 * keep_scale : 0.f;
-                        pv[c][e + 1] = k1_ ? p1 * keep_scale : 0.f;
+                        dp0 = k0_ ? dp0 * keep_scale : 0.f;
+                        dp1 = k1_ ? dp1 * keep_scale : 0.f;
+                        pd0 = k0_ ? pd0 * keep_scale : 0.f;          // dV uses the dropped probabilities, dS the un-dropped ones
+                        pd1 = k1_ ? pd1 * keep_scale : 0.f;
                     }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float th = __uint_as_float(rs[e]);
-                        dsv[c][e] = pv[c][e] * (dsv[c][e] - dl) * (1.f - th * th) * p.scale;
-                    }
+                    ppk[c][e >> 1] = pack_bf16(pd0, pd1);
+                    dpk[c][e >> 1] = pack_bf16(pr[0] * (dp0 - dl) * ds[0], pr[1] * (dp1 - dl) * ds[1]);
                 }
             }
             tc_fence_before();
@@ -504,14 +519,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int c = 0; c < 2; ++c) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const int chunk = c * 4 + g;
-                    const int off = (chunk ^ (row & 7)) << 4;
-                    *reinterpret_cast<uint4*>(prow + off) =
-                        make_uint4(pack_bf16(pv[c][g * 8], pv[c][g * 8 + 1]), pack_bf16(pv[c][g * 8 + 2], pv[c][g * 8 + 3]),
-                                   pack_bf16(pv[c][g * 8 + 4], pv[c][g * 8 + 5]), pack_bf16(pv[c][g * 8 + 6], pv[c][g * 8 + 7]));
-                    *reinterpret_cast<uint4*>(drow + off) =
-                        make_uint4(pack_bf16(dsv[c][g * 8], dsv[c][g * 8 + 1]), pack_bf16(dsv[c][g * 8 + 2], dsv[c][g * 8 + 3]),
-                                   pack_bf16(dsv[c][g * 8 + 4], dsv[c][g * 8 + 5]), pack_bf16(dsv[c][g * 8 + 6], dsv[c][g * 8 + 7]));
+                    const int off = ((c * 4 + g) ^ (row & 7)) << 4;
+                    *reinterpret_cast<uint4*>(prow + off) = make_uint4(ppk[c][g * 4], ppk[c][g * 4 + 1], ppk[c][g * 4 + 2], ppk[c][g * 4 + 3]);
+                    *reinterpret_cast<uint4*>(drow + off) = make_uint4(dpk[c][g * 4], dpk[c][g * 4 + 1], dpk[c][g * 4 + 2], dpk[c][g * 4 + 3]);
                 }
             }
             fence_proxy_async();
@@ -612,7 +622,7 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     CUtensorMap tq, tk, tv;
     const long long rows = (long long)a->B * a->H * a->Np;
     if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows)) return -1;
-    const int smem = 5 * TILE16 + 2 * PTILE + 256 + 1024;
+    const int smem = 5 * TILE16 + 2 * PTILE + 256 + 2048 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -620,7 +630,7 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
         configured = true;
     }
     dim3 grid((a->Np + TQ - 1) / TQ, a->H, a->B);
-    attn_fwd_tc_kernel<<<grid, 192, smem, st>>>(tq, tk, tv, p);
+    attn_fwd_tc_kernel<<<grid, 320, smem, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd_tc_kernel");
 }
 

@@ -79,12 +79,16 @@ struct TokState {
 
 // Stage the per-feature parameters once per block: sp[i] = { (gamma_i+1) * A[i][0..4], (gamma_i+1) * b[i], gamma_i+1, 0 }
 // (two 16-byte shared loads per feature instead of seven global loads; the (gamma+1) factor is folded in).
+// Layout: feature i = chunk*8 + e lives at sp[(e*2 + part) * nchunk + chunk], so the 32 lanes of a warp (consecutive chunks,
+// same e) read 32 consecutive float4 — bank-conflict free (the naive [i][2] layout was an 8-way conflict, ncu r1).
+__device__ __forceinline__ int sp_idx(int nchunk, int chunk, int e, int part) { return (e * 2 + part) * nchunk + chunk; }
 __device__ __forceinline__ void stage_params(const HcP& p, float4* sp) {
+    const int nchunk = p.D >> 3;
     for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
         const float g1 = __ldg(p.gamma + i) + 1.f;
         const float* a = p.afn + i * HT;
-        sp[2 * i] = make_float4(g1 * __ldg(a), g1 * __ldg(a + 1), g1 * __ldg(a + 2), g1 * __ldg(a + 3));
-        sp[2 * i + 1] = make_float4(g1 * __ldg(a + 4), g1 * __ldg(p.bfn + i), g1, 0.f);
+        sp[sp_idx(nchunk, i >> 3, i & 7, 0)] = make_float4(g1 * __ldg(a), g1 * __ldg(a + 1), g1 * __ldg(a + 2), g1 * __ldg(a + 3));
+        sp[sp_idx(nchunk, i >> 3, i & 7, 1)] = make_float4(g1 * __ldg(a + 4), g1 * __ldg(p.bfn + i), g1, 0.f);
     }
     __syncthreads();
 }
@@ -118,7 +122,7 @@ __device__ __forceinline__ void token_forward(const HcP& p, const float4* __rest
         if (c < nchunk) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float4 p0 = sp[2 * (c * 8 + e)], p1 = sp[2 * (c * 8 + e) + 1];
+                const float4 p0 = sp[sp_idx(nchunk, c, e, 0)], p1 = sp[sp_idx(nchunk, c, e, 1)];
 #pragma unroll
                 for (int s = 0; s < HS; ++s) {
                     const float rv = st.r[s][v][e];
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p, float* _
             if (c < nchunk) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float4 p0 = sp[2 * (c * 8 + e)], p1 = sp[2 * (c * 8 + e) + 1];   // already scaled by (gamma+1)
+                    const float4 p0 = sp[sp_idx(nchunk, c, e, 0)], p1 = sp[sp_idx(nchunk, c, e, 1)];   // already scaled by (gamma+1)
 #pragma unroll
                     for (int s = 0; s < HS; ++s) {
                         const float uu = ddc[s] * p1.y + dwc[s][0] * p0.x + dwc[s][1] * p0.y + dwc[s][2] * p0.z + dwc[s][3] * p0.w + dwc[s][4] * p1.x;

@@ -138,10 +138,17 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float 
     return (hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
-// Attention dropout: one 32-bit hash decides TWO neighbouring keys (16 bits each): keep iff half >= thresh, thresh = p * 65536.
-// idx = row_id * drop_stride + key with drop_stride even, so that (idx >> 1) pairs keys (2k, 2k+1) of one query row.
+// Attention dropout: one cheap 32-bit hash (murmur3 finaliser) decides TWO neighbouring keys (16 bits each): keep iff
+// half >= thresh, thresh = p * 65536. idx = row_id * drop_stride + key with drop_stride even, so (idx >> 1) pairs keys
+// (2k, 2k+1) of one query row; only the low 32 bits of the pair index are hashed (the pattern repeats after 2^33 scores).
+__device__ __forceinline__ uint32_t hash_pair32(uint32_t seedmix, uint32_t pair) {
+    uint32_t x = pair * 0x9E3779B1u + seedmix;
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t seed_mix32(uint64_t seed) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA77u); }
 __device__ __forceinline__ bool dropout_keep16(uint64_t seed, uint64_t idx, uint32_t thresh) {
-    const uint32_t h = hash_u32(seed, idx >> 1);
+    const uint32_t h = hash_pair32(seed_mix32(seed), (uint32_t)(idx >> 1));
     return ((idx & 1) ? (h >> 16) : (h & 0xffffu)) >= thresh;
 }
 

@@ -144,16 +144,21 @@ __device__ __forceinline__ void conv_rows(const float (&w)[31], const float (*sr
     }
 }
 
+// row validity (inside the sequence and not masked) is staged once per tile so that no global load sits behind a branch
+// on another global load (the first version chained mask -> dy loads per row and was latency-bound: ncu r1).
 __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const b200_dwconv_args a) {
     __shared__ float xs[CV_TN + 2 * CV_HALO][CV_TC];
+    __shared__ unsigned char sok[CV_TN + 2 * CV_HALO];
     const int n0 = blockIdx.x * CV_TN, c0 = blockIdx.y * CV_TC, b = blockIdx.z;
     const int pad = a.ksize / 2, shift = CV_HALO - pad;   // taps are centred inside the 31-wide register window
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
+    if (threadIdx.x < CV_TN + 2 * CV_HALO) sok[threadIdx.x] = tok_ok(a.mask, b, n0 - CV_HALO + (int)threadIdx.x, a.Np);
+    __syncthreads();
     for (int i = threadIdx.x; i < (CV_TN + 2 * CV_HALO) * (CV_TC / 8); i += 256) {
         const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
         const int n = n0 - CV_HALO + r;
         float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (tok_ok(a.mask, b, n, a.Np) && c0 + ch < a.D) {
+        if (sok[r] && c0 + ch < a.D) {
             const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + n) * a.D + c0 + ch);
             v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
             v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
@@ -175,20 +180,21 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const b200_dwconv_args 
     for (int jj = 0; jj < 16; ++jj) {
         const int n = n0 + tg * 16 + jj;
         if (n < a.Np) {
-            const float o = tok_ok(a.mask, b, n, a.Np) ? out[jj] / (1.f + __expf(-out[jj])) : 0.f;
+            const float o = sok[tg * 16 + jj + CV_HALO] ? out[jj] / (1.f + __expf(-out[jj])) : 0.f;
             y[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(o);
         }
     }
 }
 
 constexpr int CV_TILES_PER_BLOCK = 4;   // n-tiles marched by one block: weight/bias partial sums stay in registers across them
-constexpr int CV_P1 = 96;               // phase-1 rows (tile + halo each side = 94, padded to 4 x 24)
+constexpr int CV_P1 = 96;               // phase-1 rows (tile + halo each side = 94, padded to 8 x 12)
 
-__global__ void __launch_bounds__(256) dwconv_bwd_kernel(const b200_dwconv_args a) {
+__global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const b200_dwconv_args a) {
     extern __shared__ float sm[];
     float (*xs)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm);                              // [CV_P1 + 30] rows, token n0 - 30 + r
     float (*dps)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (CV_P1 + 30) * CV_TC);       // [CV_P1] rows, token n0 - 15 + r
     float (*sdw)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (2 * CV_P1 + 30) * CV_TC);   // [32] (31 taps + bias)
+    unsigned char* sok = reinterpret_cast<unsigned char*>(sm + (2 * CV_P1 + 30 + 32) * CV_TC);  // [CV_P1 + 30] row validity
     const int c0 = blockIdx.y * CV_TC, b = blockIdx.z;
     const int pad = a.ksize / 2, shift = CV_HALO - pad;
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
@@ -198,24 +204,24 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const b200_dwconv_args 
     const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
     const bool cok = c0 + cl < a.D;
     const float bias = cok ? a.bias[c0 + cl] : 0.f;
-    float w[31], wr[31], dwk[31];
+    float w[31], dwk[31];
 #pragma unroll
     for (int k = 0; k < 31; ++k) {
         w[k] = (cok && k >= shift && k - shift < a.ksize) ? a.weight[(size_t)(c0 + cl) * a.ksize + (k - shift)] : 0.f;
         dwk[k] = 0.f;
     }
-#pragma unroll
-    for (int k = 0; k < 31; ++k) wr[k] = w[30 - k];   // flipped taps for the transposed convolution (dx)
     float db = 0.f;
     const int ntiles = (a.Np + CV_TN - 1) / CV_TN;
     for (int tile = blockIdx.x * CV_TILES_PER_BLOCK; tile < min(ntiles, (int)(blockIdx.x + 1) * CV_TILES_PER_BLOCK); ++tile) {
         const int n0 = tile * CV_TN;
         __syncthreads();
+        if (threadIdx.x < CV_P1 + 30) sok[threadIdx.x] = tok_ok(a.mask, b, n0 - 2 * CV_HALO + (int)threadIdx.x, a.Np);
+        __syncthreads();
         for (int i = threadIdx.x; i < (CV_P1 + 30) * (CV_TC / 8); i += 256) {
             const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
             const int n = n0 - 2 * CV_HALO + r;
             float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (tok_ok(a.mask, b, n, a.Np) && c0 + ch < a.D) {
+            if (sok[r] && c0 + ch < a.D) {
                 const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + n) * a.D + c0 + ch);
                 v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
                 v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
@@ -223,35 +229,52 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const b200_dwconv_args 
 #pragma unroll
             for (int j = 0; j < 8; ++j) xs[r][ch + j] = v[j];
         }
-        __syncthreads();
-        // phase 1: d(pre-activation) for tokens n0-15 .. n0+80 (24 rows per thread group)
-        {
-            float pre[24];
-            conv_rows<24>(w, xs, tg * 24, cl, bias, pre);
+        for (int i = threadIdx.x; i < CV_P1 * (CV_TC / 8); i += 256) {   // dy tile (token n0 - 15 + r) staged into dps
+            const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
+            const int n = n0 - CV_HALO + r;
+            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (sok[r + CV_HALO] && c0 + ch < a.D) {
+                const uint4 u = *reinterpret_cast<const uint4*>(dy + ((size_t)b * a.Np + n) * a.D + c0 + ch);
+                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+                v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+            }
 #pragma unroll
-            for (int j = 0; j < 24; ++j) {
-                const int r = tg * 24 + j, n = n0 - CV_HALO + r;
-                float d = 0.f;
-                if (cok && tok_ok(a.mask, b, n, a.Np)) {
-                    const float s = 1.f / (1.f + __expf(-pre[j]));
-                    d = __bfloat162float(dy[((size_t)b * a.Np + n) * a.D + c0 + cl]) * s * (1.f + pre[j] * (1.f - s));
-                }
-                dps[r][cl] = d;
+            for (int j = 0; j < 8; ++j) dps[r][ch + j] = v[j];
+        }
+        __syncthreads();
+        // phase 1: d(pre-activation) = dy * silu'(pre), in place over the staged dy (two 12-row sweeps per thread group)
+#pragma unroll 1
+        for (int hp = 0; hp < 2; ++hp) {
+            float pre[12];
+            const int r0 = tg * 24 + hp * 12;
+            conv_rows<12>(w, xs, r0, cl, bias, pre);
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const float s = 1.f / (1.f + __expf(-pre[j]));
+                dps[r0 + j][cl] *= s * (1.f + pre[j] * (1.f - s));
             }
         }
         __syncthreads();
         // phase 2: dx = flipped conv of d_pre; weight / bias partial sums accumulate in registers across tiles
         if (cok) {
-            float dxo[16];
-            conv_rows<16>(wr, dps, tg * 16, cl, 0.f, dxo);
+            {
+                float wr[31], dxo[16];
+#pragma unroll
+                for (int k = 0; k < 31; ++k) wr[k] = w[30 - k];
+                conv_rows<16>(wr, dps, tg * 16, cl, 0.f, dxo);
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int r = tg * 16 + jj, n = n0 + r;
+                    if (n < a.Np) dx[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(sok[r + 2 * CV_HALO] ? dxo[jj] : 0.f);
+                }
+            }
             float win[46];
 #pragma unroll
             for (int j = 0; j < 46; ++j) win[j] = xs[tg * 16 + CV_HALO + j][cl];
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-                const int r = tg * 16 + jj, n = n0 + r;
-                if (n < a.Np) {
-                    dx[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(tok_ok(a.mask, b, n, a.Np) ? dxo[jj] : 0.f);
+                const int r = tg * 16 + jj;
+                if (n0 + r < a.Np) {
                     const float dpr = dps[r + CV_HALO][cl];
                     db += dpr;
 #pragma unroll
@@ -437,7 +460,7 @@ extern "C" int b200_dwconv_fwd(const b200_dwconv_args* a, b200_stream_t stream) 
 extern "C" int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream) {
     if (check_conv(a)) return -1;
     B200_REQUIRE(a->dy && a->dx && a->dweight && a->dbias, "dwconv_bwd: null pointer");
-    const size_t smem = (size_t)(2 * CV_P1 + 30 + 32) * CV_TC * sizeof(float);
+    const size_t smem = (size_t)(2 * CV_P1 + 30 + 32) * CV_TC * sizeof(float) + 128;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -198,7 +198,8 @@ def run_gpu(args):
         e0.record()
         out = orig_gemm(A, Bm, M, Nn, K, **kw)
         e1.record()
-        prof['events'].append((e0, e1))
+        prof['events'].append((e0, e1, (M, Nn, K, int(kw.get('a_mn', False)), int(kw.get('b_mn', False)), int(kw.get('split_k', 1)),
+                                        int(bool(kw.get('geglu'))), int(kw.get('A2') is not None))))
         prof['flops'] += 2.0 * M * Nn * K
         return out
 
@@ -213,7 +214,16 @@ def run_gpu(args):
             step(dev_mel, False)
         torch.cuda.synchronize()
         ops.gemm = orig_gemm
-    gemm_ms = sum(a.elapsed_time(b) for a, b in prof['events'])
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof['events'])
+    if os.environ.get('B200_GEMM_BREAKDOWN') and rank == 0:
+        agg = {}
+        for a, b, key in prof['events']:
+            t = agg.setdefault(key, [0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+        print('GEMM breakdown over %d profiled steps: (M, N, K, a_mn, b_mn, split, geglu, two_src) count ms TF/s' % nprof, file=sys.stderr)
+        for key, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print('  %-44s n=%4d  %8.3f ms  %7.1f TF/s' % (str(key), n, ms, 2.0 * key[0] * key[1] * key[2] * n / ms * 1e-9), file=sys.stderr)
     n_gemm = len(prof['events'])
     if rank != 0:
         if world > 1:

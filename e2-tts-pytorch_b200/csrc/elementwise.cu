@@ -325,7 +325,9 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh,
                                                          int inner, float dropout_p, unsigned long long seed) {
     const int nchunk = inner >> 3;
     const long long total = T * nchunk;
-    const float ks = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    const uint32_t thr = (uint32_t)(dropout_p * 65536.f);
+    const float ks = dropout_p > 0.f ? 65536.f / (65536.f - (float)thr) : 1.f;
+    const uint32_t seedmix = seed_mix32(seed);
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int c = (int)(i % nchunk);
         const long long row = i / nchunk;
@@ -335,10 +337,18 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh,
         unpack8(*reinterpret_cast<const uint4*>(dh + (size_t)row * inner + hcol), d);
         unpack8(*reinterpret_cast<const uint4*>(ug + pu), u);
         unpack8(*reinterpret_cast<const uint4*>(ug + pu + 64), g);
+        if (dropout_p > 0.f) {   // same pair hash as the GEGLU epilogue of the forward GEMM
+            const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned long long)inner + hcol) >> 1);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const uint32_t hsh = hash_pair32(seedmix, pbase + (j >> 1));
+                d[j] = ((hsh & 0xffffu) >= thr) ? d[j] * ks : 0.f;
+                d[j + 1] = ((hsh >> 16) >= thr) ? d[j + 1] * ks : 0.f;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float dd = d[j];
-            if (dropout_p > 0.f) dd = dropout_keep(seed, (unsigned long long)row * inner + hcol + j, dropout_p) ? dd * ks : 0.f;
+            const float dd = d[j];
             const float cdf = 0.5f * (1.f + erff(g[j] * 0.70710678118654752440f));
             const float pdf = 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
             du[j] = dd * g[j] * cdf;

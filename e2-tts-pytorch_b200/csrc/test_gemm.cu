@@ -39,7 +39,7 @@ static float* dev_f32(size_t n, float scale = 1.f, float off = 0.f) {
 }
 static double gelu(double x) { return 0.5 * x * (1.0 + erf(x * 0.70710678118654752440)); }
 
-struct Case { const char* name; int M, N, K; int a_mn, b_mn; int K1; int bias, colscale, rowmask, resid, geglu, split, fp32; };
+struct Case { const char* name; int M, N, K; int a_mn, b_mn; int K1; int bias, colscale, rowmask, resid, geglu, split, fp32; int tile = 0; };
 
 static int run_case(const Case& c) {
     const int M = c.M, N = c.N, K = c.K;
@@ -82,7 +82,7 @@ static int run_case(const Case& c) {
     g.M = M; g.N = N; g.K = K; g.a_mn_major = c.a_mn; g.b_mn_major = c.b_mn;
     g.D = D; g.ldd = ldd; g.d_fp32 = c.fp32; g.D2 = D2; g.ldd2 = ldd2;
     g.bias = bias; g.colscale = cs; g.rows_per_batch = rpb; g.rowmask = mask; g.resid = resid; g.ldr = ldr;
-    g.geglu = c.geglu; g.dropout_p = 0.f; g.seed = 0; g.split_k = c.split;
+    g.geglu = c.geglu; g.dropout_p = 0.f; g.seed = 0; g.split_k = c.split; g.force_tile = c.tile;
     int rc = b200_gemm(&g, 0);
     if (rc) { printf("[%s] b200_gemm rc=%d: %s\n", c.name, rc, b200_last_error()); return 1; }
     cudaError_t e = cudaDeviceSynchronize();
@@ -125,13 +125,13 @@ static int run_case(const Case& c) {
     return bad;
 }
 
-static void bench(const char* name, int M, int N, int K, int a_mn, int b_mn, int split, int fp32, int geglu) {
+static void bench(const char* name, int M, int N, int K, int a_mn, int b_mn, int split, int fp32, int geglu, int tile = 0) {
     long lda = a_mn ? M : K, ldb = b_mn ? N : K;
     __nv_bfloat16* A = dev_bf16((size_t)M * K, 0.1f); __nv_bfloat16* B = dev_bf16((size_t)N * K, 0.1f);
     void* D; CK(cudaMalloc(&D, (size_t)M * N * 4)); void* D2; CK(cudaMalloc(&D2, (size_t)M * N * 2));
     b200_gemm_args g = {};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.a_mn_major = a_mn; g.b_mn_major = b_mn;
-    g.D = D; g.ldd = geglu ? N / 2 : N; g.d_fp32 = fp32; g.split_k = split; g.geglu = geglu; g.D2 = geglu ? D2 : nullptr; g.ldd2 = N;
+    g.D = D; g.ldd = geglu ? N / 2 : N; g.d_fp32 = fp32; g.split_k = split; g.geglu = geglu; g.D2 = geglu ? D2 : nullptr; g.ldd2 = N; g.force_tile = tile;
     for (int i = 0; i < 3; ++i) if (b200_gemm(&g, 0)) { printf("bench %s: %s\n", name, b200_last_error()); return; }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int it = 20;
@@ -141,7 +141,7 @@ static void bench(const char* name, int M, int N, int K, int a_mn, int b_mn, int
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("bench %s failed: %s\n", name, cudaGetErrorString(e)); exit(3); }
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= it;
-    printf("bench %-24s M=%d N=%d K=%d split=%d: %.3f ms  %.1f TFLOP/s\n", name, M, N, K, split, ms, 2.0 * M * N * K / ms * 1e-9);
+    printf("bench %-24s tile=%d M=%d N=%d K=%d split=%d: %.3f ms  %.1f TFLOP/s\n", name, tile, M, N, K, split, ms, 2.0 * M * N * K / ms * 1e-9);
     cudaFree(A); cudaFree(B); cudaFree(D); cudaFree(D2);
 }
 
@@ -163,6 +163,7 @@ int main(int argc, char** argv) {
     };
     int bad = 0;
     for (auto& c : cases) bad += run_case(c);
+    for (auto c : cases) { c.tile = 2; bad += run_case(c); }   // same cases on the 256 x 128 CTA tile
     printf("correctness: %d failing case(s)\n", bad);
     if (argc > 1) {
         bench("ff-in (geglu)", 16896, 4096, 512, 0, 0, 1, 0, 1);
@@ -173,6 +174,15 @@ int main(int argc, char** argv) {
         bench("dW ff-in", 4096, 512, 16896, 1, 1, 4, 1, 0);
         bench("dW attn-out split16", 512, 512, 16896, 1, 1, 16, 1, 0);
         bench("square 8192", 8192, 8192, 8192, 0, 0, 1, 0, 0);
+        for (int tile = 1; tile <= 2; ++tile) {
+            bench("ff-in (geglu)", 16896, 4096, 512, 0, 0, 1, 0, 1, tile);
+            bench("ff-out", 16896, 512, 2048, 0, 0, 1, 0, 0, tile);
+            bench("qkv", 16896, 1552, 512, 0, 0, 1, 0, 0, tile);
+            bench("cross (S streams)", 67584, 512, 768, 0, 0, 1, 0, 0, tile);
+            bench("dX ff-in", 16896, 512, 4096, 0, 1, 1, 0, 0, tile);
+            bench("dW ff-in", 4096, 512, 16896, 1, 1, 4, 1, 0, tile);
+            bench("square 8192", 8192, 8192, 8192, 0, 0, 1, 0, 0, tile);
+        }
     }
     return bad ? 1 : 0;
 }

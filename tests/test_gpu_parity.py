@@ -451,3 +451,32 @@ def test_attention_tcgen05_backward_matches_mma_sync_backward(pkg, Np, masked, d
             ops.ATTN_BWD_ENTRY = 'b200_attn_bwd'
     for nm, a, b_ in zip(['dq', 'dk', 'dv', 'dgate'], res['b200_attn_bwd'], res['b200_attn_bwd_legacy']):
         assert rel_l2(a, b_) < 2e-2, (nm, rel_l2(a, b_))
+
+
+def test_feedforward_dropout_mask_is_consistent_between_forward_and_backward(pkg):
+    """GEGLU dropout (counter-based pair hash in the GEMM epilogue, recomputed by geglu_bwd): directional-derivative check."""
+    torch.manual_seed(8)
+    ops, mods = pkg.ops, pkg.modules
+    B, Np, d = 2, 96, 128
+    T = B * Np
+    ff = mods.FeedForward(d, 4, 0.).to(dev())
+    lin1, lin2 = ff.ff[0].proj, ff.ff[2]
+    inner = lin2.weight.shape[1]
+    nb = inner // 64
+    w1p = bf(lin1.weight.detach().view(2, nb, 64, d).transpose(0, 1).reshape(2 * inner, d))
+    b1p = lin1.bias.detach().view(2, nb, 64).transpose(0, 1).reshape(2 * inner).contiguous()
+    w2p = bf(lin2.weight.detach())
+    x = bf(torch.randn(T, d, device=dev()))
+    run = lambda xx, seed: ops.FeedForward.apply(xx, lin1.weight, lin1.bias, lin2.weight, lin2.bias, w1p, b1p, w2p, None, B, Np, 0.3, seed)
+    x1 = x.clone().requires_grad_()
+    y1 = run(x1, 77)
+    w = torch.randn_like(y1, dtype=torch.float32)
+    (dx,) = torch.autograd.grad((y1.float() * w).sum(), [x1])
+    dirn = bf(torch.randn_like(x.float()))
+    eps = 0.125
+    y2 = run(bf(x.float() + eps * dirn.float()), 77)
+    lhs = float(((y2.float() - y1.float()) * w).sum()) / eps
+    rhs = float((dx.float() * dirn.float()).sum())
+    assert abs(lhs - rhs) <= 0.08 * abs(rhs) + 1.0, (lhs, rhs)
+    assert rel_l2(run(x, 77).float().cpu(), y1.float().cpu()) == 0.0          # deterministic for a fixed seed
+    assert rel_l2(run(x, 78).float().cpu(), y1.float().cpu()) > 1e-2          # and seed-dependent

@@ -473,10 +473,11 @@ def test_feedforward_dropout_mask_is_consistent_between_forward_and_backward(pkg
     w = torch.randn_like(y1, dtype=torch.float32)
     (dx,) = torch.autograd.grad((y1.float() * w).sum(), [x1])
     dirn = bf(torch.randn_like(x.float()))
-    eps = 0.125
-    y2 = run(bf(x.float() + eps * dirn.float()), 77)
-    lhs = float(((y2.float() - y1.float()) * w).sum()) / eps
-    rhs = float((dx.float() * dirn.float()).sum())
-    assert abs(lhs - rhs) <= 0.08 * abs(rhs) + 1.0, (lhs, rhs)
+    eps = 0.0625   # central difference: the GEGLU is nonlinear, second-order terms cancel
+    xp, xm = bf(x.float() + eps * dirn.float()), bf(x.float() - eps * dirn.float())
+    step = (xp.float() - xm.float())          # the perturbation actually applied after bf16 rounding
+    lhs = float(((run(xp, 77).float() - run(xm, 77).float()) * w).sum())
+    rhs = float((dx.float() * step).sum())
+    assert abs(lhs - rhs) <= 0.1 * abs(rhs) + 2.0, (lhs, rhs)
     assert rel_l2(run(x, 77).float().cpu(), y1.float().cpu()) == 0.0          # deterministic for a fixed seed
     assert rel_l2(run(x, 78).float().cpu(), y1.float().cpu()) > 1e-2          # and seed-dependent

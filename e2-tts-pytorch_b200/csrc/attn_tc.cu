@@ -442,18 +442,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t seedmix = seed_mix32(p.seed);
         const float keep_scale = p.keep_scale;
 
-        auto flush_dq = [&](int i) {   // dQ_i (TMEM) -> fp32 global atomics; this thread owns 32 of the 64 columns of its row
+        float* dq_stg = reinterpret_cast<float*>(sDS + PTILE + 256) + mw * (32 * 33);
+        auto flush_dq = [&](int i) {   // dQ_i (TMEM) -> fp32 global atomics; this warp owns 32 rows x 32 of the 64 columns
             uint32_t r[32];
             tmem_ld32(tDQ + half * 32 + lane_off, r);
             tmem_ld_wait();
             tc_fence_before();
-            const int qi = i * TQ + row;
-            if (qi < p.Np) {
-                float* dst = p.dq_acc + ((size_t)bh * p.Np + qi) * DH + half * 32;
+            float v[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) atomicAdd(dst + c, __uint_as_float(r[c]));
-            }
-            __syncwarp();
+            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]);
+            const int q0r = i * TQ + qd * 32;
+            warp_red_rows_f32(dq_stg, v, p.dq_acc + (size_t)bh * p.Np * DH + half * 32, DH, q0r, p.Np, 32, lane);
             if (lane == 0) mbar_arrive(dq_empty);
         };
 
@@ -669,7 +668,7 @@ extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) 
     CUtensorMap tq, tk, tv, tdo;
     const long long rows = (long long)a->B * a->H * a->Np;
     if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows) || make_head_map(&tdo, a->ws_dO, rows)) return -1;
-    const int smem = 6 * TILE16 + 2 * PTILE + 256 + 1024;
+    const int smem = 6 * TILE16 + 2 * PTILE + 256 + 8 * 32 * 33 * 4 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

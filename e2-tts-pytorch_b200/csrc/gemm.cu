@@ -47,8 +47,8 @@ struct GemmSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
     static constexpr int kStages = (MH == 1) ? 6 : 4;
     static constexpr int TILE_BYTES = kStages * STAGE_BYTES;
-    static constexpr int BAR_BYTES = 256;
-    static constexpr int STG_BYTES = 8 * 4096;   // one 32 x 128 B staging tile per epilogue warp
+    static constexpr int BAR_BYTES = 160;
+    static constexpr int STG_BYTES = 8 * 4224;   // per epilogue warp: 32 x 128 B bf16 staging tile, or 32 x 33 fp32 for split-K atomics
     static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // + slack for manual 1024B alignment
 };
 
@@ -222,7 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float* cs = (p.colscale && row_ok) ? p.colscale + (long long)(row / p.rows_per_batch) * p.N : nullptr;
 
             if (!p.geglu) {
-                uint8_t* stg = stg_base + ew * 4096;
+                uint8_t* stg = stg_base + ew * 4224;
                 const int row0 = tm * BMT + mh * BM + q * 32;
                 uint4 held[8];   // bf16 pieces of an even chunk, kept until its odd partner completes a 128-byte row segment
 #pragma unroll 1
@@ -235,7 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (col0 >= p.N) continue;                       // warp-uniform
                     const int nvalid = min(32, p.N - col0);
                     const bool pair_full = !p.d_fp32 && (tn * BN + (c & ~1) * 32 + 64 <= p.N);   // warp-uniform: staged 128-byte rows
-                    if (!row_ok && !pair_full) continue;
+                    if (!row_ok && !pair_full && !p.atomic_out) continue;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -266,10 +266,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(rp[j]);
                         }
                     }
-                    if (p.d_fp32) {
+                    if (p.d_fp32 && p.atomic_out) {
+                        warp_red_rows_f32(reinterpret_cast<float*>(stg), v, reinterpret_cast<float*>(p.D) + col0, p.ldd, row0, p.M, nvalid, lane);
+                    } else if (p.d_fp32) {
                         float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
-                        if (p.atomic_out) {
-                            for (int j = 0; j < nvalid; ++j) atomicAdd(dp + j, v[j]);
+                        if (!row_ok) {
                         } else if (nvalid == 32 && (p.ldd & 3) == 0) {
 #pragma unroll
                             for (int g = 0; g < 8; ++g)
@@ -314,7 +315,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tmem_ld_wait();
                     const int colp = tn * BN + c * 32;         // packed column of u (GEGLU requires N % 128 == 0: always in range)
                     const int hcol0 = tn * 64 + c * 32;        // hidden-unit column
-                    uint8_t* stg = stg_base + ew * 4096;
+                    uint8_t* stg = stg_base + ew * 4224;
                     const int row0 = tm * BMT + mh * BM + q * 32;
                     float u[32], g[32];
 #pragma unroll

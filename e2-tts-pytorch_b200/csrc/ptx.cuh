@@ -119,6 +119,23 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
     return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Coalesced fp32 accumulation of a row-per-lane 32 x 32 block: lane l holds v[0..31] = 32 consecutive columns of row (row0 + l).
+// The block is transposed through a padded smem tile so that every RED instruction adds 32 CONSECUTIVE floats of one row
+// (one 128-byte L2 transaction instead of 32 scattered 4-byte ones).  stg: 32 x 33 floats, private to the warp.
+__device__ __forceinline__ void warp_red_rows_f32(float* stg, const float (&v)[32], float* base, long long ld, int row0, int nrows_total,
+                                                  int ncols_valid, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = v[c];
+    __syncwarp();
+    if (lane < ncols_valid) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r)
+            if (row0 + r < nrows_total) atomicAdd(base + (long long)(row0 + r) * ld + lane, stg[r * 33 + lane]);
+    }
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

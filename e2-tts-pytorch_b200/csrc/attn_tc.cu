@@ -311,15 +311,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ================================================================================================ backward
-// One CTA per (128-key tile, head, batch), 320 threads:
+// One CTA per (128-key tile, head, batch), 576 threads:
 //   warp 0 lane 0 : TMA producer — K, V once; Q_i / dO_i tiles (128 queries) through a 2-stage ring
 //   warp 1 lane 0 : MMA issuer   — per query tile i:  S = Q_i K^T, dP = dO_i V^T           (128x128x16 x4 each, K-major operands)
 //                                   then, once the math warps have written P and dS (bf16) to swizzled smem:
 //                                   dV += P^T dO_i, dK += dS^T Q_i (A MN-major from the P / dS tiles, B MN-major)
 //                                   dQ_i = dS K                    (A K-major dS tile, B = K tile MN-major)
-//   warps 2..9    : math         — row r = 32*(warp%4)+lane, key half = (warp-2)/4: recompute softclamp + softmax from the
-//                                   saved LSE, dS = P (dP - delta)(1 - tanh^2) scale, write P_drop / dS tiles, flush dQ_i
-//                                   from TMEM with fp32 global atomics, finally store dK, dV.
+//   warps 2..17   : math         — row r = 32*(warp%4)+lane, key quarter = (warp-2)/4 (4 warps per scheduler hide the MUFU /
+//                                   TMEM latencies): recompute softclamp + softmax from the saved LSE,
+//                                   dS = P (dP - delta)(1 - tanh^2) scale, write P_drop / dS tiles; warps 2..9 also flush dQ_i
+//                                   from TMEM with coalesced fp32 atomics and finally store dK, dV.
 // TMEM columns: S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448).
 struct AttnBwdTcP {
     const unsigned int* maskbits; int mask_words;
@@ -332,7 +333,7 @@ struct AttnBwdTcP {
     unsigned long long seed;
 };
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmDO, const AttnBwdTcP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -364,7 +365,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
         mbar_init(kv_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 8); mbar_init(pds_full, 8); mbar_init(mma3_done, 1); mbar_init(dq_empty, 8);
+        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 16); mbar_init(pds_full, 16); mbar_init(mma3_done, 1); mbar_init(dq_empty, 8);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -433,16 +434,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     } else {
         // -------------------------------------------------------------------- math warps
         const int mw = warp - 2;
-        const int qd = warp & 3, half = mw >> 2;
+        const int qd = warp & 3, part = mw >> 2;   // part: which 32 of the tile's 128 keys
+        const int half = part & 1;                 // dQ / dK / dV column half handled by warps with part < 2
+        const bool flusher = part < 2;
         const int row = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + kt * 4 + half * 2;
-        const unsigned int mbits[2] = {mb[0], mb[1]};
-        const bool all_valid = (mbits[0] & mbits[1]) == 0xffffffffu;
+        const unsigned int mbits1 = p.maskbits[(size_t)b * p.mask_words + kt * 4 + part];
+        const bool all_valid = mbits1 == 0xffffffffu;
         const uint32_t seedmix = seed_mix32(p.seed);
         const float keep_scale = p.keep_scale;
 
-        float* dq_stg = reinterpret_cast<float*>(sDS + PTILE + 256) + mw * (32 * 33);
+        float* dq_stg = reinterpret_cast<float*>(sDS + PTILE + 256) + (mw & 7) * (32 * 33);
         auto flush_dq = [&](int i) {   // dQ_i (TMEM) -> fp32 global atomics; this warp owns 32 rows x 32 of the 64 columns
             uint32_t r[32];
             tmem_ld32(tDQ + half * 32 + lane_off, r);
@@ -465,17 +467,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float lse2 = lse * LOG2E_F;
             mbar_wait(sdp_full, ph);
             tc_fence_after();
-            uint32_t ppk[2][16], dpk[2][16];   // bf16-packed P_drop and dS of this thread's 64 keys
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            uint32_t ppk[16], dpk[16];   // bf16-packed P_drop and dS of this thread's 32 keys
+            {
                 uint32_t rs[32], rd[32];
-                tmem_ld32(tS + half * 64 + c * 32 + lane_off, rs);
-                tmem_ld32(tDP + half * 64 + c * 32 + lane_off, rd);
+                tmem_ld32(tS + part * 32 + lane_off, rs);
+                tmem_ld32(tDP + part * 32 + lane_off, rd);
                 tmem_ld_wait();
                 uint32_t pbase = 0;
                 if (p.dropout_p > 0.f) {
                     const unsigned long long kbase = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride +
-                                                     (unsigned long long)(k0 + half * 64 + c * 32);
+                                                     (unsigned long long)(k0 + part * 32);
                     pbase = (uint32_t)(kbase >> 1);
                 }
 #pragma unroll
@@ -485,7 +486,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     for (int u = 0; u < 2; ++u) {
                         const float th = tanh_approx(__uint_as_float(rs[e + u]) * p.scale_over_clamp);
                         float pe = ex2_approx(p.clamp * LOG2E_F * th - lse2);
-                        pe = (rvalid && (all_valid || ((mbits[c] >> (e + u)) & 1u))) ? pe : 0.f;
+                        pe = (rvalid && (all_valid || ((mbits1 >> (e + u)) & 1u))) ? pe : 0.f;
                         pr[u] = pe;
                         ds[u] = (1.f - th * th) * p.scale;           // d(clamped logit)/d(raw logit) * scale
                     }
@@ -499,8 +500,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         pd0 = k0_ ? pd0 * keep_scale : 0.f;          // dV uses the dropped probabilities, dS the un-dropped ones
                         pd1 = k1_ ? pd1 * keep_scale : 0.f;
                     }
-                    ppk[c][e >> 1] = pack_bf16(pd0, pd1);
-                    dpk[c][e >> 1] = pack_bf16(pr[0] * (dp0 - dl) * ds[0], pr[1] * (dp1 - dl) * ds[1]);
+                    ppk[e >> 1] = pack_bf16(pd0, pd1);
+                    dpk[e >> 1] = pack_bf16(pr[0] * (dp0 - dl) * ds[0], pr[1] * (dp1 - dl) * ds[1]);
                 }
             }
             tc_fence_before();
@@ -510,18 +511,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (i > 0) {
                 mbar_wait(mma3_done, (i - 1) & 1);
                 tc_fence_after();
-                flush_dq(i - 1);
+                if (flusher) flush_dq(i - 1);
             }
-            uint8_t* prow = sP + half * TILE16 + row * 128;
-            uint8_t* drow = sDS + half * TILE16 + row * 128;
+            uint8_t* prow = sP + (part >> 1) * TILE16 + row * 128;
+            uint8_t* drow = sDS + (part >> 1) * TILE16 + row * 128;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int off = ((c * 4 + g) ^ (row & 7)) << 4;
-                    *reinterpret_cast<uint4*>(prow + off) = make_uint4(ppk[c][g * 4], ppk[c][g * 4 + 1], ppk[c][g * 4 + 2], ppk[c][g * 4 + 3]);
-                    *reinterpret_cast<uint4*>(drow + off) = make_uint4(dpk[c][g * 4], dpk[c][g * 4 + 1], dpk[c][g * 4 + 2], dpk[c][g * 4 + 3]);
-                }
+            for (int g = 0; g < 4; ++g) {
+                const int off = (((part & 1) * 4 + g) ^ (row & 7)) << 4;
+                *reinterpret_cast<uint4*>(prow + off) = make_uint4(ppk[g * 4], ppk[g * 4 + 1], ppk[g * 4 + 2], ppk[g * 4 + 3]);
+                *reinterpret_cast<uint4*>(drow + off) = make_uint4(dpk[g * 4], dpk[g * 4 + 1], dpk[g * 4 + 2], dpk[g * 4 + 3]);
             }
             fence_proxy_async();
             __syncwarp();
@@ -529,10 +527,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(mma3_done, (nq - 1) & 1);
         tc_fence_after();
-        flush_dq(nq - 1);
-        // ---- dV, dK (TMEM lanes = keys): this thread stores 32 of the 64 columns of key row `row`
+        if (flusher) flush_dq(nq - 1);
+        // ---- dV, dK (TMEM lanes = keys): a flusher thread stores 32 of the 64 columns of key row `row`
         const int key = k0 + row;
-        {
+        if (flusher) {
             uint32_t rv[32], rk[32];
             tmem_ld32(tDV + half * 32 + lane_off, rv);
             tmem_ld32(tDK + half * 32 + lane_off, rk);
@@ -676,6 +674,6 @@ extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) 
         configured = true;
     }
     dim3 grid(p.nq, a->H, a->B);
-    attn_bwd_tc_kernel<<<grid, 320, smem, st>>>(tq, tk, tv, tdo, p);
+    attn_bwd_tc_kernel<<<grid, 576, smem, st>>>(tq, tk, tv, tdo, p);
     return check_launch("attn_bwd_tc_kernel");
 }

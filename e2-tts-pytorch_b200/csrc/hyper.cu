@@ -168,7 +168,7 @@ __device__ __forceinline__ const float* norm_gain(const HcP& p, long long tok) {
 }
 
 template <int VPT>
-__global__ void __launch_bounds__(256) hc_width_fwd_kernel(const HcP p) {
+__global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(const HcP p) {
     extern __shared__ float4 sp[];
     stage_params(p, sp);
     const int lane = threadIdx.x & 31;

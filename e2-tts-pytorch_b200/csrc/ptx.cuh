@@ -122,13 +122,31 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
 // Coalesced fp32 accumulation of a row-per-lane 32 x 32 block: lane l holds v[0..31] = 32 consecutive columns of row (row0 + l).
 // The block is transposed through a padded smem tile so that every RED instruction adds 32 CONSECUTIVE floats of one row
 // (one 128-byte L2 transaction instead of 32 scattered 4-byte ones).  stg: 32 x 33 floats, private to the warp.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void warp_red_rows_f32(float* stg, const float (&v)[32], float* base, long long ld, int row0, int nrows_total,
                                                   int ncols_valid, int lane) {
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = v[c];
     __syncwarp();
-    if (lane < ncols_valid) {
+    if (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+        // 16-byte vector reductions (REDG.F32x4): 8 lanes cover the 128 bytes of a row, 4 rows per instruction
+        const int cg = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            if (row0 + r < nrows_total) {
+                const float* sp = stg + r * 33 + cg;
+                float* dst = base + (long long)(row0 + r) * ld + cg;
+                if (cg + 4 <= ncols_valid) red_add_v4(dst, sp[0], sp[1], sp[2], sp[3]);
+                else
+                    for (int j = 0; j < 4; ++j)
+                        if (cg + j < ncols_valid) atomicAdd(dst + j, sp[j]);
+            }
+        }
+    } else if (lane < ncols_valid) {
 #pragma unroll 4
         for (int r = 0; r < 32; ++r)
             if (row0 + r < nrows_total) atomicAdd(base + (long long)(row0 + r) * ld + lane, stg[r * 33 + lane]);

@@ -254,7 +254,7 @@ def run_gpu(args):
                      'step_flops': fl, 'step_tensor_frac': fl / (ms_dev * 1e-3) / 1e12 / peak_tf},
     }
     if world == 1 and not args.no_cpu:
-        line['cpu_baseline'] = run_cpu(CONFIGS[args.config], steps=2, warmup=1, batch=2, budget_s=90.0)
+        line['cpu_baseline'] = run_cpu(CONFIGS[args.config], steps=1, warmup=1, batch=1, budget_s=60.0)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -274,7 +274,7 @@ def main():
         if int(os.environ.get('RANK', '0')) != 0:
             return
         cfg = CONFIGS[args.config]
-        r = run_cpu(cfg, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1), batch=2, budget_s=150.0)
+        r = run_cpu(cfg, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1), batch=1, budget_s=120.0)
         print(json.dumps({
             'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'mel-frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

@@ -320,42 +320,68 @@ __global__ void __launch_bounds__(256) qkv_post_bwd_kernel(const QkvP p) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEGLU backward
-// ug packed [T, 2*inner] ([u(64)|gate(64)] per 128 columns), dh [T, inner] -> dug packed
-__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh, const __nv_bfloat16* ug, __nv_bfloat16* dug, long long T,
+// ug packed [T, 2*inner] ([u(64)|gate(64)] per 128 columns), dh [T, inner] -> dug packed; the bias gradient of the GLU
+// projection (column sums of dug, packed order) is accumulated in the same pass (db must be zeroed by the caller).
+constexpr int GB_ROWS = 256;   // rows per block (8 row lanes x 32)
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh, const __nv_bfloat16* ug, __nv_bfloat16* dug, float* db, long long T,
                                                          int inner, float dropout_p, unsigned long long seed) {
+    __shared__ float red[8][32][17];
     const int nchunk = inner >> 3;
-    const long long total = T * nchunk;
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     const uint32_t thr = (uint32_t)(dropout_p * 65536.f);
     const float ks = dropout_p > 0.f ? 65536.f / (65536.f - (float)thr) : 1.f;
     const uint32_t seedmix = seed_mix32(seed);
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int c = (int)(i % nchunk);
-        const long long row = i / nchunk;
+    float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < nchunk) {
         const int hcol = c * 8;
-        const size_t pu = (size_t)row * 2 * inner + (hcol >> 6) * 128 + (hcol & 63);
-        float d[8], u[8], g[8], du[8], dg[8];
-        unpack8(*reinterpret_cast<const uint4*>(dh + (size_t)row * inner + hcol), d);
-        unpack8(*reinterpret_cast<const uint4*>(ug + pu), u);
-        unpack8(*reinterpret_cast<const uint4*>(ug + pu + 64), g);
-        if (dropout_p > 0.f) {   // same pair hash as the GEGLU epilogue of the forward GEMM
-            const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned long long)inner + hcol) >> 1);
+        const long long r1 = min(T, (long long)(blockIdx.y + 1) * GB_ROWS);
+        for (long long row = (long long)blockIdx.y * GB_ROWS + rl; row < r1; row += 8) {
+            const size_t pu = (size_t)row * 2 * inner + (hcol >> 6) * 128 + (hcol & 63);
+            float d[8], u[8], g[8], du[8], dg[8];
+            unpack8(*reinterpret_cast<const uint4*>(dh + (size_t)row * inner + hcol), d);
+            unpack8(*reinterpret_cast<const uint4*>(ug + pu), u);
+            unpack8(*reinterpret_cast<const uint4*>(ug + pu + 64), g);
+            if (dropout_p > 0.f) {   // same pair hash as the GEGLU epilogue of the forward GEMM
+                const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned long long)inner + hcol) >> 1);
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                const uint32_t hsh = hash_pair32(seedmix, pbase + (j >> 1));
-                d[j] = ((hsh & 0xffffu) >= thr) ? d[j] * ks : 0.f;
-                d[j + 1] = ((hsh >> 16) >= thr) ? d[j + 1] * ks : 0.f;
+                for (int j = 0; j < 8; j += 2) {
+                    const uint32_t hsh = hash_pair32(seedmix, pbase + (j >> 1));
+                    d[j] = ((hsh & 0xffffu) >= thr) ? d[j] * ks : 0.f;
+                    d[j + 1] = ((hsh >> 16) >= thr) ? d[j + 1] * ks : 0.f;
+                }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float dd = d[j];
-            const float cdf = 0.5f * (1.f + erff(g[j] * 0.70710678118654752440f));
-            const float pdf = 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
-            du[j] = dd * g[j] * cdf;
-            dg[j] = dd * u[j] * (cdf + g[j] * pdf);
+            for (int j = 0; j < 8; ++j) {
+                const float cdf = 0.5f * (1.f + erff(g[j] * 0.70710678118654752440f));
+                const float pdf = 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
+                du[j] = d[j] * g[j] * cdf;
+                dg[j] = d[j] * u[j] * (cdf + g[j] * pdf);
+            }
+            const uint4 pu4 = pack8(du), pg4 = pack8(dg);
+            *reinterpret_cast<uint4*>(dug + pu) = pu4;
+            *reinterpret_cast<uint4*>(dug + pu + 64) = pg4;
+            float fu[8], fg[8];   // sum what the weight-gradient GEMM will actually read (bf16-rounded)
+            unpack8(pu4, fu);
+            unpack8(pg4, fg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { su[j] += fu[j]; sg[j] += fg[j]; }
         }
-        *reinterpret_cast<uint4*>(dug + pu) = pack8(du);
-        *reinterpret_cast<uint4*>(dug + pu + 64) = pack8(dg);
+    }
+    if (db) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[rl][cl][j] = su[j]; red[rl][cl][8 + j] = sg[j]; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+            const int cc = i >> 4, j = i & 15;
+            const int chunk = blockIdx.x * 32 + cc;
+            if (chunk >= nchunk) continue;
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += red[k][cc][j];
+            const int hcol = chunk * 8 + (j & 7);
+            atomicAdd(db + (hcol >> 6) * 128 + (hcol & 63) + (j >= 8 ? 64 : 0), s);
+        }
     }
 }
 
@@ -685,10 +711,12 @@ extern "C" int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stre
     return check_launch("qkv_post_bwd_kernel");
 }
 
-extern "C" int b200_geglu_bwd(const void* dh, const void* ug, void* dug, int64_t T, int32_t inner, float dropout_p, uint64_t seed, b200_stream_t stream) {
+extern "C" int b200_geglu_bwd(const void* dh, const void* ug, void* dug, float* db_packed, int64_t T, int32_t inner, float dropout_p, uint64_t seed,
+                              b200_stream_t stream) {
     B200_REQUIRE(dh && ug && dug && T > 0 && inner > 0 && (inner % 64) == 0, "geglu_bwd: inner must be a multiple of 64");
-    geglu_bwd_kernel<<<grid_for(T * (inner / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        (const __nv_bfloat16*)dh, (const __nv_bfloat16*)ug, (__nv_bfloat16*)dug, T, inner, dropout_p, seed);
+    dim3 grid((inner / 8 + 31) / 32, (unsigned)((T + GB_ROWS - 1) / GB_ROWS));
+    geglu_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __nv_bfloat16*)dh, (const __nv_bfloat16*)ug, (__nv_bfloat16*)dug, db_packed, T, inner, dropout_p, seed);
     return check_launch("geglu_bwd_kernel");
 }
 

@@ -240,9 +240,12 @@ __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(c
 // grid.y = batch element: a block never straddles two batch elements (adaptive-gain gradient is per batch).
 constexpr int HC_TOK_PER_BLOCK = 64;
 constexpr int HC_REC = 40;
+#ifndef HC_BWD_MIN_BLOCKS
+#define HC_BWD_MIN_BLOCKS 1
+#endif
 
 template <int VPT>
-__global__ void __launch_bounds__(256) hc_width_bwd_kernel(const HcP p, float* __restrict__ rec) {
+__global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(const HcP p, float* __restrict__ rec) {
     extern __shared__ float4 sp[];
     __shared__ float s_scal[32];
     if (threadIdx.x < 32) s_scal[threadIdx.x] = 0.f;

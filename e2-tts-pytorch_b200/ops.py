@@ -319,9 +319,9 @@ class Attention(Function):
         lib.call('b200_qkv_post_bwd', a, _stream())
         dx = gemm(d_qkvg, wpack, T, Din, ncat, lda=ld, ldb=Din, b_mn=True)
         dW = grad_weight(d_qkvg, xn, T, ncat, Din, ldy=ld)
-        db = colsum(d_qkvg, T, ncat, ld)
-        return (dx, dW[:I], dW[I:2 * I], dW[2 * I:3 * I], dW[3 * I:3 * I + H], db[3 * I:3 * I + H],
-                dW[3 * I + H:3 * I + 2 * H] if has_mix else None, db[3 * I + H:3 * I + 2 * H] if has_mix else None,
+        db = colsum(d_qkvg[:, 3 * I:], T, ld - 3 * I, ld)   # only the head-gate / value-residual-mix logits have biases
+        return (dx, dW[:I], dW[I:2 * I], dW[2 * I:3 * I], dW[3 * I:3 * I + H], db[:H],
+                dW[3 * I + H:3 * I + 2 * H] if has_mix else None, db[H:2 * H] if has_mix else None,
                 d_vfirst, None, None, None, None, None, None, None, None, None, None)
 
 
@@ -389,10 +389,10 @@ class FeedForward(Function):
         dh = gemm(dz, w2pack, T, inner, Din, b_mn=True)
         dW2 = grad_weight(dz, h, T, Din, inner)
         dug = torch.empty_like(ug)
-        lib.call('b200_geglu_bwd', dh, ug, dug, T, inner, float(dropout_p), int(seed), _stream())
+        db1p = torch.zeros(2 * inner, device=xn.device, dtype=F32)
+        lib.call('b200_geglu_bwd', dh, ug, dug, db1p, T, inner, float(dropout_p), int(seed), _stream())
         dx = gemm(dug, w1pack, T, Din, 2 * inner, b_mn=True)
         dW1p = grad_weight(dug, xn, T, 2 * inner, Din)
-        db1p = colsum(dug, T, 2 * inner, 2 * inner)
         nb = inner // 64
         dW1 = dW1p.view(nb, 2, 64, Din).transpose(0, 1).reshape(2 * inner, Din)   # undo the GEGLU interleave (layout only)
         db1 = db1p.view(nb, 2, 64).transpose(0, 1).reshape(2 * inner)

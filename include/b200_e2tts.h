@@ -202,8 +202,10 @@ typedef struct {
 int b200_qkv_post_fwd(const b200_qkv_post_args* a, b200_stream_t stream);
 int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stream);
 
-/* GEGLU backward on the packed pre-activations saved by b200_gemm(geglu=1) (A.2). */
-int b200_geglu_bwd(const void* dh, const void* ug, void* dug, int64_t T, int32_t inner, float dropout_p, uint64_t seed, b200_stream_t stream);
+/* GEGLU backward on the packed pre-activations saved by b200_gemm(geglu=1) (A.2); db_packed (fp32 [2*inner], packed order,
+ * zeroed by the caller, may be NULL) receives the bias gradient of the GLU projection in the same pass. */
+int b200_geglu_bwd(const void* dh, const void* ug, void* dug, float* db_packed, int64_t T, int32_t inner, float dropout_p, uint64_t seed,
+                   b200_stream_t stream);
 /* out[n] += sum_t X[t,n] (bf16 X, fp32 out; caller zeroes out) — nn.Linear bias gradients. */
 int b200_colsum(const void* X, int64_t T, int32_t ncols, int32_t ld, float* out, b200_stream_t stream);
 

@@ -1,13 +1,14 @@
 // tcgen05 / TMEM / TMA flash attention FORWARD for the softclamped, key-masked, head-gated attention of the
 // E2-TTS multistream block (x-transformers Attend as configured by the reference: SURVEY A.4 steps 4-5).
 //
-// One CTA per (128-query tile, head, batch), 320 threads, warp-specialised:
+// One CTA per (128-query tile, head, batch), 576 threads, warp-specialised:
 //   warp 0 lane 0 : TMA producer  — Q once, then K_j / V_j tiles (128 keys x 64) into a 2-stage smem ring
 //   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T  (tcgen05.mma 128x128x16 x4, both operands K-major) into TMEM S[j%2]
 //                                   O_j = P_j V_j  (tcgen05.mma 128x64x16 x8, A = P from smem (K-major), B = V MN-major)
 //                                   into TMEM O[j%2]; S_{j+1} is issued before O_j so the tensor pipe never waits on softmax
-//   warps 2..9    : softmax       — thread = (query row, key half): 64 of the 128 scores of its row (tcgen05.ld 32x32b:
-//                                   lane == row), row max exchanged between the two halves through smem;
+//   warps 2..17   : softmax       — thread = (query row, key quarter): 32 of the 128 scores of its row (tcgen05.ld 32x32b:
+//                                   lane == row; 4 warps per scheduler hide the MUFU / TMEM latencies), row max exchanged
+//                                   between the four quarters through smem;
 //                                   pass 1 row max of the raw scores, pass 2 softclamp (tanh) + exp2 + dropout,
 //                                   P_j written as bf16 into 128B-swizzled smem (the A operand of the PV MMA),
 //                                   partial O_j read back from TMEM and folded into fp32 registers with the usual
@@ -67,7 +68,7 @@ __global__ void attn_maskbits_kernel(const unsigned char* mask, unsigned int* bi
     bits[w] = v;
 }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const AttnTcP p) {
     extern __shared__ uint8_t smem_raw[];
@@ -87,7 +88,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* o_full = bars + 13;       // 2
     uint64_t* o_empty = bars + 15;      // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-    float* s_xch = reinterpret_cast<float*>(bars + 20);   // [2 parities][2 halves][128 rows] row-max exchange, then row sums
+    float* s_xch = reinterpret_cast<float*>(bars + 20);   // [2 parities][4 quarters][128 rows] row-max exchange, then row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
@@ -100,9 +101,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-            mbar_init(&p_full[i], 8);
-            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 16);
+            mbar_init(&p_full[i], 16);
+            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 16);
         }
         fence_barrier_init();
     }
@@ -167,32 +168,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else {
-        // -------------------------------------------------------------------- softmax warps: thread = (row, key half)
-        const int qd = warp & 3, half = (warp - 2) >> 2;
+        // -------------------------------------------------------------------- softmax warps: thread = (row, key quarter)
+        const int qd = warp & 3, part = (warp - 2) >> 2;
         const int row = qd * 32 + lane;
         const int qi = q0 + row;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + half * 2;
+        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + part;
         const uint32_t seedmix = seed_mix32(p.seed);
         const unsigned long long drop_row = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride;
-        float o_acc[32];
+        float o_acc[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+        for (int i = 0; i < 16; ++i) o_acc[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f, m_ref = -INFINITY;
         float m_hist0 = -INFINITY, m_hist1 = -INFINITY;
 
-        auto fold = [&](int t) {   // fold this thread's 32 columns of the partial O of tile t (buffer t & 1) into o_acc
+        auto fold = [&](int t) {   // fold this thread's 16 columns of the partial O of tile t (buffer t & 1) into o_acc
             const int st = t & 1;
             mbar_wait(&o_full[st], (t >> 1) & 1);
             tc_fence_after();
             const float mt = st ? m_hist1 : m_hist0;
             const float c = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - mt) * LOG2E_F);
             m_ref = mt;
-            uint32_t r[32];
-            tmem_ld32(tO + st * 64 + half * 32 + lane_off, r);
+            uint32_t r[16];
+            tmem_ld16(tO + st * 64 + part * 16 + lane_off, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[i] = o_acc[i] * c + __uint_as_float(r[i]);
+            for (int i = 0; i < 16; ++i) o_acc[i] = o_acc[i] * c + __uint_as_float(r[i]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[st]);
@@ -200,30 +201,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
         for (int j = 0; j < nkv; ++j) {
             const int st = j & 1;
-            const unsigned int mbits[2] = {mb[j * 4], mb[j * 4 + 1]};
-            const bool all_valid = (mbits[0] & mbits[1]) == 0xffffffffu;
+            const unsigned int mbits = mb[j * 4];
+            const bool all_valid = mbits == 0xffffffffu;
             mbar_wait(&s_full[st], (j >> 1) & 1);
             tc_fence_after();
-            const uint32_t ts = tS + st * 128 + half * 64 + lane_off;
-            // pass 1: max of the raw scores over this thread's 64 keys (tanh is monotone: clamp(max) == max(clamp))
+            const uint32_t ts = tS + st * 128 + part * 32 + lane_off;
+            // pass 1: max of the raw scores over this thread's 32 keys (tanh is monotone: clamp(max) == max(clamp))
+            uint32_t r[32];
+            tmem_ld32(ts, r);
+            tmem_ld_wait();
             float rmax = -INFINITY;
+            if (all_valid) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                tmem_ld32(ts + c * 32, r);
-                tmem_ld_wait();
-                if (all_valid) {
+                for (int i = 0; i < 32; ++i) rmax = fmaxf(rmax, __uint_as_float(r[i]));
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) rmax = fmaxf(rmax, __uint_as_float(r[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) rmax = ((mbits[c] >> i) & 1u) ? fmaxf(rmax, __uint_as_float(r[i])) : rmax;
-                }
+                for (int i = 0; i < 32; ++i) rmax = ((mbits >> i) & 1u) ? fmaxf(rmax, __uint_as_float(r[i])) : rmax;
             }
-            float* xch = s_xch + st * 256;
-            xch[half * 128 + row] = rmax;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            rmax = fmaxf(rmax, xch[(half ^ 1) * 128 + row]);
+            float* xch = s_xch + st * 512;
+            xch[part * 128 + row] = rmax;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            rmax = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row]));
             const float m_tile = (rmax == -INFINITY) ? -INFINITY : p.clamp * tanh_approx(rmax * p.scale_over_clamp);
             const float m_new = fmaxf(m_run, m_tile);
             const float ms = (m_new == -INFINITY) ? 0.f : m_new;
@@ -232,43 +230,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // the P buffer (and O buffer) of tile j-2 must have been consumed by its PV MMA: fold that partial now
             if (j >= 2) fold(j - 2);
             if (st) m_hist1 = ms; else m_hist0 = ms;
-            // pass 2: probabilities -> bf16 P tile in swizzled smem (this half = one 64-key swizzle atom)
-            uint8_t* pdst = sP + st * PTILE + half * TILE16 + row * 128;
+            // pass 2: probabilities -> bf16 P tile in swizzled smem (the scores are still in registers)
+            uint8_t* pdst = sP + st * PTILE + (part >> 1) * TILE16 + row * 128;
             const float msl = ms * LOG2E_F;
             const float cl2 = p.clamp * LOG2E_F;
+            float pv[32];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                tmem_ld32(ts + c * 32, r);
-                tmem_ld_wait();
-                float pv[32];
+            for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(cl2 * tanh_approx(__uint_as_float(r[i]) * p.scale_over_clamp) - msl);
+            if (!all_valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float e = ex2_approx(cl2 * tanh_approx(__uint_as_float(r[i]) * p.scale_over_clamp) - msl);
-                    pv[i] = e;
+                for (int i = 0; i < 32; ++i) pv[i] = ((mbits >> i) & 1u) ? pv[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) l_run += pv[i];
+            if (p.dropout_p > 0.f) {
+                const uint32_t pbase = (uint32_t)((drop_row + (unsigned long long)(j * TKV + part * 32)) >> 1);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const uint32_t h = hash_pair32(seedmix, pbase + (i >> 1));
+                    pv[i] = ((h & 0xffffu) >= p.drop_thresh) ? pv[i] * p.keep_scale : 0.f;
+                    pv[i + 1] = ((h >> 16) >= p.drop_thresh) ? pv[i + 1] * p.keep_scale : 0.f;
                 }
-                if (!all_valid) {
+            }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) pv[i] = ((mbits[c] >> i) & 1u) ? pv[i] : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) l_run += pv[i];
-                if (p.dropout_p > 0.f) {
-                    const uint32_t pbase = (uint32_t)((drop_row + (unsigned long long)(j * TKV + half * 64 + c * 32)) >> 1);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const uint32_t h = hash_pair32(seedmix, pbase + (i >> 1));
-                        pv[i] = ((h & 0xffffu) >= p.drop_thresh) ? pv[i] * p.keep_scale : 0.f;
-                        pv[i + 1] = ((h >> 16) >= p.drop_thresh) ? pv[i + 1] * p.keep_scale : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int chunk = c * 4 + g;
-                    *reinterpret_cast<uint4*>(pdst + ((chunk ^ (row & 7)) << 4)) =
-                        make_uint4(pack_bf16(pv[g * 8], pv[g * 8 + 1]), pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]),
-                                   pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]));
-                }
+            for (int g = 0; g < 4; ++g) {
+                const int chunk = (part & 1) * 4 + g;
+                *reinterpret_cast<uint4*>(pdst + ((chunk ^ (row & 7)) << 4)) =
+                    make_uint4(pack_bf16(pv[g * 8], pv[g * 8 + 1]), pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]),
+                               pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]));
             }
             tc_fence_before();          // TMEM S reads are complete
             fence_proxy_async();        // make the generic-proxy smem writes of P visible to the tensor-core (async) proxy
@@ -277,18 +266,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         if (nkv >= 2) fold(nkv - 2);
         fold(nkv - 1);
-        // ---- epilogue: total row sum over both halves, normalise, write O (ungated), Og (gated, head-merged) and LSE
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        s_xch[half * 128 + row] = l_run;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float l_tot = l_run + s_xch[(half ^ 1) * 128 + row];
+        // ---- epilogue: total row sum over the four quarters, normalise, write O (ungated), Og (gated, head-merged) and LSE
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        s_xch[part * 128 + row] = l_run;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float l_tot = (s_xch[row] + s_xch[128 + row]) + (s_xch[256 + row] + s_xch[384 + row]);
         if (qi < p.Np) {
             const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
             const float gt = p.gate ? p.gate[((size_t)b * p.Np + qi) * p.H + hh] : 1.f;
-            __nv_bfloat16* orow = p.o + ((size_t)bh * p.Np + qi) * DH + half * 32;
-            __nv_bfloat16* grow = p.og + ((size_t)b * p.Np + qi) * (size_t)(p.H * DH) + hh * DH + half * 32;
+            __nv_bfloat16* orow = p.o + ((size_t)bh * p.Np + qi) * DH + part * 16;
+            __nv_bfloat16* grow = p.og + ((size_t)b * p.Np + qi) * (size_t)(p.H * DH) + hh * DH + part * 16;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = o_acc[g * 8 + i] * inv;
@@ -299,7 +288,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     make_uint4(pack_bf16(bf16_lo(u.x) * gt, bf16_hi(u.x) * gt), pack_bf16(bf16_lo(u.y) * gt, bf16_hi(u.y) * gt),
                                pack_bf16(bf16_lo(u.z) * gt, bf16_hi(u.z) * gt), pack_bf16(bf16_lo(u.w) * gt, bf16_hi(u.w) * gt));
             }
-            if (half == 0) p.lse[(size_t)bh * p.Np + qi] = m_run + logf(l_tot);
+            if (part == 0) p.lse[(size_t)bh * p.Np + qi] = m_run + logf(l_tot);
         }
     }
     tc_fence_before();
@@ -385,8 +374,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const int st = i & 1;
                 mbar_wait(&qdo_empty[st], (((i >> 1) & 1) ^ 1));
                 mbar_arrive_expect_tx(&qdo_full[st], 2 * TILE16);
-                tma_load_2d(sQ + st * TILE16, &tmQ, &qdo_full[st], 0, row_base + i * TQ);
-                tma_load_2d(sDO + st * TILE16, &tmDO, &qdo_full[st], 0, row_base + i * TQ);
+                const int qt_i = (i + kt) % nq;   // staggered query-tile order: the key-tile CTAs of one head never flush the same dQ rows together
+                tma_load_2d(sQ + st * TILE16, &tmQ, &qdo_full[st], 0, row_base + qt_i * TQ);
+                tma_load_2d(sDO + st * TILE16, &tmDO, &qdo_full[st], 0, row_base + qt_i * TQ);
             }
         }
     } else if (warp == 1) {
@@ -453,14 +443,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             float v[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]);
-            const int q0r = i * TQ + qd * 32;
+            const int q0r = ((i + kt) % nq) * TQ + qd * 32;
             warp_red_rows_f32(dq_stg, v, p.dq_acc + (size_t)bh * p.Np * DH + half * 32, DH, q0r, p.Np, 32, lane);
             if (lane == 0) mbar_arrive(dq_empty);
         };
 
         for (int i = 0; i < nq; ++i) {
             const uint32_t ph = i & 1;
-            const int qi = i * TQ + row;
+            const int qi = ((i + kt) % nq) * TQ + row;
             const bool rvalid = qi < p.Np;
             const float lse = rvalid ? p.lse[(size_t)bh * p.Np + qi] : 0.f;
             const float dl = rvalid ? p.delta[(size_t)bh * p.Np + qi] : 0.f;
@@ -619,7 +609,7 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     CUtensorMap tq, tk, tv;
     const long long rows = (long long)a->B * a->H * a->Np;
     if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows)) return -1;
-    const int smem = 5 * TILE16 + 2 * PTILE + 256 + 2048 + 1024;
+    const int smem = 5 * TILE16 + 2 * PTILE + 256 + 4096 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -627,7 +617,7 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
         configured = true;
     }
     dim3 grid((a->Np + TQ - 1) / TQ, a->H, a->B);
-    attn_fwd_tc_kernel<<<grid, 320, smem, st>>>(tq, tk, tv, p);
+    attn_fwd_tc_kernel<<<grid, 576, smem, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd_tc_kernel");
 }
 

@@ -26,6 +26,9 @@ __global__ void ref_gemm(const __nv_bfloat16* A, long lda, int a_mn, const __nv_
     C[(long)m * N + n] = acc;
 }
 
+__global__ void tiny_kernel(float* p) { if (threadIdx.x == 0 && blockIdx.x == 0) p[0] += 1.f; }
+__global__ void tiny_smem_kernel(float* p) { extern __shared__ float sm[]; sm[threadIdx.x] = p[threadIdx.x]; __syncthreads(); if (threadIdx.x == 0) p[0] = sm[1]; }
+
 static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }
 static __nv_bfloat16* dev_bf16(size_t n, float scale = 1.f) {
     std::vector<__nv_bfloat16> h(n);
@@ -125,13 +128,17 @@ static int run_case(const Case& c) {
     return bad;
 }
 
-static void bench(const char* name, int M, int N, int K, int a_mn, int b_mn, int split, int fp32, int geglu, int tile = 0) {
+static void bench(const char* name, int M, int N, int K, int a_mn, int b_mn, int split, int fp32, int geglu, int tile = 0, int epi = 0) {
     long lda = a_mn ? M : K, ldb = b_mn ? N : K;
     __nv_bfloat16* A = dev_bf16((size_t)M * K, 0.1f); __nv_bfloat16* B = dev_bf16((size_t)N * K, 0.1f);
     void* D; CK(cudaMalloc(&D, (size_t)M * N * 4)); void* D2; CK(cudaMalloc(&D2, (size_t)M * N * 2));
     b200_gemm_args g = {};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.a_mn_major = a_mn; g.b_mn_major = b_mn;
     g.D = D; g.ldd = geglu ? N / 2 : N; g.d_fp32 = fp32; g.split_k = split; g.geglu = geglu; g.D2 = geglu ? D2 : nullptr; g.ldd2 = N; g.force_tile = tile;
+    if (epi & 1) g.bias = dev_f32(N);
+    if (epi & 2) { g.colscale = dev_f32((size_t)(M / 1056 + 1) * N, 0.5f, 1.f); g.rows_per_batch = 1056; }
+    if (epi & 4) { unsigned char* mk; CK(cudaMalloc(&mk, M)); CK(cudaMemset(mk, 1, M)); g.rowmask = mk; }
+    if (epi & 8) { g.resid = dev_bf16((size_t)M * N); g.ldr = N; }
     for (int i = 0; i < 3; ++i) if (b200_gemm(&g, 0)) { printf("bench %s: %s\n", name, b200_last_error()); return; }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int it = 20;
@@ -141,7 +148,7 @@ static void bench(const char* name, int M, int N, int K, int a_mn, int b_mn, int
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("bench %s failed: %s\n", name, cudaGetErrorString(e)); exit(3); }
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= it;
-    printf("bench %-24s tile=%d M=%d N=%d K=%d split=%d: %.3f ms  %.1f TFLOP/s\n", name, tile, M, N, K, split, ms, 2.0 * M * N * K / ms * 1e-9);
+    printf("bench %-24s epi=%d tile=%d M=%d N=%d K=%d split=%d: %.3f ms  %.1f TFLOP/s\n", name, epi, tile, M, N, K, split, ms, 2.0 * M * N * K / ms * 1e-9);
     cudaFree(A); cudaFree(B); cudaFree(D); cudaFree(D2);
 }
 
@@ -165,6 +172,49 @@ int main(int argc, char** argv) {
     for (auto& c : cases) bad += run_case(c);
     for (auto c : cases) { c.tile = 2; bad += run_case(c); }   // same cases on the 256 x 128 CTA tile
     printf("correctness: %d failing case(s)\n", bad);
+    if (argc > 4) {   // fixed-cost probe: per-launch time of a one-tile GEMM, alone and interleaved with other kernels
+        const int M = 128, N = 128, K = 64;
+        __nv_bfloat16* A = dev_bf16((size_t)M * K); __nv_bfloat16* B = dev_bf16((size_t)N * K);
+        void* D; CK(cudaMalloc(&D, (size_t)M * N * 2)); float* scratch; CK(cudaMalloc(&scratch, 4096));
+        b200_gemm_args g = {}; g.A = A; g.lda = K; g.B = B; g.ldb = K; g.M = M; g.N = N; g.K = K; g.D = D; g.ldd = N; g.split_k = 1;
+        cudaFuncSetAttribute(tiny_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int mode = 0; mode < 4; ++mode) {
+            for (int w = 0; w < 5; ++w) b200_gemm(&g, 0);
+            cudaDeviceSynchronize();
+            const int it = 200;
+            cudaEventRecord(e0);
+            for (int i = 0; i < it; ++i) {
+                b200_gemm(&g, 0);
+                if (mode == 1) tiny_kernel<<<148, 256>>>(scratch);
+                if (mode == 2) tiny_smem_kernel<<<148, 256, 100 * 1024>>>(scratch);
+                if (mode == 3) { tiny_kernel<<<148, 256>>>(scratch); tiny_kernel<<<148, 256>>>(scratch); }
+            }
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            printf("latency mode %d (0 gemm only, 1 gemm+tiny, 2 gemm+tiny(100KB smem), 3 gemm+2 tiny): %.2f us per iteration\n", mode, ms * 1e3 / it);
+        }
+        cudaEventRecord(e0);
+        for (int i = 0; i < 200; ++i) tiny_kernel<<<148, 256>>>(scratch);
+        cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("tiny kernel alone: %.2f us per launch\n", ms * 1e3 / 200);
+        return 0;
+    }
+    if (argc > 3) {   // ncu targets: one shape per run
+        const int which = atoi(argv[3]);
+        if (which == 0) bench("attn-out", 16896, 512, 512, 0, 0, 1, 0, 0, 0, 6);
+        if (which == 1) bench("ff-in (geglu)", 16896, 4096, 512, 0, 0, 1, 0, 1, 0, 1);
+        if (which == 2) bench("dW small", 512, 512, 67584, 1, 1, 10, 1, 0, 0, 0);
+        return 0;
+    }
+    if (argc > 2) {
+        for (int epi : {0, 1, 2, 4, 8, 7}) bench("ff-out", 16896, 512, 2048, 0, 0, 1, 0, 0, 0, epi);
+        for (int epi : {0, 2, 4, 6}) bench("attn-out", 16896, 512, 512, 0, 0, 1, 0, 0, 0, epi);
+        bench("attn-out bmn", 16896, 512, 512, 0, 1, 1, 0, 0, 0, 0);
+        return 0;
+    }
     if (argc > 1) {
         bench("ff-in (geglu)", 16896, 4096, 512, 0, 0, 1, 0, 1);
         bench("ff-out", 16896, 512, 2048, 0, 0, 1, 0, 0);

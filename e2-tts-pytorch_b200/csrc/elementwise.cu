@@ -578,32 +578,42 @@ __global__ void __launch_bounds__(256) rowgate_bwd_kernel(const __nv_bfloat16* d
     extern __shared__ float sacc[];  // [D]
     const int b = blockIdx.y;
     const int r0 = blockIdx.x * rows_per_block, r1 = min(rows_per_batch, r0 + rows_per_block);
+    const int nchunk = D >> 3;
+    const int nrl = max(1, 256 / nchunk);            // row lanes: each thread keeps ONE 8-column chunk and marches over rows
+    const int c = threadIdx.x % nchunk, rl = threadIdx.x / nchunk;
     if (cs) {
         for (int i = threadIdx.x; i < D; i += 256) sacc[i] = 0.f;
         __syncthreads();
     }
-    const int nchunk = D >> 3;
-    const int total = (r1 - r0) * nchunk;
-    for (int idx = threadIdx.x; idx < total; idx += 256) {
-        const int r = r0 + idx / nchunk, c = idx % nchunk;
-        const size_t row = (size_t)b * rows_per_batch + r;
-        float g[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(dy + row * D + c * 8), g);
-        const bool keep = !mask || mask[row];
+    for (int cc = c; cc < nchunk && rl < nrl; cc += 256) {   // (single pass unless D > 2048)
+        float s8[8] = {1, 1, 1, 1, 1, 1, 1, 1}, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (cs) {
-            float yv[8];
-            unpack8(*reinterpret_cast<const uint4*>(y + row * D + c * 8), yv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float s = __ldg(cs + (size_t)b * D + c * 8 + j);
-                o[j] = keep ? g[j] * s : 0.f;
-                if (keep) atomicAdd(&sacc[c * 8 + j], g[j] * yv[j] / s);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = keep ? g[j] : 0.f;
+            for (int j = 0; j < 8; ++j) s8[j] = __ldg(cs + (size_t)b * D + cc * 8 + j);
         }
-        *reinterpret_cast<uint4*>(dz + row * D + c * 8) = pack8(o);
+        for (int r = r0 + rl; r < r1; r += nrl) {
+            const size_t row = (size_t)b * rows_per_batch + r;
+            float g[8], o[8];
+            unpack8(*reinterpret_cast<const uint4*>(dy + row * D + cc * 8), g);
+            const bool keep = !mask || mask[row];
+            if (cs) {
+                float yv[8];
+                unpack8(*reinterpret_cast<const uint4*>(y + row * D + cc * 8), yv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = keep ? g[j] * s8[j] : 0.f;
+                    acc[j] += keep ? g[j] * yv[j] : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = keep ? g[j] : 0.f;
+            }
+            *reinterpret_cast<uint4*>(dz + row * D + cc * 8) = pack8(o);
+        }
+        if (cs) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&sacc[cc * 8 + j], acc[j] / s8[j]);
+        }
     }
     if (cs) {
         __syncthreads();
@@ -722,8 +732,11 @@ extern "C" int b200_geglu_bwd(const void* dh, const void* ug, void* dug, float* 
 
 extern "C" int b200_colsum(const void* X, int64_t T, int32_t ncols, int32_t ld, float* out, b200_stream_t stream) {
     B200_REQUIRE(X && out && T > 0 && ncols > 0 && ld >= ncols && (ld % 8) == 0, "colsum: bad arguments");
-    const int rows_per_block = 512;
-    dim3 grid((ncols + 255) / 256, (unsigned)((T + rows_per_block - 1) / rows_per_block));
+    // enough row slabs to fill the GPU even for narrow matrices (the first version used 512-row slabs: 66 blocks for a 512-wide matrix)
+    const int col_blocks = (ncols + 255) / 256;
+    int rows_per_block = 512;
+    while (rows_per_block > 32 && (long long)col_blocks * ((T + rows_per_block - 1) / rows_per_block) < 4LL * num_sms()) rows_per_block >>= 1;
+    dim3 grid(col_blocks, (unsigned)((T + rows_per_block - 1) / rows_per_block));
     colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)X, T, ncols, ld, out, rows_per_block);
     return check_launch("colsum_kernel");
 }

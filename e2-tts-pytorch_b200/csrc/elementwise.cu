@@ -386,36 +386,61 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh,
 }
 
 // ------------------------------------------------------------------------------------------------ column sums (bias grads)
-// out[n] += sum_t X[t, n]  (X bf16 [T, ld]); out must be zeroed by the caller
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* X, long long T, int ncols, int ld, float* out, int rows_per_block) {
-    __shared__ float red[8][32 * 8 + 1];
-    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int col0 = (blockIdx.x * 32 + cg) * 8;
+// out[n] += sum_t X[t, n]  (X bf16 [T, ld]); out must be zeroed by the caller.
+// A block is CL 8-column chunk lanes x (256 / CL) row lanes; narrow matrices (the 16 gate-logit columns of the packed qkv
+// gradient) use a small CL so that all 256 threads stay busy. Each thread keeps four 16-byte loads in flight; row lanes are
+// combined by warp shuffles, warps through shared memory, and one atomicAdd per column per block reaches HBM.
+template <int CL>
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ X, long long T, int ncols, int ld,
+                                                     float* __restrict__ out, int rows_per_block) {
+    constexpr int RL = 256 / CL;
+    __shared__ float red[8][CL * 8];
+    const int cg = threadIdx.x % CL, rl = threadIdx.x / CL;
+    const int col0 = (blockIdx.x * CL + cg) * 8;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     const long long r1 = min(T, r0 + rows_per_block);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (col0 < ncols) {
-        for (long long r = r0 + rl; r < r1; r += 8) {
-            float v[8];
-            if (col0 + 8 <= ncols) {
-                unpack8(*reinterpret_cast<const uint4*>(X + (size_t)r * ld + col0), v);
-            } else {
+    if (col0 + 8 <= ncols) {
+        for (long long r = r0 + rl; r < r1; r += 4 * RL) {
+            uint4 u[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = col0 + j < ncols ? __bfloat162float(X[(size_t)r * ld + col0 + j]) : 0.f;
+            for (int k = 0; k < 4; ++k) {
+                const long long rr = r + (long long)k * RL;
+                u[k] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(X + (size_t)rr * ld + col0)) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+            for (int k = 0; k < 4; ++k) {
+                float v[8];
+                unpack8(u[k], v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+            }
         }
+    } else if (col0 < ncols) {
+        for (long long r = r0 + rl; r < r1; r += RL)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (col0 + j < ncols) acc[j] += __bfloat162float(X[(size_t)r * ld + col0 + j]);
     }
+    // row lanes that share a warp: lanes differing in bits >= log2(CL)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+    for (int o = CL; o < 32; o <<= 1)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (CL == 32 || lane < CL) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][(lane % CL) * 8 + j] = acc[j];
+    }
     __syncthreads();
-    const int t = threadIdx.x;
-    float s = 0.f;
+    // CL == 32: a warp owns one row-lane, the 8 warps are the 8 row lanes; CL < 32: every warp holds all CL chunks
+    if (threadIdx.x < CL * 8) {
+        float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += red[k][t];
-    const int col = blockIdx.x * 256 + t;
-    if (col < ncols) atomicAdd(out + col, s);
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        const int col = blockIdx.x * CL * 8 + threadIdx.x;
+        if (col < ncols) atomicAdd(out + col, s);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ final norm (head)
@@ -571,53 +596,72 @@ __global__ void __launch_bounds__(256) flow_loss_bwd_kernel(const LossP p) {
 
 
 // ------------------------------------------------------------------------------------------------ gate / mask backward
-// Forward epilogue was y = mask * cs[b,:] * z. Given dy and y: dz = dy * mask * cs, d_cs[b,:] += sum_rows dy * y / cs.
-__global__ void __launch_bounds__(256) rowgate_bwd_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* y, const float* cs,
-                                                           const unsigned char* mask, __nv_bfloat16* dz, float* d_cs,
-                                                           int rows_per_batch, int D, int rows_per_block) {
-    extern __shared__ float sacc[];  // [D]
+// Forward epilogue was y = mask * cs[b,:] * (x W^T + bias). Given dy and y: dz = dy * mask * cs, d_cs[b,:] += sum_rows dy * y / cs,
+// and (optionally) d_bias[:] += sum_rows dz — the bias gradient rides along so that no separate column-sum pass re-reads dz.
+// Each thread keeps ONE 8-column chunk and marches over rows, four rows (eight 16-byte loads) in flight.
+__global__ void __launch_bounds__(256) rowgate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                                           const float* __restrict__ cs, const unsigned char* __restrict__ mask,
+                                                           __nv_bfloat16* __restrict__ dz, float* __restrict__ d_cs,
+                                                           float* __restrict__ d_bias, int rows_per_batch, int D, int rows_per_block) {
+    extern __shared__ float sacc[];  // [D] gate sums, then [D] bias sums
+    float* sbias = sacc + D;
     const int b = blockIdx.y;
     const int r0 = blockIdx.x * rows_per_block, r1 = min(rows_per_batch, r0 + rows_per_block);
     const int nchunk = D >> 3;
-    const int nrl = max(1, 256 / nchunk);            // row lanes: each thread keeps ONE 8-column chunk and marches over rows
+    const int nrl = max(1, 256 / nchunk);            // row lanes
     const int c = threadIdx.x % nchunk, rl = threadIdx.x / nchunk;
-    if (cs) {
-        for (int i = threadIdx.x; i < D; i += 256) sacc[i] = 0.f;
+    if (cs || d_bias) {
+        for (int i = threadIdx.x; i < 2 * D; i += 256) sacc[i] = 0.f;
         __syncthreads();
     }
     for (int cc = c; cc < nchunk && rl < nrl; cc += 256) {   // (single pass unless D > 2048)
-        float s8[8] = {1, 1, 1, 1, 1, 1, 1, 1}, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float s8[8] = {1, 1, 1, 1, 1, 1, 1, 1}, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (cs) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) s8[j] = __ldg(cs + (size_t)b * D + cc * 8 + j);
         }
-        for (int r = r0 + rl; r < r1; r += nrl) {
-            const size_t row = (size_t)b * rows_per_batch + r;
-            float g[8], o[8];
-            unpack8(*reinterpret_cast<const uint4*>(dy + row * D + cc * 8), g);
-            const bool keep = !mask || mask[row];
-            if (cs) {
-                float yv[8];
-                unpack8(*reinterpret_cast<const uint4*>(y + row * D + cc * 8), yv);
+        for (int r = r0 + rl; r < r1; r += 4 * nrl) {
+            uint4 ug[4], uy[4];
+            bool keep[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rr = r + k * nrl;
+                const bool ok = rr < r1;
+                const size_t row = (size_t)b * rows_per_batch + (ok ? rr : r);
+                ug[k] = __ldg(reinterpret_cast<const uint4*>(dy + row * D + cc * 8));
+                uy[k] = cs ? __ldg(reinterpret_cast<const uint4*>(y + row * D + cc * 8)) : make_uint4(0, 0, 0, 0);
+                keep[k] = ok && (!mask || mask[row]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rr = r + k * nrl;
+                if (rr >= r1) break;
+                const size_t row = (size_t)b * rows_per_batch + rr;
+                float g[8], yv[8], o[8];
+                unpack8(ug[k], g);
+                unpack8(uy[k], yv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    o[j] = keep ? g[j] * s8[j] : 0.f;
-                    acc[j] += keep ? g[j] * yv[j] : 0.f;
+                    o[j] = keep[k] ? g[j] * s8[j] : 0.f;
+                    acc[j] += keep[k] ? g[j] * yv[j] : 0.f;
+                    accb[j] += o[j];
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = keep ? g[j] : 0.f;
+                *reinterpret_cast<uint4*>(dz + row * D + cc * 8) = pack8(o);
             }
-            *reinterpret_cast<uint4*>(dz + row * D + cc * 8) = pack8(o);
         }
         if (cs) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) atomicAdd(&sacc[cc * 8 + j], acc[j] / s8[j]);
         }
+        if (d_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&sbias[cc * 8 + j], accb[j]);
+        }
     }
-    if (cs) {
+    if (cs || d_bias) {
         __syncthreads();
-        for (int i = threadIdx.x; i < D; i += 256) atomicAdd(d_cs + (size_t)b * D + i, sacc[i]);
+        if (cs) for (int i = threadIdx.x; i < D; i += 256) atomicAdd(d_cs + (size_t)b * D + i, sacc[i]);
+        if (d_bias) for (int i = threadIdx.x; i < D; i += 256) atomicAdd(d_bias + i, sbias[i]);
     }
 }
 
@@ -732,12 +776,26 @@ extern "C" int b200_geglu_bwd(const void* dh, const void* ug, void* dug, float* 
 
 extern "C" int b200_colsum(const void* X, int64_t T, int32_t ncols, int32_t ld, float* out, b200_stream_t stream) {
     B200_REQUIRE(X && out && T > 0 && ncols > 0 && ld >= ncols && (ld % 8) == 0, "colsum: bad arguments");
-    // enough row slabs to fill the GPU even for narrow matrices (the first version used 512-row slabs: 66 blocks for a 512-wide matrix)
-    const int col_blocks = (ncols + 255) / 256;
-    int rows_per_block = 512;
-    while (rows_per_block > 32 && (long long)col_blocks * ((T + rows_per_block - 1) / rows_per_block) < 4LL * num_sms()) rows_per_block >>= 1;
+    const int nchunk = (ncols + 7) / 8;
+    int cl = 32;
+    while (cl > 2 && cl / 2 >= nchunk) cl >>= 1;     // chunk lanes per block: 32 for wide matrices, fewer when ncols < 256
+    const int col_blocks = (nchunk + cl - 1) / cl;
+    const int rl = 256 / cl;
+    // about two blocks per SM, each thread marching over >= 4 rows; few enough blocks that the final atomics stay cheap
+    long long slabs = (2LL * num_sms() + col_blocks - 1) / col_blocks;
+    long long rows_per_block = (T + slabs - 1) / slabs;
+    const long long min_rows = 4LL * rl;
+    rows_per_block = ((rows_per_block + min_rows - 1) / min_rows) * min_rows;
     dim3 grid(col_blocks, (unsigned)((T + rows_per_block - 1) / rows_per_block));
-    colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)X, T, ncols, ld, out, rows_per_block);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* x = (const __nv_bfloat16*)X;
+    switch (cl) {
+        case 32: colsum_kernel<32><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
+        case 16: colsum_kernel<16><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
+        case 8: colsum_kernel<8><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
+        case 4: colsum_kernel<4><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
+        default: colsum_kernel<2><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
+    }
     return check_launch("colsum_kernel");
 }
 
@@ -784,13 +842,13 @@ extern "C" int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t st
 }
 
 extern "C" int b200_rowgate_bwd(const void* dy, const void* y, const float* cs, const uint8_t* mask, void* dz, float* d_cs,
-                                int32_t B, int32_t rows_per_batch, int32_t D, b200_stream_t stream) {
+                                float* d_bias, int32_t B, int32_t rows_per_batch, int32_t D, b200_stream_t stream) {
     B200_REQUIRE(dy && dz && B > 0 && B <= 65535 && rows_per_batch > 0 && D % 8 == 0, "rowgate_bwd: bad arguments");
     B200_REQUIRE(!cs || (y && d_cs), "rowgate_bwd: gate backward needs y and d_cs");
     const int rpb = 64;
     dim3 grid((rows_per_batch + rpb - 1) / rpb, B);
-    rowgate_bwd_kernel<<<grid, 256, (size_t)D * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, cs, mask, (__nv_bfloat16*)dz, d_cs, rows_per_batch, D, rpb);
+    rowgate_bwd_kernel<<<grid, 256, (size_t)D * 8, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, cs, mask, (__nv_bfloat16*)dz, d_cs, d_bias, rows_per_batch, D, rpb);
     return check_launch("rowgate_bwd_kernel");
 }
 

@@ -40,12 +40,15 @@ struct GemmParams {
 
 // MH = number of 128-row halves of the CTA tile: MH == 2 gives a 256 x BN tile (two MMAs per k-step share one B tile), which
 // cuts the L2 -> smem bytes per FLOP by 25% — with 128 x 128 tiles the kernel is L2-bandwidth bound (profiles/r1_gemm_shapes).
-template <int BN, int MH>
+// CG = 2 pairs two CTAs (a 2-CTA cluster on neighbouring SMs) on one tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own
+// 128 A rows and HALF of the B tile (BN/2 rows), so a 256 x 256 pair tile costs 32 KB of L2 -> smem traffic per CTA per k-block
+// for 2*128*256*64 FLOP — 128 FLOP/B against 87 FLOP/B for the single-CTA 256 x 128 tile.
+template <int BN, int MH, int CG>
 struct GemmSmem {
     static constexpr int A_BYTES = MH * A_STAGE_BYTES;
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
-    static constexpr int kStages = (MH == 1) ? 6 : 4;
+    static constexpr int kStages = (STAGE_BYTES <= 32768) ? 6 : 4;
     static constexpr int TILE_BYTES = kStages * STAGE_BYTES;
     static constexpr int BAR_BYTES = 160;
     static constexpr int STG_BYTES = 8 * 4224;   // per epilogue warp: 32 x 128 B bf16 staging tile, or 32 x 33 fp32 for split-K atomics
@@ -79,13 +82,19 @@ __device__ __forceinline__ void warp_store_rows(uint8_t* stg, const uint4 (&vals
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN, bool A_MN, bool B_MN, int MH>
+template <int BN, bool A_MN, bool B_MN, int MH, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-    using S = GemmSmem<BN, MH>;
+    using S = GemmSmem<BN, MH, CG>;
+    static_assert(CG == 1 || (CG == 2 && MH == 1 && BN == 256), "pair kernel: 2 x (128 x 256) tile");
+    static_assert(2 * MH * BN <= 512, "accumulators must fit TMEM");
     constexpr int kStages = S::kStages;
     constexpr int BMT = BM * MH;   // rows of the CTA tile
+    constexpr int BNL = BN / CG;   // B rows this CTA stages
+    // work items are tiles of (CG * BMT) x BN; with CG == 2 the two CTAs of a cluster walk the same list and own 128 rows each
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int w_first = blockIdx.x / CG, w_step = gridDim.x / CG;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;
@@ -107,18 +116,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(&full_bar[i], 1);
+            mbar_init(&full_bar[i], CG);        // pair: the leader's barrier takes one arrival per producer (+ both CTAs' TMA bytes)
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 8);
+            mbar_init(&tempty_bar[i], 8 * CG);  // pair: both CTAs' epilogue warps release the accumulator at the leader
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * MH * BN);
+    if (warp == 1) {
+        if constexpr (CG == 2) tmem_alloc_cg2(tmem_slot, 2 * MH * BN);
+        else tmem_alloc(tmem_slot, 2 * MH * BN);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();   // peer barriers initialised before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -127,44 +140,62 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ------------------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+            auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+                if constexpr (CG == 2) tma_load_2d_cg2(dst, m, bar, c0, c1);   // bytes are credited to the leader CTA's barrier
+                else tma_load_2d(dst, m, bar, c0, c1);
+            };
+            for (int w = w_first; w < p.num_work; w += w_step) {
                 const int tm = w % p.tiles_m;
                 const int rest = w / p.tiles_m;
                 const int tn = rest % p.tiles_n;
                 const int sp = rest / p.tiles_n;
                 const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int arow = (tm * CG + (int)rank) * BMT;      // first A row of this CTA
+                const int brow = tn * BN + (int)rank * BNL;        // first B row (output column) this CTA stages
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    if constexpr (CG == 2) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+                        else mbar_arrive_cluster(&full_bar[stage], 0);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    }
                     uint8_t* a_dst = smA + stage * S::A_BYTES;
                     uint8_t* b_dst = smB + stage * S::B_STAGE_BYTES;
                     if constexpr (!A_MN) {
 #pragma unroll
                         for (int h = 0; h < MH; ++h) {
-                            if (kb < p.kb_a1) tma_load_2d(a_dst + h * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, tm * BMT + h * BM);
-                            else tma_load_2d(a_dst + h * A_STAGE_BYTES, &tmA2, &full_bar[stage], (kb - p.kb_a1) * BK, tm * BMT + h * BM);
+                            if (kb < p.kb_a1) load(a_dst + h * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, arow + h * BM);
+                            else load(a_dst + h * A_STAGE_BYTES, &tmA2, &full_bar[stage], (kb - p.kb_a1) * BK, arow + h * BM);
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < BMT / 64; ++i)
-                            tma_load_2d(a_dst + i * (BK * 128), &tmA, &full_bar[stage], tm * BMT + i * 64, kb * BK);
+                            load(a_dst + i * (BK * 128), &tmA, &full_bar[stage], arow + i * 64, kb * BK);
                     }
                     if constexpr (!B_MN) {
-                        tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, tn * BN);
+                        load(b_dst, &tmB, &full_bar[stage], kb * BK, brow);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BN / 64; ++i)
-                            tma_load_2d(b_dst + i * (BK * 128), &tmB, &full_bar[stage], tn * BN + i * 64, kb * BK);
+                        for (int i = 0; i < BNL / 64; ++i)
+                            load(b_dst + i * (BK * 128), &tmB, &full_bar[stage], brow + i * 64, kb * BK);
                     }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+            if constexpr (CG == 2) {
+                // the leader's commits multicast into this CTA's empty barriers: let the last ones land before the CTA may exit
+                for (int i = 0; i < kStages; ++i) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+        if (lane == 0 && rank == 0) {
+            // ------------------------------------------------------------ MMA issuer (pair: the leader CTA issues for both)
+            constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
             // K-major: 8-row groups 1024 B apart, one swizzle atom along K; MN-major: 64-element MN atoms
             // BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
             constexpr uint32_t a_lbo = A_MN ? BK * 128 : 0, b_lbo = B_MN ? BK * 128 : 0;
@@ -173,7 +204,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
+            for (int w = w_first; w < p.num_work; w += w_step, ++iter) {
                 const int sp = (w / p.tiles_m) / p.tiles_n;
                 const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -190,12 +221,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int h = 0; h < MH; ++h) {
                         const uint64_t adesc = make_smem_desc_sw128(smem_u32(smA + stage * S::A_BYTES + h * A_STAGE_BYTES), a_lbo, 1024);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma_f16(tmem_d + h * BN, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                                     (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            if constexpr (CG == 2)
+                                umma_f16_cg2(tmem_d + h * BN, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                                             (kb > kb0 || k > 0) ? 1u : 0u);
+                            else
+                                umma_f16(tmem_d + h * BN, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                                         (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
                     }
-                    umma_commit(&empty_bar[stage]);            // smem slot is free once these MMAs retire
-                    if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+                    if constexpr (CG == 2) {
+                        umma_commit_cg2(&empty_bar[stage], 3);                      // frees the slot in both CTAs
+                        if (kb == kb1 - 1) umma_commit_cg2(&tfull_bar[as], 3);      // both CTAs' accumulators complete
+                    } else {
+                        umma_commit(&empty_bar[stage]);            // smem slot is free once these MMAs retire
+                        if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -206,8 +247,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int chalf = (warp - 2) >> 2; // which half of the tile columns (two 32-column chunks) this warp drains
         const int ew = warp - 2;           // epilogue warp index -> private staging tile
         int iter = 0;
-        for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
-            const int tm = w % p.tiles_m;
+        for (int w = w_first; w < p.num_work; w += w_step, ++iter) {
+            const int tm = (w % p.tiles_m) * CG + (int)rank;   // 128*MH-row tile index of this CTA
             const int tn = (w / p.tiles_m) % p.tiles_n;
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
@@ -226,7 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int row0 = tm * BMT + mh * BM + q * 32;
                 uint4 held[8];   // bf16 pieces of an even chunk, kept until its odd partner completes a 128-byte row segment
 #pragma unroll 1
-                for (int c = chalf * 2; c < chalf * 2 + 2; ++c) {
+                for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
                     uint32_t r[32];
                     __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated tail of the previous chunk
                     tmem_ld32(taddr + c * 32, r);
@@ -321,17 +362,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
             } else {
-                // GEGLU: tile columns [0,64) = u, [64,128) = gate of the same 64 hidden units (BN == 128 only)
+                // GEGLU: every 128 packed columns hold [0,64) = u, [64,128) = gate of the same 64 hidden units
                 const float keep_scale = p.dropout_p > 0.f ? 65536.f / (65536.f - (float)(uint32_t)(p.dropout_p * 65536.f)) : 1.f;
-                {
+#pragma unroll 1
+                for (int sub = 0; sub < BN / 128; ++sub) {
                     const int c = chalf;
+                    if (tn * BN + sub * 128 >= p.N) continue;   // warp-uniform (N % 128 == 0: a 128-column group is all in or all out)
                     uint32_t ru[32], rg[32];
                     __syncwarp();
-                    tmem_ld32(taddr + c * 32, ru);
-                    tmem_ld32(taddr + 64 + c * 32, rg);
+                    tmem_ld32(taddr + sub * 128 + c * 32, ru);
+                    tmem_ld32(taddr + sub * 128 + 64 + c * 32, rg);
                     tmem_ld_wait();
-                    const int colp = tn * BN + c * 32;         // packed column of u (GEGLU requires N % 128 == 0: always in range)
-                    const int hcol0 = tn * 64 + c * 32;        // hidden-unit column
+                    const int colp = tn * BN + sub * 128 + c * 32;         // packed column of u
+                    const int hcol0 = tn * (BN / 2) + sub * 64 + c * 32;   // hidden-unit column
                     uint8_t* stg = stg_base + ew * 4224;
                     const int row0 = tm * BMT + mh * BM + q * 32;
                     float u[32], g[32];
@@ -389,15 +432,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }  // mh
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(&tempty_bar[as], 0);
+                else mbar_arrive(&tempty_bar[as]);
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();   // neither CTA may retire while its peer can still touch its smem / TMEM
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * MH * BN);
+        if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, 2 * MH * BN);
+        else tmem_dealloc(tmem_base, 2 * MH * BN);
     }
 }
 
@@ -436,15 +484,35 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t oute
     return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int MH>
+template <int BN, bool A_MN, bool B_MN, int MH, int CG = 1>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const GemmParams& p, cudaStream_t st) {
-    using S = GemmSmem<BN, MH>;
-    auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, MH>;
+    using S = GemmSmem<BN, MH, CG>;
+    auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, MH, CG>;
     static bool configured = false;  // idempotent attribute; racing first calls set the same value
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         B200_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
+    }
+    if constexpr (CG == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        static int pairs = 0;   // co-resident 2-CTA clusters (one CTA per SM): the persistent grid
+        if (!pairs) {
+            cfg.gridDim = dim3(2 * (num_sms() / 2));
+            int n = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+            B200_REQUIRE(e == cudaSuccess && n > 0, "gemm: cudaOccupancyMaxActiveClusters: %s (%d)", cudaGetErrorString(e), n);
+            pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+        }
+        cfg.gridDim = dim3(2 * (p.num_work < pairs ? p.num_work : pairs));
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA, tA2, tB, p);
+        B200_REQUIRE(e == cudaSuccess, "gemm: cluster launch: %s", cudaGetErrorString(e));
+        return check_launch("gemm_tcgen05_kernel<pair>");
     }
     const int grid = p.num_work < num_sms() ? p.num_work : num_sms();
     kern<<<grid, kGemmThreads, S::TOTAL, st>>>(tA, tA2, tB, p);
@@ -463,9 +531,13 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
     const bool a_mn = a->a_mn_major != 0, b_mn = a->b_mn_major != 0;
     GemmParams p{};
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
-    const int BN = 128;
-    const int MH = (a->force_tile == 1) ? 1 : ((a->force_tile == 2 || p.M >= 256) ? 2 : 1);   // 256-row CTA tiles for tall problems
-    p.tiles_m = (p.M + BM * MH - 1) / (BM * MH);
+    // force_tile: 0 auto, 1 = 128x128, 2 = 256x128, 3 = CTA-pair 2x(128x256)
+    static const int pair_env = getenv("B200_GEMM_PAIR") ? atoi(getenv("B200_GEMM_PAIR")) : 1;   // developer A/B switch, default on
+    const bool pair = a->force_tile == 3 || (a->force_tile == 0 && pair_env && p.M >= 512 && p.N >= 256);
+    const int BN = pair ? 256 : 128;
+    const int MH = pair ? 1 : (a->force_tile == 1) ? 1 : ((a->force_tile == 2 || p.M >= 256) ? 2 : 1);   // 256-row CTA tiles for tall problems
+    const int tile_rows = pair ? 2 * BM : BM * MH;
+    p.tiles_m = (p.M + tile_rows - 1) / tile_rows;
     p.tiles_n = (p.N + BN - 1) / BN;
     p.kb_total = (p.K + BK - 1) / BK;
     p.kb_a1 = p.kb_total;
@@ -510,7 +582,7 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
     } else {
         tA2 = tA;
     }
-    if (!b_mn) rc = make_map(&tB, a->B, a->K, a->N, a->ldb, BN);
+    if (!b_mn) rc = make_map(&tB, a->B, a->K, a->N, a->ldb, 128);   // 128 B rows per CTA for both the 128-wide tile and the pair's half of 256
     else rc = make_map(&tB, a->B, a->N, a->K, a->ldb, BK);
     if (rc) return rc;
 
@@ -518,7 +590,13 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
         static const bool trace = getenv("B200_GEMM_TRACE") != nullptr;   // developer aid: correlate ncu launch lists with problem shapes
         if (trace)
             fprintf(stderr, "GEMMTRACE %d %d %d amn=%d bmn=%d split=%d geglu=%d two=%d mh=%d epi=%d%d%d%d\n", p.M, p.N, p.K, (int)a_mn, (int)b_mn, split,
-                    p.geglu, a->A2 != nullptr, MH, p.bias != nullptr, p.colscale != nullptr, p.rowmask != nullptr, p.resid != nullptr);
+                    p.geglu, a->A2 != nullptr, pair ? 3 : MH, p.bias != nullptr, p.colscale != nullptr, p.rowmask != nullptr, p.resid != nullptr);
+    }
+    if (pair) {
+        if (!a_mn && !b_mn) return launch_gemm<256, false, false, 1, 2>(tA, tA2, tB, p, st);
+        if (!a_mn && b_mn) return launch_gemm<256, false, true, 1, 2>(tA, tA2, tB, p, st);
+        if (a_mn && !b_mn) return launch_gemm<256, true, false, 1, 2>(tA, tA2, tB, p, st);
+        return launch_gemm<256, true, true, 1, 2>(tA, tA2, tB, p, st);
     }
     if (MH == 2) {
         if (!a_mn && !b_mn) return launch_gemm<128, false, false, 2>(tA, tA2, tB, p, st);

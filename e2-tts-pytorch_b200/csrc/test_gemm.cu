@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "../../include/b200_e2tts.h"
 
@@ -169,6 +170,29 @@ int main(int argc, char** argv) {
         {"geglu", 260, 512, 128, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0},
     };
     int bad = 0;
+    if (argc > 1 && !strcmp(argv[1], "pair")) {   // CTA-pair (cta_group::2) kernel: own process, a pipeline bug traps the context
+        cases.push_back({"kmajor multi-wave", 2048 + 32, 768, 512, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0});
+        cases.push_back({"dW-like split", 512, 512, 4096, 1, 1, 0, 0, 0, 0, 0, 0, 4, 1});
+        cases.push_back({"two-source wide", 1000, 512, 768, 0, 0, 512, 1, 0, 0, 1, 0, 1, 0});
+        cases.push_back({"geglu wide", 1100, 1408, 256, 0, 0, 0, 1, 0, 0, 0, 1, 1, 0});
+        for (auto c : cases) { c.tile = 3; bad += run_case(c); }
+        printf("pair correctness: %d failing case(s)\n", bad);
+        if (bad) return 1;
+        for (int tile = 2; tile <= 3; ++tile) {
+            bench("ff-in (geglu)", 16896, 4096, 512, 0, 0, 1, 0, 1, tile, 1);
+            bench("ff-out", 16896, 512, 2048, 0, 0, 1, 0, 0, tile);
+            bench("attn-out", 16896, 512, 512, 0, 0, 1, 0, 0, tile, 6);
+            bench("qkv", 16896, 1552, 512, 0, 0, 1, 0, 0, tile);
+            bench("cross (S streams)", 67584, 512, 768, 0, 0, 1, 0, 0, tile);
+            bench("dX ff-in", 16896, 512, 4096, 0, 1, 1, 0, 0, tile);
+            bench("dX qkv", 16896, 512, 1552, 0, 1, 1, 0, 0, tile);
+            bench("dW ff-in", 4096, 512, 16896, 1, 1, 4, 1, 0, tile);
+            bench("dW ff-out", 512, 2048, 16896, 1, 1, 4, 1, 0, tile);
+            bench("dW attn-out split16", 512, 512, 16896, 1, 1, 16, 1, 0, tile);
+            bench("square 8192", 8192, 8192, 8192, 0, 0, 1, 0, 0, tile);
+        }
+        return 0;
+    }
     for (auto& c : cases) bad += run_case(c);
     for (auto c : cases) { c.tile = 2; bad += run_case(c); }   // same cases on the 256 x 128 CTA tile
     printf("correctness: %d failing case(s)\n", bad);

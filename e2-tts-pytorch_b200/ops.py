@@ -325,14 +325,15 @@ class Attention(Function):
                 d_vfirst, None, None, None, None, None, None, None, None, None, None)
 
 
-def _rowgate_bwd(dy, y, cs, mask, B, rpb, D):
-    """dz = dy * mask * cs ; d_cs (fp32 [B, D]) — backward of the fused GEMM epilogue."""
+def _rowgate_bwd(dy, y, cs, mask, B, rpb, D, want_bias=False):
+    """dz = dy * mask * cs ; d_cs (fp32 [B, D]) ; optionally d_bias = colsum(dz) — backward of the fused GEMM epilogue."""
     if cs is None and mask is None:
-        return dy, None
+        return (dy, None, None) if want_bias else (dy, None)
     dz = torch.empty_like(dy)
     d_cs = torch.zeros_like(cs) if cs is not None else None
-    lib.call('b200_rowgate_bwd', dy, y, cs, mask, dz, d_cs, B, rpb, D, _stream())
-    return dz, d_cs
+    d_bias = torch.zeros(D, device=dy.device, dtype=F32) if want_bias else None
+    lib.call('b200_rowgate_bwd', dy, y, cs, mask, dz, d_cs, d_bias, B, rpb, D, _stream())
+    return (dz, d_cs, d_bias) if want_bias else (dz, d_cs)
 
 
 class OutProj(Function):
@@ -382,10 +383,10 @@ class FeedForward(Function):
         T, Din = xn.shape
         if colscale is not None:
             # y = cs * (h W2^T + b2): recover the pre-gate value through y / cs inside the kernel
-            dz, d_cs = _rowgate_bwd(_c(dy), y, colscale, None, B, Np, Din)
+            dz, d_cs, db2 = _rowgate_bwd(_c(dy), y, colscale, None, B, Np, Din, want_bias=True)   # bias grad rides along
         else:
             dz, d_cs = _c(dy), None
-        db2 = colsum(dz, T, Din, Din)
+            db2 = colsum(dz, T, Din, Din)
         dh = gemm(dz, w2pack, T, inner, Din, b_mn=True)
         dW2 = grad_weight(dz, h, T, Din, inner)
         dug = torch.empty_like(ug)

@@ -230,10 +230,11 @@ typedef struct {
 int b200_flow_loss_fwd(const b200_flow_loss_args* a, b200_stream_t stream);
 int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t stream);
 
-/* Backward of the GEMM epilogue y = rowmask * colscale[b,:] * z (AdaLNZero gate :346-351, A.4 step 6):
- * dz = dy * mask * cs (bf16), d_cs[b,:] += sum_rows dy * y / cs (fp32, caller zeroes). cs/mask may be NULL. */
+/* Backward of the GEMM epilogue y = rowmask * colscale[b,:] * (z + bias) (AdaLNZero gate :346-351, A.4 step 6):
+ * dz = dy * mask * cs (bf16), d_cs[b,:] += sum_rows dy * y / cs (fp32, caller zeroes), and when d_bias != NULL
+ * d_bias[:] += sum_rows dz (fp32 [D], caller zeroes). cs/mask/d_bias may be NULL. */
 int b200_rowgate_bwd(const void* dy, const void* y, const float* cs, const uint8_t* mask, void* dz, float* d_cs,
-                     int32_t B, int32_t rows_per_batch, int32_t D, b200_stream_t stream);
+                     float* d_bias, int32_t B, int32_t rows_per_batch, int32_t D, b200_stream_t stream);
 int b200_cast_rows(const float* src, void* dst, int64_t rows, int32_t cols, int32_t ld, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -5,15 +5,13 @@
 //   warp 0 lane 0 : TMA producer  — Q once, then K_j / V_j tiles (128 keys x 64) into a 2-stage smem ring
 //   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T  (tcgen05.mma 128x128x16 x4, both operands K-major) into TMEM S[j%2]
 //                                   O_j = P_j V_j  (tcgen05.mma 128x64x16 x8, A = P from smem (K-major), B = V MN-major)
-//                                   into TMEM O[j%2]; S_{j+1} is issued before O_j so the tensor pipe never waits on softmax
+//                                   accumulating into TMEM O; S_{j+1} is issued before O_j so the tensor pipe never waits on softmax
 //   warps 2..17   : softmax       — thread = (query row, key quarter): 32 of the 128 scores of its row (tcgen05.ld 32x32b:
-//                                   lane == row; 4 warps per scheduler hide the MUFU / TMEM latencies), row max exchanged
-//                                   between the four quarters through smem;
-//                                   pass 1 row max of the raw scores, pass 2 softclamp (tanh) + exp2 + dropout,
-//                                   P_j written as bf16 into 128B-swizzled smem (the A operand of the PV MMA),
-//                                   partial O_j read back from TMEM and folded into fp32 registers with the usual
-//                                   online-softmax rescale.
-// mbarrier pipelines: q_full, k_full/v_full/kv_empty[2], s_full/s_empty[2], p_full[2], o_full/o_empty[2].
+//                                   lane == row; 4 warps per scheduler hide the MUFU / TMEM latencies). The softclamp bounds the
+//                                   logits to [-clamp, clamp], so exp() needs no running maximum: one pass softclamp (tanh) +
+//                                   exp2 + dropout, P_j written as bf16 into 128B-swizzled smem (the A operand of the PV MMA);
+//                                   P V accumulates in ONE TMEM accumulator over all key tiles and is read back once.
+// mbarrier pipelines: q_full, k_full/v_full/kv_empty[2], s_full/s_empty[2], p_full/p_empty[2], o_full.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -85,10 +83,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* s_full = bars + 7;        // 2
     uint64_t* s_empty = bars + 9;       // 2
     uint64_t* p_full = bars + 11;       // 2
-    uint64_t* o_full = bars + 13;       // 2
-    uint64_t* o_empty = bars + 15;      // 2
+    uint64_t* p_empty = bars + 13;      // 2
+    uint64_t* o_full = bars + 15;       // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-    float* s_xch = reinterpret_cast<float*>(bars + 20);   // [2 parities][4 quarters][128 rows] row-max exchange, then row sums
+    float* s_xch = reinterpret_cast<float*>(bars + 20);   // [4 quarters][128 rows] row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
@@ -99,11 +97,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(q_full, 1);
+        mbar_init(o_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 16);
-            mbar_init(&p_full[i], 16);
-            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 16);
+            mbar_init(&p_full[i], 16); mbar_init(&p_empty[i], 1);
         }
         fence_barrier_init();
     }
@@ -112,7 +110,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tO = tmem_base + 256;   // S[2] at +0/+128, O[2] at +256/+320
+    const uint32_t tS = tmem_base, tO = tmem_base + 256;   // S[2] at +0/+128, O at +256 (64 columns, accumulated over all key tiles)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -153,22 +151,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     const uint32_t ph = (jj >> 1) & 1;
                     mbar_wait(&p_full[st], ph);
                     mbar_wait(&v_full[st], ph);
-                    mbar_wait(&o_empty[st], ph ^ 1);
                     tc_fence_after();
                     const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + st * TILE16), 128 * 128, 1024);
                     const uint32_t pbase = smem_u32(sP + st * PTILE);
 #pragma unroll
                     for (int k = 0; k < TKV / 16; ++k) {
                         const uint64_t pdesc = make_smem_desc_sw128(pbase + (k >> 2) * TILE16 + (k & 3) * 32, 0, 1024);
-                        umma_f16(tO + st * 64, pdesc, vdesc + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : 0u);
+                        umma_f16(tO, pdesc, vdesc + (uint64_t)(k * 128), idesc_o, (jj > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&o_full[st]);
                     umma_commit(&kv_empty[st]);
+                    umma_commit(&p_empty[st]);
+                    if (jj == nkv - 1) umma_commit(o_full);
                 }
             }
         }
     } else {
         // -------------------------------------------------------------------- softmax warps: thread = (row, key quarter)
+        // The softclamp bounds every logit to [-clamp, clamp] (clamp <= 64 on this path), so exp(logit) stays inside the fp32 / bf16
+        // range without a running row maximum: no max pass, no cross-warp exchange per tile, no rescale — P V accumulates in TMEM
+        // over all key tiles and is read once. LSE = log(sum exp(logit)).
         const int qd = warp & 3, part = (warp - 2) >> 2;
         const int row = qd * 32 + lane;
         const int qi = q0 + row;
@@ -176,82 +177,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + part;
         const uint32_t seedmix = seed_mix32(p.seed);
         const unsigned long long drop_row = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride;
-        float o_acc[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f, m_ref = -INFINITY;
-        float m_hist0 = -INFINITY, m_hist1 = -INFINITY;
-
-        auto fold = [&](int t) {   // fold this thread's 16 columns of the partial O of tile t (buffer t & 1) into o_acc
-            const int st = t & 1;
-            mbar_wait(&o_full[st], (t >> 1) & 1);
-            tc_fence_after();
-            const float mt = st ? m_hist1 : m_hist0;
-            const float c = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - mt) * LOG2E_F);
-            m_ref = mt;
-            uint32_t r[16];
-            tmem_ld16(tO + st * 64 + part * 16 + lane_off, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o_acc[i] = o_acc[i] * c + __uint_as_float(r[i]);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[st]);
-        };
+        const float2 soc2 = make_float2(p.scale_over_clamp, p.scale_over_clamp);
+        const float2 cl2 = make_float2(p.clamp * LOG2E_F, p.clamp * LOG2E_F);
+        float2 l2 = make_float2(0.f, 0.f);
 
         for (int j = 0; j < nkv; ++j) {
             const int st = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
             const unsigned int mbits = mb[j * 4];
-            const bool all_valid = mbits == 0xffffffffu;
-            mbar_wait(&s_full[st], (j >> 1) & 1);
+            mbar_wait(&s_full[st], ph);
             tc_fence_after();
-            const uint32_t ts = tS + st * 128 + part * 32 + lane_off;
-            // pass 1: max of the raw scores over this thread's 32 keys (tanh is monotone: clamp(max) == max(clamp))
             uint32_t r[32];
-            tmem_ld32(ts, r);
+            tmem_ld32(tS + st * 128 + part * 32 + lane_off, r);
             tmem_ld_wait();
-            float rmax = -INFINITY;
-            if (all_valid) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) rmax = fmaxf(rmax, __uint_as_float(r[i]));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) rmax = ((mbits >> i) & 1u) ? fmaxf(rmax, __uint_as_float(r[i])) : rmax;
-            }
-            float* xch = s_xch + st * 512;
-            xch[part * 128 + row] = rmax;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            rmax = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row]));
-            const float m_tile = (rmax == -INFINITY) ? -INFINITY : p.clamp * tanh_approx(rmax * p.scale_over_clamp);
-            const float m_new = fmaxf(m_run, m_tile);
-            const float ms = (m_new == -INFINITY) ? 0.f : m_new;
-            l_run *= (m_run == -INFINITY) ? 0.f : ex2_approx((m_run - ms) * LOG2E_F);
-            m_run = m_new;
-            // the P buffer (and O buffer) of tile j-2 must have been consumed by its PV MMA: fold that partial now
-            if (j >= 2) fold(j - 2);
-            if (st) m_hist1 = ms; else m_hist0 = ms;
-            // pass 2: probabilities -> bf16 P tile in swizzled smem (the scores are still in registers)
-            uint8_t* pdst = sP + st * PTILE + (part >> 1) * TILE16 + row * 128;
-            const float msl = ms * LOG2E_F;
-            const float cl2 = p.clamp * LOG2E_F;
+            tc_fence_before();          // the scores are in registers: hand the S buffer back before doing the math
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
             float pv[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(cl2 * tanh_approx(__uint_as_float(r[i]) * p.scale_over_clamp) - msl);
-            if (!all_valid) {
+            for (int i = 0; i < 32; i += 2) {
+                const float2 x = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), soc2);
+                const float2 y = __fmul2_rn(make_float2(tanh_approx(x.x), tanh_approx(x.y)), cl2);
+                pv[i] = ex2_approx(y.x);
+                pv[i + 1] = ex2_approx(y.y);
+            }
+            if (mbits != 0xffffffffu) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) pv[i] = ((mbits >> i) & 1u) ? pv[i] : 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) l_run += pv[i];
-            if (p.dropout_p > 0.f) {
+            for (int i = 0; i < 32; i += 2) l2 = __fadd2_rn(l2, make_float2(pv[i], pv[i + 1]));
+            if (p.dropout_p > 0.f) {   // the 1/(1-p) factor is applied once, to the normalised output
                 const uint32_t pbase = (uint32_t)((drop_row + (unsigned long long)(j * TKV + part * 32)) >> 1);
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     const uint32_t h = hash_pair32(seedmix, pbase + (i >> 1));
-                    pv[i] = ((h & 0xffffu) >= p.drop_thresh) ? pv[i] * p.keep_scale : 0.f;
-                    pv[i + 1] = ((h >> 16) >= p.drop_thresh) ? pv[i + 1] * p.keep_scale : 0.f;
+                    pv[i] = ((h & 0xffffu) >= p.drop_thresh) ? pv[i] : 0.f;
+                    pv[i + 1] = ((h >> 16) >= p.drop_thresh) ? pv[i + 1] : 0.f;
                 }
             }
+            // the P buffer was last read by the PV MMA of tile j-2
+            mbar_wait(&p_empty[st], ph ^ 1);
+            uint8_t* pdst = sP + st * PTILE + (part >> 1) * TILE16 + row * 128;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int chunk = (part & 1) * 4 + g;
@@ -259,20 +226,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     make_uint4(pack_bf16(pv[g * 8], pv[g * 8 + 1]), pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]),
                                pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]));
             }
-            tc_fence_before();          // TMEM S reads are complete
             fence_proxy_async();        // make the generic-proxy smem writes of P visible to the tensor-core (async) proxy
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&s_empty[st]); mbar_arrive(&p_full[st]); }
+            if (lane == 0) mbar_arrive(&p_full[st]);
         }
-        if (nkv >= 2) fold(nkv - 2);
-        fold(nkv - 1);
         // ---- epilogue: total row sum over the four quarters, normalise, write O (ungated), Og (gated, head-merged) and LSE
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        s_xch[part * 128 + row] = l_run;
+        s_xch[part * 128 + row] = l2.x + l2.y;
         asm volatile("bar.sync 1, 512;" ::: "memory");
         const float l_tot = (s_xch[row] + s_xch[128 + row]) + (s_xch[256 + row] + s_xch[384 + row]);
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        uint32_t ro[16];
+        tmem_ld16(tO + part * 16 + lane_off, ro);
+        tmem_ld_wait();
         if (qi < p.Np) {
-            const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+            const float inv = l_tot > 0.f ? p.keep_scale / l_tot : 0.f;
             const float gt = p.gate ? p.gate[((size_t)b * p.Np + qi) * p.H + hh] : 1.f;
             __nv_bfloat16* orow = p.o + ((size_t)bh * p.Np + qi) * DH + part * 16;
             __nv_bfloat16* grow = p.og + ((size_t)b * p.Np + qi) * (size_t)(p.H * DH) + hh * DH + part * 16;
@@ -280,7 +248,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int g = 0; g < 2; ++g) {
                 float v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = o_acc[g * 8 + i] * inv;
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(ro[g * 8 + i]) * inv;
                 const uint4 u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 *reinterpret_cast<uint4*>(orow + g * 8) = u;
                 // gate the bf16-rounded output (what the backward pass sees) for consistency
@@ -288,7 +256,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     make_uint4(pack_bf16(bf16_lo(u.x) * gt, bf16_hi(u.x) * gt), pack_bf16(bf16_lo(u.y) * gt, bf16_hi(u.y) * gt),
                                pack_bf16(bf16_lo(u.z) * gt, bf16_hi(u.z) * gt), pack_bf16(bf16_lo(u.w) * gt, bf16_hi(u.w) * gt));
             }
-            if (part == 0) p.lse[(size_t)bh * p.Np + qi] = m_run + logf(l_tot);
+            if (part == 0) p.lse[(size_t)bh * p.Np + qi] = logf(l_tot);
         }
     }
     tc_fence_before();
@@ -469,29 +437,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                                      (unsigned long long)(k0 + part * 32);
                     pbase = (uint32_t)(kbase >> 1);
                 }
+                // warp-uniform: no key of this quarter is masked and every query row of the tile exists
+                const bool no_mask = all_valid && (((i + kt) % nq) * TQ + TQ <= p.Np);
+                const float2 soc2 = make_float2(p.scale_over_clamp, p.scale_over_clamp), cl2 = make_float2(p.clamp * LOG2E_F, p.clamp * LOG2E_F);
+                const float2 nlse2 = make_float2(-lse2, -lse2), sc2 = make_float2(p.scale, p.scale), nsc2 = make_float2(-p.scale, -p.scale);
+                const float2 ks2 = make_float2(keep_scale, keep_scale), ndl2 = make_float2(-dl, -dl);
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
-                    float pr[2], ds[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float th = tanh_approx(__uint_as_float(rs[e + u]) * p.scale_over_clamp);
-                        float pe = ex2_approx(p.clamp * LOG2E_F * th - lse2);
-                        pe = (rvalid && (all_valid || ((mbits1 >> (e + u)) & 1u))) ? pe : 0.f;
-                        pr[u] = pe;
-                        ds[u] = (1.f - th * th) * p.scale;           // d(clamped logit)/d(raw logit) * scale
+                    // packed fp32x2 math on the key pair (e, e+1); the 1/(1-p) of the dropped probabilities that feed dV is applied
+                    // once to the dV accumulator in the epilogue
+                    const float2 x = __fmul2_rn(make_float2(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])), soc2);
+                    const float2 th = make_float2(tanh_approx(x.x), tanh_approx(x.y));
+                    const float2 y = __ffma2_rn(th, cl2, nlse2);
+                    float2 pe = make_float2(ex2_approx(y.x), ex2_approx(y.y));
+                    if (!no_mask) {
+                        pe.x = (rvalid && ((mbits1 >> e) & 1u)) ? pe.x : 0.f;
+                        pe.y = (rvalid && ((mbits1 >> (e + 1)) & 1u)) ? pe.y : 0.f;
                     }
-                    float dp0 = __uint_as_float(rd[e]), dp1 = __uint_as_float(rd[e + 1]);
-                    float pd0 = pr[0], pd1 = pr[1];
+                    const float2 ds = __ffma2_rn(__fmul2_rn(th, nsc2), th, sc2);   // (1 - tanh^2) * scale = d(clamped logit)/d(raw score)
+                    float2 dp = make_float2(__uint_as_float(rd[e]), __uint_as_float(rd[e + 1]));
+                    float2 pd = pe;
+                    float2 t;
                     if (p.dropout_p > 0.f) {
                         const uint32_t h = hash_pair32(seedmix, pbase + (e >> 1));
                         const bool k0_ = (h & 0xffffu) >= p.drop_thresh, k1_ = (h >> 16) >= p.drop_thresh;
-                        dp0 = k0_ ? dp0 * keep_scale : 0.f;
-                        dp1 = k1_ ? dp1 * keep_scale : 0.f;
-                        pd0 = k0_ ? pd0 * keep_scale : 0.f;          // dV uses the dropped probabilities, dS the un-dropped ones
-                        pd1 = k1_ ? pd1 * keep_scale : 0.f;
+                        dp.x = k0_ ? dp.x : 0.f; dp.y = k1_ ? dp.y : 0.f;
+                        pd.x = k0_ ? pd.x : 0.f; pd.y = k1_ ? pd.y : 0.f;      // dV uses the dropped probabilities, dS the un-dropped ones
+                        t = __ffma2_rn(dp, ks2, ndl2);
+                    } else {
+                        t = __fadd2_rn(dp, ndl2);
                     }
-                    ppk[e >> 1] = pack_bf16(pd0, pd1);
-                    dpk[e >> 1] = pack_bf16(pr[0] * (dp0 - dl) * ds[0], pr[1] * (dp1 - dl) * ds[1]);
+                    const float2 dsv = __fmul2_rn(__fmul2_rn(pe, t), ds);
+                    ppk[e >> 1] = pack_bf16(pd.x, pd.y);
+                    dpk[e >> 1] = pack_bf16(dsv.x, dsv.y);
                 }
             }
             tc_fence_before();
@@ -530,9 +508,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 __nv_bfloat16* dkp = p.dk + ((size_t)bh * p.Np + key) * DH + half * 32;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
+                    const float ks = keep_scale;   // deferred 1/(1-p) of the dropped probabilities
                     *reinterpret_cast<uint4*>(dvp + g * 8) =
-                        make_uint4(pack_bf16(__uint_as_float(rv[g * 8]), __uint_as_float(rv[g * 8 + 1])), pack_bf16(__uint_as_float(rv[g * 8 + 2]), __uint_as_float(rv[g * 8 + 3])),
-                                   pack_bf16(__uint_as_float(rv[g * 8 + 4]), __uint_as_float(rv[g * 8 + 5])), pack_bf16(__uint_as_float(rv[g * 8 + 6]), __uint_as_float(rv[g * 8 + 7])));
+                        make_uint4(pack_bf16(__uint_as_float(rv[g * 8]) * ks, __uint_as_float(rv[g * 8 + 1]) * ks), pack_bf16(__uint_as_float(rv[g * 8 + 2]) * ks, __uint_as_float(rv[g * 8 + 3]) * ks),
+                                   pack_bf16(__uint_as_float(rv[g * 8 + 4]) * ks, __uint_as_float(rv[g * 8 + 5]) * ks), pack_bf16(__uint_as_float(rv[g * 8 + 6]) * ks, __uint_as_float(rv[g * 8 + 7]) * ks));
                     *reinterpret_cast<uint4*>(dkp + g * 8) =
                         make_uint4(pack_bf16(__uint_as_float(rk[g * 8]), __uint_as_float(rk[g * 8 + 1])), pack_bf16(__uint_as_float(rk[g * 8 + 2]), __uint_as_float(rk[g * 8 + 3])),
                                    pack_bf16(__uint_as_float(rk[g * 8 + 4]), __uint_as_float(rk[g * 8 + 5])), pack_bf16(__uint_as_float(rk[g * 8 + 6]), __uint_as_float(rk[g * 8 + 7])));
@@ -589,6 +568,9 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     B200_REQUIRE(a->B > 0 && a->H > 0 && a->Np > 0 && a->B <= 65535 && a->H <= 65535, "attn_fwd: bad shape");
     B200_REQUIRE(a->softclamp > 0.f, "attn_fwd: softclamp value must be > 0 (the reference always clamps, e2_tts.py:548-551)");
     B200_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "attn_fwd: dropout must be in [0,1)");
+    // the tcgen05 kernel exponentiates the clamped logits without a running maximum: exp(+-64) is well inside fp32 / bf16 range,
+    // a looser clamp (the reference default is 50, e2_tts.py:548-551) goes through the online-softmax mma.sync kernel instead
+    if (a->softclamp > 64.f) return b200_attn_fwd_legacy(a, stream);
     AttnTcP p{};
     p.nkv = (a->Np + TKV - 1) / TKV;
     p.mask_words = p.nkv * 4;

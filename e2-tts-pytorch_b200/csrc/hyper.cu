@@ -9,6 +9,8 @@
 // HBM layout: residual streams are (token, stream, d) bf16 so the 4 streams of a token are adjacent (the
 // reference's '(b s) n d' puts them N'*d apart). One warp owns one token; all reductions are warp shuffles.
 // These kernels are HBM-bound: width reads S*d and writes (S+1)*d bf16 per token (algorithmic minimum).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -66,74 +68,111 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
+// Packed fp32x2 arithmetic: one FFMA2 issues two FMAs per lane. With three register operands a scalar FFMA issues every other
+// cycle per scheduler, so these FMA-heavy per-token kernels are FMA-pipe bound unless the math is paired (elements 2i, 2i+1 of a
+// bf16x2 word make the natural pair).
+typedef float2 f2;
+__device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 fmul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 splat(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float hsum(f2 a) { return a.x + a.y; }
+__device__ __forceinline__ void unpack8p(const uint4& u, f2 (&f)[4]) {
+    f[0] = make_float2(bf16_lo(u.x), bf16_hi(u.x)); f[1] = make_float2(bf16_lo(u.y), bf16_hi(u.y));
+    f[2] = make_float2(bf16_lo(u.z), bf16_hi(u.z)); f[3] = make_float2(bf16_lo(u.w), bf16_hi(u.w));
+}
+__device__ __forceinline__ uint4 pack8p(const f2 (&f)[4]) {
+    return make_uint4(pack_bf16(f[0].x, f[0].y), pack_bf16(f[1].x, f[1].y), pack_bf16(f[2].x, f[2].y), pack_bf16(f[3].x, f[3].y));
+}
+__device__ __forceinline__ f2 lo2(const float4& q) { return make_float2(q.x, q.y); }
+__device__ __forceinline__ f2 hi2(const float4& q) { return make_float2(q.z, q.w); }
+
 // Per-token forward state shared by the forward and backward kernels.
 template <int VPT>
 struct TokState {
-    float r[HS][VPT][8];
+    f2 r[HS][VPT][4];     // the 4 streams, element pairs (2i, 2i+1)
     float inv[HS];        // sqrt(D) / max(||r_s||, 1e-12)
-    float tha[HS][HT];    // tanh(n^_s . A[:,t])
-    float thb[HS];        // tanh(n^_s . b)
-    float alpha[HS][HT];
-    float beta[HS];
+    float alpha[HS][HT];  // broadcast to every lane
+    // Lane-owned scalars. Lane l = s*HT + t (l < 20) owns alpha[s][t]; lane 20 + s owns beta[s]:
+    float myraw;          //   raw dot product <r_s, (gamma+1) * A[:,t]>  (resp. b) left in this lane by the reduction
+    float myinv;          //   inv of the lane's stream
+    float myth;           //   tanh(myraw * myinv)
+    float myval;          //   alpha[s][t] (resp. beta[s])
 };
+// token-invariant lane constants: the dynamic scale and static term of the scalar a lane owns
+struct LaneConst { float scale, stat; };
+__device__ __forceinline__ LaneConst lane_const(const HcP& p, int lane) {
+    LaneConst lc;
+    lc.scale = lane < HS * HT ? __ldg(p.ascale) : (lane < HS * HT + HS ? __ldg(p.bscale) : 0.f);
+    lc.stat = lane < HS * HT ? __ldg(p.salpha + lane) : (lane < HS * HT + HS ? __ldg(p.sbeta + lane - HS * HT) : 0.f);
+    return lc;
+}
 
-// Stage the per-feature parameters once per block: sp[i] = { (gamma_i+1) * A[i][0..4], (gamma_i+1) * b[i], gamma_i+1, 0 }
-// (two 16-byte shared loads per feature instead of seven global loads; the (gamma+1) factor is folded in).
-// Layout: feature i = chunk*8 + e lives at sp[(e*2 + part) * nchunk + chunk], so the 32 lanes of a warp (consecutive chunks,
-// same e) read 32 consecutive float4 — bank-conflict free (the naive [i][2] layout was an 8-way conflict, ncu r1).
-__device__ __forceinline__ int sp_idx(int nchunk, int chunk, int e, int part) { return (e * 2 + part) * nchunk + chunk; }
+// Stage the per-feature parameters once per block, (gamma+1) folded in, as element PAIRS: for pair j of chunk c
+//   part 0 = { A0[e0], A0[e1], A1[e0], A1[e1] },  part 1 = { A2.., A3.. },  part 2 = { A4[e0], A4[e1], b[e0], b[e1] }
+// at sp[(j*3 + part) * nchunk + c]: the 32 lanes of a warp (consecutive chunks, same j/part) read 32 consecutive float4 —
+// bank-conflict free (a naive per-feature layout was an 8-way conflict, ncu r1). 12 * nchunk float4 = 24 * D bytes.
+__device__ __forceinline__ int sp_idx(int nchunk, int chunk, int j, int part) { return (j * 3 + part) * nchunk + chunk; }
+__host__ __device__ inline size_t hc_param_smem(int D) { return (size_t)(D / 8) * 12 * sizeof(float4); }
 __device__ __forceinline__ void stage_params(const HcP& p, float4* sp) {
     const int nchunk = p.D >> 3;
-    for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
-        const float g1 = __ldg(p.gamma + i) + 1.f;
-        const float* a = p.afn + i * HT;
-        sp[sp_idx(nchunk, i >> 3, i & 7, 0)] = make_float4(g1 * __ldg(a), g1 * __ldg(a + 1), g1 * __ldg(a + 2), g1 * __ldg(a + 3));
-        sp[sp_idx(nchunk, i >> 3, i & 7, 1)] = make_float4(g1 * __ldg(a + 4), g1 * __ldg(p.bfn + i), g1, 0.f);
+    for (int pi = threadIdx.x; pi < (p.D >> 1); pi += blockDim.x) {
+        const int e0 = 2 * pi, e1 = e0 + 1;
+        const float g0 = __ldg(p.gamma + e0) + 1.f, g1 = __ldg(p.gamma + e1) + 1.f;
+        const float* a0 = p.afn + e0 * HT;
+        const float* a1 = p.afn + e1 * HT;
+        const int c = pi >> 2, j = pi & 3;
+        sp[sp_idx(nchunk, c, j, 0)] = make_float4(g0 * __ldg(a0), g1 * __ldg(a1), g0 * __ldg(a0 + 1), g1 * __ldg(a1 + 1));
+        sp[sp_idx(nchunk, c, j, 1)] = make_float4(g0 * __ldg(a0 + 2), g1 * __ldg(a1 + 2), g0 * __ldg(a0 + 3), g1 * __ldg(a1 + 3));
+        sp[sp_idx(nchunk, c, j, 2)] = make_float4(g0 * __ldg(a0 + 4), g1 * __ldg(a1 + 4), g0 * __ldg(p.bfn + e0), g1 * __ldg(p.bfn + e1));
     }
     __syncthreads();
 }
 
 template <int VPT>
-__device__ __forceinline__ void token_forward(const HcP& p, const float4* __restrict__ sp, long long tok, int lane, TokState<VPT>& st) {
+__device__ __forceinline__ void token_forward(const HcP& p, const float4* __restrict__ sp, const __nv_bfloat16* __restrict__ rsrc, int lane,
+                                              const LaneConst& lc, TokState<VPT>& st) {   // rsrc: this token's [HS][D] block (HBM or smem copy)
     const int nchunk = p.D >> 3;
-    float ss[HS] = {0.f, 0.f, 0.f, 0.f};
+    f2 ss2[HS], acc[HS][6];
 #pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-        const int c = lane + 32 * v;
+    for (int s = 0; s < HS; ++s) {
+        ss2[s] = splat(0.f);
 #pragma unroll
-        for (int s = 0; s < HS; ++s) {
-            if (c < nchunk) {
-                const uint4 u = *reinterpret_cast<const uint4*>(p.xres + ((size_t)tok * HS + s) * p.D + c * 8);
-                unpack8(u, st.r[s][v]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) st.r[s][v][e] = 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ss[s] += st.r[s][v][e] * st.r[s][v][e];
-        }
+        for (int k = 0; k < 6; ++k) acc[s][k] = splat(0.f);
     }
-    float red[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) red[i] = 0.f;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
         const int c = lane + 32 * v;
         if (c < nchunk) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float4 p0 = sp[sp_idx(nchunk, c, e, 0)], p1 = sp[sp_idx(nchunk, c, e, 1)];
+            for (int s = 0; s < HS; ++s) unpack8p(*reinterpret_cast<const uint4*>(rsrc + (size_t)s * p.D + c * 8), st.r[s][v]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 q0 = sp[sp_idx(nchunk, c, j, 0)], q1 = sp[sp_idx(nchunk, c, j, 1)], q2 = sp[sp_idx(nchunk, c, j, 2)];
 #pragma unroll
                 for (int s = 0; s < HS; ++s) {
-                    const float rv = st.r[s][v][e];
-                    red[s * HT + 0] += rv * p0.x; red[s * HT + 1] += rv * p0.y; red[s * HT + 2] += rv * p0.z;
-                    red[s * HT + 3] += rv * p0.w; red[s * HT + 4] += rv * p1.x; red[HS * HT + s] += rv * p1.y;
+                    const f2 rp = st.r[s][v][j];
+                    ss2[s] = ffma2(rp, rp, ss2[s]);
+                    acc[s][0] = ffma2(rp, lo2(q0), acc[s][0]); acc[s][1] = ffma2(rp, hi2(q0), acc[s][1]);
+                    acc[s][2] = ffma2(rp, lo2(q1), acc[s][2]); acc[s][3] = ffma2(rp, hi2(q1), acc[s][3]);
+                    acc[s][4] = ffma2(rp, lo2(q2), acc[s][4]); acc[s][5] = ffma2(rp, hi2(q2), acc[s][5]);
                 }
             }
+        } else {
+#pragma unroll
+            for (int s = 0; s < HS; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st.r[s][v][j] = splat(0.f);
         }
     }
+    float red[32];
 #pragma unroll
-    for (int s = 0; s < HS; ++s) red[28 + s] = ss[s];   // the four sums of squares ride along in the same reduction
+    for (int s = 0; s < HS; ++s) {
+#pragma unroll
+        for (int t = 0; t < HT; ++t) red[s * HT + t] = hsum(acc[s][t]);
+        red[HS * HT + s] = hsum(acc[s][5]);
+        red[24 + s] = 0.f;
+        red[28 + s] = hsum(ss2[s]);   // the four sums of squares ride along in the same reduction
+    }
     const float mine = warp_reduce32(red, lane);         // lane l owns total #l
     const float sqrtD = sqrtf((float)p.D);
     float invs[HS];
@@ -142,7 +181,7 @@ __device__ __forceinline__ void token_forward(const HcP& p, const float4* __rest
         invs[s] = sqrtD / fmaxf(sqrtf(__shfl_sync(0xffffffffu, mine, 28 + s)), 1e-12f);
         st.inv[s] = invs[s];
     }
-    // each lane applies inv_s and tanh to the ONE dot product it owns, then the 24 results are broadcast
+    // each lane applies inv_s, tanh, scale and static term to the ONE dot product it owns; only the 20 alphas are broadcast
     float myinv = invs[0];
     {
         const int s_of = lane < HS * HT ? lane / HT : lane - HS * HT;
@@ -150,82 +189,110 @@ __device__ __forceinline__ void token_forward(const HcP& p, const float4* __rest
         for (int s = 1; s < HS; ++s) myinv = (s_of == s) ? invs[s] : myinv;
     }
     const float th = tanhf(mine * myinv);
-    const float sa = __ldg(p.ascale), sb = __ldg(p.bscale);
+    st.myraw = mine;
+    st.myinv = myinv;
+    st.myth = th;
+    st.myval = th * lc.scale + lc.stat;
 #pragma unroll
-    for (int s = 0; s < HS; ++s) {
-        st.thb[s] = __shfl_sync(0xffffffffu, th, HS * HT + s);
-        st.beta[s] = st.thb[s] * sb + __ldg(p.sbeta + s);
+    for (int s = 0; s < HS; ++s)
 #pragma unroll
-        for (int t = 0; t < HT; ++t) {
-            st.tha[s][t] = __shfl_sync(0xffffffffu, th, s * HT + t);
-            st.alpha[s][t] = st.tha[s][t] * sa + __ldg(p.salpha + s * HT + t);
-        }
-    }
+        for (int t = 0; t < HT; ++t) st.alpha[s][t] = __shfl_sync(0xffffffffu, st.myval, s * HT + t);
 }
 
 __device__ __forceinline__ const float* norm_gain(const HcP& p, long long tok) {
     return p.norm_mode == 2 ? p.ng + (size_t)(tok / p.rows_per_batch) * p.D : p.ng;
 }
+__device__ __forceinline__ void load_gain8(const float* g, f2 (&o)[4]) {   // 8 consecutive fp32 gains (32-byte aligned)
+    const float4 a = __ldg(reinterpret_cast<const float4*>(g)), b = __ldg(reinterpret_cast<const float4*>(g) + 1);
+    o[0] = lo2(a); o[1] = hi2(a); o[2] = lo2(b); o[3] = hi2(b);
+}
 
-template <int VPT>
+// PF: every warp prefetches its NEXT token's 4 streams into a private shared-memory double buffer with one bulk (TMA) copy while
+// it works on the current one. Without it the kernel alternates load and math phases with ~8 warps per SM and sits on
+// long-scoreboard stalls (profiles/r1g_ncu_full_hc_width_*).
+template <int VPT, bool PF>
 __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(const HcP p) {
     extern __shared__ float4 sp[];
-    stage_params(p, sp);
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    __shared__ uint64_t bars[8][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warp_global = (long long)blockIdx.x * 8 + warp;
     const long long nwarps = (long long)gridDim.x * 8;
     const int nchunk = p.D >> 3;
-    for (long long tok = warp_global; tok < p.T; tok += nwarps) {
+    const uint32_t tok_bytes = (uint32_t)(HS * p.D * 2);
+    uint8_t* wbuf = reinterpret_cast<uint8_t*>(sp) + hc_param_smem(p.D) + (size_t)warp * 2 * tok_bytes;
+    if (PF && lane == 0) {
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
+        fence_barrier_init();
+        if (warp_global < p.T) {
+            mbar_arrive_expect_tx(&bars[warp][0], tok_bytes);
+            bulk_load_1d(wbuf, p.xres + (size_t)warp_global * HS * p.D, tok_bytes, &bars[warp][0]);
+        }
+    }
+    stage_params(p, sp);
+    const LaneConst lc = lane_const(p, lane);
+    int it = 0;
+    for (long long tok = warp_global; tok < p.T; tok += nwarps, ++it) {
+        const __nv_bfloat16* rsrc = p.xres + (size_t)tok * HS * p.D;
+        if (PF) {
+            const int buf = it & 1;
+            const long long nxt = tok + nwarps;
+            __syncwarp();   // every lane is done reading the other buffer (previous token)
+            if (lane == 0 && nxt < p.T) {
+                mbar_arrive_expect_tx(&bars[warp][buf ^ 1], tok_bytes);
+                bulk_load_1d(wbuf + (size_t)(buf ^ 1) * tok_bytes, p.xres + (size_t)nxt * HS * p.D, tok_bytes, &bars[warp][buf ^ 1]);
+            }
+            mbar_wait(&bars[warp][buf], (uint32_t)(it >> 1) & 1u);
+            rsrc = reinterpret_cast<const __nv_bfloat16*>(wbuf + (size_t)buf * tok_bytes);
+        }
         TokState<VPT> st;
-        token_forward<VPT>(p, sp, tok, lane, st);
-        float br[VPT][8];
-        float bss = 0.f;
+        token_forward<VPT>(p, sp, rsrc, lane, lc, st);
+        f2 br[VPT][4];
+        f2 bss2 = splat(0.f);
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int c = lane + 32 * v;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float acc = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                f2 acc = fmul2(splat(st.alpha[0][0]), st.r[0][v][j]);
 #pragma unroll
-                for (int s = 0; s < HS; ++s) acc += st.alpha[s][0] * st.r[s][v][e];
-                br[v][e] = acc;
-                bss += acc * acc;
+                for (int s = 1; s < HS; ++s) acc = ffma2(splat(st.alpha[s][0]), st.r[s][v][j], acc);
+                br[v][j] = acc;
+                bss2 = ffma2(acc, acc, bss2);
             }
             if (c < nchunk) {
 #pragma unroll
                 for (int t = 1; t < HT; ++t) {
-                    float o[8];
+                    f2 o[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float acc = 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        f2 acc = fmul2(splat(st.alpha[0][t]), st.r[0][v][j]);
 #pragma unroll
-                        for (int s = 0; s < HS; ++s) acc += st.alpha[s][t] * st.r[s][v][e];
-                        o[e] = acc;
+                        for (int s = 1; s < HS; ++s) acc = ffma2(splat(st.alpha[s][t]), st.r[s][v][j], acc);
+                        o[j] = acc;
                     }
-                    *reinterpret_cast<uint4*>(p.res_out + ((size_t)tok * HS + (t - 1)) * p.D + c * 8) = pack8(o);
+                    *reinterpret_cast<uint4*>(p.res_out + ((size_t)tok * HS + (t - 1)) * p.D + c * 8) = pack8p(o);
                 }
             }
         }
-        {
-            float bsel = st.beta[0];
-#pragma unroll
-            for (int s = 1; s < HS; ++s) bsel = (lane == s) ? st.beta[s] : bsel;
-            if (lane < HS) p.beta_out[(size_t)tok * HS + lane] = bsel;
-        }
+        if (lane >= HS * HT && lane < HS * HT + HS) p.beta_out[(size_t)tok * HS + (lane - HS * HT)] = st.myval;   // lane-owned betas
         float c_norm = 1.f;
         const float* ng = nullptr;
         if (p.norm_mode) {
-            c_norm = sqrtf((float)p.D) / fmaxf(sqrtf(warp_sum(bss)), 1e-12f);
+            c_norm = sqrtf((float)p.D) / fmaxf(sqrtf(warp_sum(hsum(bss2))), 1e-12f);
             ng = norm_gain(p, tok);
         }
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int c = lane + 32 * v;
             if (c < nchunk) {
-                float o[8];
+                if (p.norm_mode) {
+                    f2 g[4];
+                    load_gain8(ng + c * 8, g);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = p.norm_mode ? br[v][e] * c_norm * __ldg(ng + c * 8 + e) : br[v][e];
-                *reinterpret_cast<uint4*>(p.branch + (size_t)tok * p.D + c * 8) = pack8(o);
+                    for (int j = 0; j < 4; ++j) br[v][j] = fmul2(fmul2(br[v][j], splat(c_norm)), g[j]);
+                }
+                *reinterpret_cast<uint4*>(p.branch + (size_t)tok * p.D + c * 8) = pack8p(br[v]);
             }
         }
     }
@@ -244,190 +311,214 @@ constexpr int HC_REC = 40;
 #define HC_BWD_MIN_BLOCKS 1
 #endif
 
-template <int VPT>
+template <int VPT, bool PF>
 __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(const HcP p, float* __restrict__ rec) {
     extern __shared__ float4 sp[];
     __shared__ float s_scal[32];
+    __shared__ uint64_t bars[8][2];
     if (threadIdx.x < 32) s_scal[threadIdx.x] = 0.f;
-    stage_params(p, sp);
     const int D = p.D, nchunk = D >> 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * HC_TOK_PER_BLOCK;
     const int n1 = min(p.rows_per_batch, n0 + HC_TOK_PER_BLOCK);
-    float g_sal[HS][HT], g_sbe[HS], g_as = 0.f, g_bs = 0.f;
-#pragma unroll
-    for (int s = 0; s < HS; ++s) {
-        g_sbe[s] = 0.f;
-#pragma unroll
-        for (int t = 0; t < HT; ++t) g_sal[s][t] = 0.f;
+    // PF: per-warp double buffer {r [HS][D], d_res [HS][D], d_branch [D]} filled by bulk (TMA) copies one token ahead
+    const uint32_t tok_bytes = (uint32_t)(HS * D * 2), br_bytes = (uint32_t)(D * 2), buf_bytes = 2 * tok_bytes + br_bytes;
+    uint8_t* wbuf = reinterpret_cast<uint8_t*>(sp) + hc_param_smem(D) + (size_t)warp * 2 * buf_bytes;
+    auto prefetch = [&](int n, int buf) {
+        const size_t tk = (size_t)b * p.rows_per_batch + n;
+        uint8_t* dst = wbuf + (size_t)buf * buf_bytes;
+        mbar_arrive_expect_tx(&bars[warp][buf], buf_bytes);
+        bulk_load_1d(dst, p.xres + tk * HS * D, tok_bytes, &bars[warp][buf]);
+        bulk_load_1d(dst + tok_bytes, p.d_res + tk * HS * D, tok_bytes, &bars[warp][buf]);
+        bulk_load_1d(dst + 2 * tok_bytes, p.d_branch + tk * D, br_bytes, &bars[warp][buf]);
+    };
+    if (PF && lane == 0) {
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
+        fence_barrier_init();
+        if (n0 + warp < n1) prefetch(n0 + warp, 0);
     }
-    const float sa = __ldg(p.ascale), sb = __ldg(p.bscale);
+    stage_params(p, sp);
+    const LaneConst lc = lane_const(p, lane);
+    float g_stat = 0.f, g_scale = 0.f;   // lane-owned: d(static_alpha[l] | static_beta[l-20]) and this lane's share of d(dynamic scale)
     const float invD = 1.f / (float)D;
 
-    for (int n = n0 + warp; n < n1; n += 8) {
+    int it = 0;
+    for (int n = n0 + warp; n < n1; n += 8, ++it) {
         const long long tok = (long long)b * p.rows_per_batch + n;
+        const __nv_bfloat16* rsrc = p.xres + (size_t)tok * HS * D;
+        const __nv_bfloat16* drsrc = p.d_res + (size_t)tok * HS * D;
+        const __nv_bfloat16* dbsrc = p.d_branch + (size_t)tok * D;
+        if (PF) {
+            const int buf = it & 1;
+            __syncwarp();   // every lane is done reading the other buffer (previous token)
+            if (lane == 0 && n + 8 < n1) prefetch(n + 8, buf ^ 1);
+            mbar_wait(&bars[warp][buf], (uint32_t)(it >> 1) & 1u);
+            const uint8_t* src = wbuf + (size_t)buf * buf_bytes;
+            rsrc = reinterpret_cast<const __nv_bfloat16*>(src);
+            drsrc = reinterpret_cast<const __nv_bfloat16*>(src + tok_bytes);
+            dbsrc = reinterpret_cast<const __nv_bfloat16*>(src + 2 * tok_bytes);
+        }
         TokState<VPT> st;
-        token_forward<VPT>(p, sp, tok, lane, st);
+        token_forward<VPT>(p, sp, rsrc, lane, lc, st);
 
         // ---- branch (mix_0), its norm, and d(mix_0)
-        float dm0[VPT][8];
+        f2 dm0[VPT][4];
         float cn = 1.f;
         {
-            float br[VPT][8], dy[VPT][8];
-            float bss = 0.f;
+            f2 br[VPT][4];
+            f2 bss2 = splat(0.f);
 #pragma unroll
             for (int v = 0; v < VPT; ++v) {
                 const int c = lane + 32 * v;
-                if (c < nchunk) unpack8(*reinterpret_cast<const uint4*>(p.d_branch + (size_t)tok * D + c * 8), dy[v]);
+                if (c < nchunk) {
+                    unpack8p(*reinterpret_cast<const uint4*>(dbsrc + c * 8), dm0[v]);   // dy for now
+                } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    if (c >= nchunk) dy[v][e] = 0.f;
-                    float acc = 0.f;
+                    for (int j = 0; j < 4; ++j) dm0[v][j] = splat(0.f);
+                }
 #pragma unroll
-                    for (int s = 0; s < HS; ++s) acc += st.alpha[s][0] * st.r[s][v][e];
-                    br[v][e] = acc;
-                    bss += acc * acc;
+                for (int j = 0; j < 4; ++j) {
+                    f2 acc = fmul2(splat(st.alpha[0][0]), st.r[0][v][j]);
+#pragma unroll
+                    for (int s = 1; s < HS; ++s) acc = ffma2(splat(st.alpha[s][0]), st.r[s][v][j], acc);
+                    br[v][j] = acc;
+                    bss2 = ffma2(acc, acc, bss2);
                 }
             }
             if (p.norm_mode) {
-                cn = sqrtf((float)D) / fmaxf(sqrtf(warp_sum(bss)), 1e-12f);
+                cn = sqrtf((float)D) / fmaxf(sqrtf(warp_sum(hsum(bss2))), 1e-12f);
                 const float* ng = norm_gain(p, tok);
-                float dot = 0.f;
+                f2 dot2 = splat(0.f);
 #pragma unroll
                 for (int v = 0; v < VPT; ++v) {
                     const int c = lane + 32 * v;
                     if (c < nchunk) {
+                        f2 g[4];
+                        load_gain8(ng + c * 8, g);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) dot += __ldg(ng + c * 8 + e) * dy[v][e] * br[v][e];
+                        for (int j = 0; j < 4; ++j) {
+                            dm0[v][j] = fmul2(g[j], dm0[v][j]);             // gain * dy
+                            dot2 = ffma2(dm0[v][j], br[v][j], dot2);
+                        }
                     }
                 }
-                dot = warp_sum(dot);
-                const float k2 = cn * cn * cn * invD * dot;
-#pragma unroll
-                for (int v = 0; v < VPT; ++v) {
-                    const int c = lane + 32 * v;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        dm0[v][e] = (c < nchunk) ? cn * __ldg(ng + c * 8 + e) * dy[v][e] - br[v][e] * k2 : 0.f;
-                }
-            } else {
+                const float dot = warp_sum(hsum(dot2));
+                const f2 nk2 = splat(-(cn * cn * cn * invD * dot)), cn2 = splat(cn);
 #pragma unroll
                 for (int v = 0; v < VPT; ++v)
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) dm0[v][e] = dy[v][e];
+                    for (int j = 0; j < 4; ++j) dm0[v][j] = ffma2(dm0[v][j], cn2, fmul2(br[v][j], nk2));   // 0 beyond nchunk
             }
         }
         // ---- d_alpha[s][t] = <d_mix_t, r_s>; start d_r_s = sum_t alpha[s][t] d_mix_t
-        float dr[HS][VPT][8];
-        float red[32];
+        f2 dr[HS][VPT][4];
+        f2 red2[HS][HT];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) red[i] = 0.f;
+        for (int s = 0; s < HS; ++s)
+#pragma unroll
+            for (int t = 0; t < HT; ++t) red2[s][t] = splat(0.f);
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int c = lane + 32 * v;
 #pragma unroll
             for (int s = 0; s < HS; ++s)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    dr[s][v][e] = st.alpha[s][0] * dm0[v][e];
-                    red[s * HT] += dm0[v][e] * st.r[s][v][e];
+                for (int j = 0; j < 4; ++j) {
+                    dr[s][v][j] = fmul2(splat(st.alpha[s][0]), dm0[v][j]);
+                    red2[s][0] = ffma2(dm0[v][j], st.r[s][v][j], red2[s][0]);
                 }
             if (c < nchunk) {
 #pragma unroll
                 for (int t = 1; t < HT; ++t) {
-                    float dm[8];
-                    unpack8(*reinterpret_cast<const uint4*>(p.d_res + ((size_t)tok * HS + (t - 1)) * D + c * 8), dm);
+                    f2 dm[4];
+                    unpack8p(*reinterpret_cast<const uint4*>(drsrc + (size_t)(t - 1) * D + c * 8), dm);
 #pragma unroll
                     for (int s = 0; s < HS; ++s)
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            dr[s][v][e] += st.alpha[s][t] * dm[e];
-                            red[s * HT + t] += dm[e] * st.r[s][v][e];
+                        for (int j = 0; j < 4; ++j) {
+                            dr[s][v][j] = ffma2(splat(st.alpha[s][t]), dm[j], dr[s][v][j]);
+                            red2[s][t] = ffma2(dm[j], st.r[s][v][j], red2[s][t]);
                         }
                 }
             }
         }
-        const float mine = warp_reduce32(red, lane);
-        float dwc[HS][HT], ddc[HS];
+        float red[32];
 #pragma unroll
-        for (int s = 0; s < HS; ++s) {
-            const float dbe = p.d_beta ? __ldg(p.d_beta + (size_t)tok * HS + s) : 0.f;
-            ddc[s] = dbe * sb * (1.f - st.thb[s] * st.thb[s]);
-            g_bs += dbe * st.thb[s];
-            g_sbe[s] += dbe;
+        for (int i = 0; i < 32; ++i) red[i] = 0.f;
 #pragma unroll
-            for (int t = 0; t < HT; ++t) {
-                const float da = __shfl_sync(0xffffffffu, mine, s * HT + t);
-                dwc[s][t] = da * sa * (1.f - st.tha[s][t] * st.tha[s][t]);
-                g_as += da * st.tha[s][t];
-                g_sal[s][t] += da;
-            }
-        }
-        // per-token record for the parameter kernel
+        for (int s = 0; s < HS; ++s)
+#pragma unroll
+            for (int t = 0; t < HT; ++t) red[s * HT + t] = hsum(red2[s][t]);
+        const float mine = warp_reduce32(red, lane);     // lane s*HT+t owns d_alpha[s][t]; lanes >= 20 hold 0
+        // ---- scalar backward, lane-owned (lane l < 20: alpha_l, lane 20+s: beta_s): d(static), d(scale), d(tanh argument)
+        const bool is_beta = lane >= HS * HT && lane < HS * HT + HS;
+        const float dval = is_beta ? (p.d_beta ? __ldg(p.d_beta + (size_t)tok * HS + (lane - HS * HT)) : 0.f) : mine;
+        g_stat += dval;
+        g_scale += dval * st.myth;
+        const float mycoef = dval * lc.scale * (1.f - st.myth * st.myth);   // d_wc[s][t] (resp. d_dc[s]); 0 in lanes >= 24
+        // per-token record for the parameter kernel: inv[4], d_wc[20], d_dc[4], alpha[:,0][4], c_norm
         {
-            float val = 0.f;
+            float a0 = st.alpha[0][0], iv = st.inv[0];
 #pragma unroll
-            for (int s = 0; s < HS; ++s) {
-                if (lane == s) val = st.inv[s];
-                if (lane == 24 + s) val = ddc[s];
-                if (lane == 28 + s) val = st.alpha[s][0];
-#pragma unroll
-                for (int t = 0; t < HT; ++t)
-                    if (lane == 4 + s * HT + t) val = dwc[s][t];
+            for (int s = 1; s < HS; ++s) {
+                a0 = (lane == 24 + s) ? st.alpha[s][0] : a0;
+                iv = (lane == s) ? st.inv[s] : iv;
             }
-            rec[(size_t)tok * HC_REC + lane] = val;
+            if (lane < 28) rec[(size_t)tok * HC_REC + 4 + lane] = lane < 24 ? mycoef : a0;
+            if (lane < HS) rec[(size_t)tok * HC_REC + lane] = iv;
             if (lane == 0) rec[(size_t)tok * HC_REC + 32] = cn;
         }
-        // ---- through n^ = r * inv * (gamma+1)
-        float R[HS] = {0.f, 0.f, 0.f, 0.f};
-        float u[HS][VPT][8];
+        // ---- through n^ = r * inv * (gamma+1): u_s = sum_k coef[s][k] * P_k (P = the staged (gamma+1)-scaled A / b columns),
+        //      d_r_s += inv_s * u_s - r_s * inv_s^3 / D * <u_s, r_s>.  <u_s, r_s> = sum_k coef[s][k] * <P_k, r_s>, and those raw dot
+        //      products are what the forward reduction left in lanes 0..23 — no second pass over the features is needed.
+        float nk3[HS], cw[HS][6];
+        {
+            const float term = mycoef * st.myraw;
+            const float cws = mycoef * st.myinv;
+#pragma unroll
+            for (int s = 0; s < HS; ++s) {
+                float Rs = __shfl_sync(0xffffffffu, term, HS * HT + s);
+                cw[s][5] = __shfl_sync(0xffffffffu, cws, HS * HT + s);
+#pragma unroll
+                for (int t = 0; t < HT; ++t) {
+                    Rs += __shfl_sync(0xffffffffu, term, s * HT + t);
+                    cw[s][t] = __shfl_sync(0xffffffffu, cws, s * HT + t);
+                }
+                nk3[s] = -(st.inv[s] * st.inv[s] * st.inv[s] * invD * Rs);
+            }
+        }
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int c = lane + 32 * v;
             if (c < nchunk) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float4 p0 = sp[sp_idx(nchunk, c, e, 0)], p1 = sp[sp_idx(nchunk, c, e, 1)];   // already scaled by (gamma+1)
+                for (int j = 0; j < 4; ++j) {
+                    const float4 q0 = sp[sp_idx(nchunk, c, j, 0)], q1 = sp[sp_idx(nchunk, c, j, 1)], q2 = sp[sp_idx(nchunk, c, j, 2)];
 #pragma unroll
                     for (int s = 0; s < HS; ++s) {
-                        const float uu = ddc[s] * p1.y + dwc[s][0] * p0.x + dwc[s][1] * p0.y + dwc[s][2] * p0.z + dwc[s][3] * p0.w + dwc[s][4] * p1.x;
-                        u[s][v][e] = uu;
-                        R[s] += uu * st.r[s][v][e];
+                        f2 acc = ffma2(st.r[s][v][j], splat(nk3[s]), dr[s][v][j]);
+                        acc = ffma2(splat(cw[s][0]), lo2(q0), acc); acc = ffma2(splat(cw[s][1]), hi2(q0), acc);
+                        acc = ffma2(splat(cw[s][2]), lo2(q1), acc); acc = ffma2(splat(cw[s][3]), hi2(q1), acc);
+                        acc = ffma2(splat(cw[s][4]), lo2(q2), acc); acc = ffma2(splat(cw[s][5]), hi2(q2), acc);
+                        dr[s][v][j] = acc;
                     }
                 }
-            } else {
 #pragma unroll
                 for (int s = 0; s < HS; ++s)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) u[s][v][e] = 0.f;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < HS; ++s) {
-            const float Rs = warp_sum(R[s]);
-            const float k3 = st.inv[s] * st.inv[s] * st.inv[s] * invD * Rs;
-#pragma unroll
-            for (int v = 0; v < VPT; ++v) {
-                const int c = lane + 32 * v;
-                if (c < nchunk) {
-                    float o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = dr[s][v][e] + st.inv[s] * u[s][v][e] - st.r[s][v][e] * k3;
-                    *reinterpret_cast<uint4*>(p.d_xres + ((size_t)tok * HS + s) * D + c * 8) = pack8(o);
-                }
+                    *reinterpret_cast<uint4*>(p.d_xres + ((size_t)tok * HS + s) * D + c * 8) = pack8p(dr[s][v]);
             }
         }
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < HS; ++s) {
-            atomicAdd(&s_scal[20 + s], g_sbe[s]);
-#pragma unroll
-            for (int t = 0; t < HT; ++t) atomicAdd(&s_scal[s * HT + t], g_sal[s][t]);
+    {
+        if (lane < HS * HT + HS) atomicAdd(&s_scal[lane], g_stat);   // [0,20) static_alpha, [20,24) static_beta
+        const float gas = warp_sum(lane < HS * HT ? g_scale : 0.f);
+        const float gbs = warp_sum((lane >= HS * HT && lane < HS * HT + HS) ? g_scale : 0.f);
+        if (lane == 0) {
+            atomicAdd(&s_scal[24], gas);
+            atomicAdd(&s_scal[25], gbs);
         }
-        atomicAdd(&s_scal[24], g_as);
-        atomicAdd(&s_scal[25], g_bs);
     }
     __syncthreads();
     if (threadIdx.x < 20) atomicAdd(p.g_salpha + threadIdx.x, s_scal[threadIdx.x]);
@@ -439,74 +530,79 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
 constexpr int HC_PARAM_TOK = 128;   // tokens per block (4 groups of 32)
 constexpr int HC_PARAM_COLS = 128;  // feature columns per block (64 threads x 2)
 
-__global__ void __launch_bounds__(256) hc_width_bwd_param_kernel(const HcP p, const float* __restrict__ rec) {
-    __shared__ float srec[HC_PARAM_TOK][36];
+__global__ void __launch_bounds__(256, 2) hc_width_bwd_param_kernel(const HcP p, const float* __restrict__ rec) {
+    __shared__ float4 srec[HC_PARAM_TOK][9];   // 36 floats of a token record: inv[4], d_wc[20], d_dc[4], alpha0[4], c_norm, pad[3]
     __shared__ float sred[8][HC_PARAM_COLS];
     const int D = p.D, b = blockIdx.z;
     const int n0 = blockIdx.x * HC_PARAM_TOK;
     const int ntok = min(p.rows_per_batch - n0, HC_PARAM_TOK);
     const long long tok0 = (long long)b * p.rows_per_batch + n0;
-    for (int i = threadIdx.x; i < ntok * 36; i += 256) srec[i / 36][i % 36] = rec[(size_t)(tok0 + i / 36) * HC_REC + (i % 36)];
+    for (int i = threadIdx.x; i < ntok * 9; i += 256)
+        srec[i / 9][i % 9] = *reinterpret_cast<const float4*>(rec + (size_t)(tok0 + i / 9) * HC_REC + (i % 9) * 4);
     for (int i = threadIdx.x; i < 8 * HC_PARAM_COLS; i += 256) sred[i / HC_PARAM_COLS][i % HC_PARAM_COLS] = 0.f;
     __syncthreads();
     const int cp = threadIdx.x & 63, tg = threadIdx.x >> 6;
     const int col = blockIdx.y * HC_PARAM_COLS + cp * 2;
     if (col < D) {
-        float g1[2], bf[2], af[2][HT], gaf[2][HT], gbf[2] = {0.f, 0.f}, ggam[2] = {0.f, 0.f}, gng[2] = {0.f, 0.f};
+        // the thread's two adjacent feature columns form one fp32x2 pair through the whole loop
+        f2 g1, bf, af[HT], gaf[HT], gbf = splat(0.f), ggam = splat(0.f), gng = splat(0.f);
+        g1 = make_float2(__ldg(p.gamma + col) + 1.f, __ldg(p.gamma + col + 1) + 1.f);
+        bf = make_float2(__ldg(p.bfn + col), __ldg(p.bfn + col + 1));
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            g1[q] = __ldg(p.gamma + col + q) + 1.f;
-            bf[q] = __ldg(p.bfn + col + q);
-#pragma unroll
-            for (int t = 0; t < HT; ++t) { af[q][t] = __ldg(p.afn + (col + q) * HT + t); gaf[q][t] = 0.f; }
+        for (int t = 0; t < HT; ++t) {
+            af[t] = make_float2(__ldg(p.afn + col * HT + t), __ldg(p.afn + (col + 1) * HT + t));
+            gaf[t] = splat(0.f);
         }
         const int nbeg = tg * 32, nend = min(ntok, nbeg + 32);
-#pragma unroll 4
-        for (int n = nbeg; n < nend; ++n) {
-            const float* rc = srec[n];
-            const size_t tok = (size_t)(tok0 + n);
-            float r[HS][2];
+        constexpr int PB = 8;   // tokens per batch: all 5 * PB loads of a batch are issued before its math (the loop is load-latency bound)
+        for (int nb = nbeg; nb < nend; nb += PB) {
+            uint32_t wr[PB][HS], wd[PB];
 #pragma unroll
-            for (int s = 0; s < HS; ++s) {
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(p.xres + (tok * HS + s) * D + col);
-                r[s][0] = bf16_lo(w); r[s][1] = bf16_hi(w);
-            }
-            float dy[2] = {0.f, 0.f};
-            if (p.norm_mode) {
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(p.d_branch + tok * D + col);
-                dy[0] = bf16_lo(w); dy[1] = bf16_hi(w);
+            for (int k = 0; k < PB; ++k) {
+                const int n = min(nb + k, nend - 1);
+                const size_t tok = (size_t)(tok0 + n);
+#pragma unroll
+                for (int s = 0; s < HS; ++s) wr[k][s] = __ldg(reinterpret_cast<const uint32_t*>(p.xres + (tok * HS + s) * D + col));
+                wd[k] = p.norm_mode ? __ldg(reinterpret_cast<const uint32_t*>(p.d_branch + tok * D + col)) : 0u;
             }
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                float bmix = 0.f;
+            for (int k = 0; k < PB; ++k) {
+                const int n = nb + k;
+                if (n >= nend) break;
+                float rc[36];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    const float4 q = srec[n][i];   // same address in every lane: broadcast
+                    rc[i * 4] = q.x; rc[i * 4 + 1] = q.y; rc[i * 4 + 2] = q.z; rc[i * 4 + 3] = q.w;
+                }
+                const f2 dy = make_float2(bf16_lo(wd[k]), bf16_hi(wd[k]));
+                f2 bmix = splat(0.f);
 #pragma unroll
                 for (int s = 0; s < HS; ++s) {
-                    const float rn = r[s][q] * rc[s];
-                    const float nh = rn * g1[q];
-                    const float ddc = rc[24 + s];
-                    float dnh = ddc * bf[q];
+                    const f2 r = make_float2(bf16_lo(wr[k][s]), bf16_hi(wr[k][s]));
+                    const f2 rn = fmul2(r, splat(rc[s]));
+                    const f2 nh = fmul2(rn, g1);
+                    const f2 ddc = splat(rc[24 + s]);
+                    f2 dnh = fmul2(ddc, bf);
 #pragma unroll
                     for (int t = 0; t < HT; ++t) {
-                        const float dwc = rc[4 + s * HT + t];
-                        dnh += dwc * af[q][t];
-                        gaf[q][t] += nh * dwc;
+                        const f2 dwc = splat(rc[4 + s * HT + t]);
+                        dnh = ffma2(dwc, af[t], dnh);
+                        gaf[t] = ffma2(nh, dwc, gaf[t]);
                     }
-                    gbf[q] += nh * ddc;
-                    ggam[q] += dnh * rn;
-                    bmix += rc[28 + s] * r[s][q];
+                    gbf = ffma2(nh, ddc, gbf);
+                    ggam = ffma2(dnh, rn, ggam);
+                    bmix = ffma2(splat(rc[28 + s]), r, bmix);
                 }
-                gng[q] += dy[q] * bmix * rc[32];
+                gng = ffma2(fmul2(dy, splat(rc[32])), bmix, gng);
             }
         }
+        const int lc = cp * 2;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int lc = cp * 2 + q;
-#pragma unroll
-            for (int t = 0; t < HT; ++t) atomicAdd(&sred[t][lc], gaf[q][t]);
-            atomicAdd(&sred[5][lc], gbf[q]);
-            atomicAdd(&sred[6][lc], ggam[q]);
-            atomicAdd(&sred[7][lc], gng[q]);
-        }
+        for (int t = 0; t < HT; ++t) { atomicAdd(&sred[t][lc], gaf[t].x); atomicAdd(&sred[t][lc + 1], gaf[t].y); }
+        atomicAdd(&sred[5][lc], gbf.x); atomicAdd(&sred[5][lc + 1], gbf.y);
+        atomicAdd(&sred[6][lc], ggam.x); atomicAdd(&sred[6][lc + 1], ggam.y);
+        atomicAdd(&sred[7][lc], gng.x); atomicAdd(&sred[7][lc + 1], gng.y);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 8 * HC_PARAM_COLS; i += 256) {
@@ -584,6 +680,17 @@ __global__ void __launch_bounds__(256) hc_depth_bwd_kernel(const HdP p) {
     }
 }
 
+static bool hc_prefetch_enabled() {
+    static const bool on = !(getenv("B200_HC_PREFETCH") && atoi(getenv("B200_HC_PREFETCH")) == 0);   // developer A/B switch, default on
+    return on;
+}
+template <typename K>
+static int set_smem(K kern, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);   // idempotent
+    B200_REQUIRE(e == cudaSuccess, "hyper-connections: cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+
 static int fill_hc(HcP& p, const b200_hc_width_args* a) {
     B200_REQUIRE(a->num_streams == HS, "hyper-connections: only num_residual_streams=4 is built (got %d)", a->num_streams);
     B200_REQUIRE(a->D >= 8 && (a->D % 8) == 0 && a->D <= 1024, "hyper-connections: D=%d must be a multiple of 8 and <= 1024", a->D);
@@ -606,11 +713,24 @@ extern "C" int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stre
     HcP p{};
     if (fill_hc(p, a)) return -1;
     p.branch = (__nv_bfloat16*)a->branch; p.res_out = (__nv_bfloat16*)a->res_out; p.beta_out = a->beta_out;
+    const size_t smem_par = hc_param_smem(a->D);
+    if (a->D <= 512 && hc_prefetch_enabled()) {
+        // prefetching variant: 2 blocks per SM, each warp owns a 2 x (HS*D*2)-byte token double buffer
+        const size_t smem = smem_par + (size_t)8 * 2 * HS * a->D * 2;
+        const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 2);
+        if (a->D <= 256) {
+            if (int rc = set_smem(hc_width_fwd_kernel<1, true>, smem)) return rc;
+            hc_width_fwd_kernel<1, true><<<grid, 256, smem, st>>>(p);
+        } else {
+            if (int rc = set_smem(hc_width_fwd_kernel<2, true>, smem)) return rc;
+            hc_width_fwd_kernel<2, true><<<grid, 256, smem, st>>>(p);
+        }
+        return check_launch("hc_width_fwd_kernel");
+    }
     const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 8);
-    const size_t smem = (size_t)a->D * 2 * sizeof(float4);
-    if (a->D <= 256) hc_width_fwd_kernel<1><<<grid, 256, smem, st>>>(p);
-    else if (a->D <= 512) hc_width_fwd_kernel<2><<<grid, 256, smem, st>>>(p);
-    else hc_width_fwd_kernel<4><<<grid, 256, smem, st>>>(p);
+    if (a->D <= 256) hc_width_fwd_kernel<1, false><<<grid, 256, smem_par, st>>>(p);
+    else if (a->D <= 512) hc_width_fwd_kernel<2, false><<<grid, 256, smem_par, st>>>(p);
+    else hc_width_fwd_kernel<4, false><<<grid, 256, smem_par, st>>>(p);
     return check_launch("hc_width_fwd_kernel");
 }
 
@@ -627,10 +747,19 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     p.g_bfn = a->g_dynamic_beta_fn; p.g_bscale = a->g_dynamic_beta_scale; p.g_sbeta = a->g_static_beta; p.g_ng = a->g_norm_gain;
     B200_REQUIRE(a->ws_records, "hc_width_bwd: missing per-token record workspace (T * 40 floats)");
     dim3 grid((a->rows_per_batch + HC_TOK_PER_BLOCK - 1) / HC_TOK_PER_BLOCK, a->T / a->rows_per_batch);
-    const size_t smem = (size_t)a->D * 2 * sizeof(float4);
-    if (a->D <= 256) hc_width_bwd_kernel<1><<<grid, 256, smem, st>>>(p, a->ws_records);
-    else if (a->D <= 512) hc_width_bwd_kernel<2><<<grid, 256, smem, st>>>(p, a->ws_records);
-    else hc_width_bwd_kernel<4><<<grid, 256, smem, st>>>(p, a->ws_records);
+    const size_t smem_par = hc_param_smem(a->D);
+    if (a->D <= 512 && hc_prefetch_enabled()) {
+        const size_t smem = smem_par + (size_t)8 * 2 * (2 * HS + 1) * a->D * 2;   // + per-warp {r, d_res, d_branch} double buffers
+        if (a->D <= 256) {
+            if (int rc = set_smem(hc_width_bwd_kernel<1, true>, smem)) return rc;
+            hc_width_bwd_kernel<1, true><<<grid, 256, smem, st>>>(p, a->ws_records);
+        } else {
+            if (int rc = set_smem(hc_width_bwd_kernel<2, true>, smem)) return rc;
+            hc_width_bwd_kernel<2, true><<<grid, 256, smem, st>>>(p, a->ws_records);
+        }
+    } else if (a->D <= 256) hc_width_bwd_kernel<1, false><<<grid, 256, smem_par, st>>>(p, a->ws_records);
+    else if (a->D <= 512) hc_width_bwd_kernel<2, false><<<grid, 256, smem_par, st>>>(p, a->ws_records);
+    else hc_width_bwd_kernel<4, false><<<grid, 256, smem_par, st>>>(p, a->ws_records);
     if (int rc = check_launch("hc_width_bwd_kernel")) return rc;
     dim3 grid2((a->rows_per_batch + HC_PARAM_TOK - 1) / HC_PARAM_TOK, (a->D + HC_PARAM_COLS - 1) / HC_PARAM_COLS, a->T / a->rows_per_batch);
     hc_width_bwd_param_kernel<<<grid2, 256, 0, st>>>(p, a->ws_records);

@@ -12,6 +12,8 @@
 //                                   exp2 + dropout, P_j written as bf16 into 128B-swizzled smem (the A operand of the PV MMA);
 //                                   P V accumulates in ONE TMEM accumulator over all key tiles and is read back once.
 // mbarrier pipelines: q_full, k_full/v_full/kv_empty[2], s_full/s_empty[2], p_full/p_empty[2], o_full.
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -39,6 +41,18 @@ __device__ __forceinline__ float tanh_approx(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// tanh of a pair on the FMA pipe: odd degree-9 Taylor polynomial, |error| < 5e-6 for |x| <= 0.5 (tanh.approx is ~5e-4). The clamp
+// argument score * scale / clamp is small in practice, so the callers take this path whenever a warp's whole tile fits the range and
+// keep MUFU.TANH for outliers: the softmax threads are MUFU/MIO-bound with two MUFU ops per score (ncu r3: xu 47 %, mio_throttle).
+constexpr float TANH_POLY_MAX = 0.5f;
+__device__ __forceinline__ float2 tanh_poly2(float2 x) {
+    const float2 x2 = __fmul2_rn(x, x);
+    float2 q = __ffma2_rn(x2, make_float2(62.f / 2835.f, 62.f / 2835.f), make_float2(-17.f / 315.f, -17.f / 315.f));
+    q = __ffma2_rn(q, x2, make_float2(2.f / 15.f, 2.f / 15.f));
+    q = __ffma2_rn(q, x2, make_float2(-1.f / 3.f, -1.f / 3.f));
+    q = __ffma2_rn(q, x2, make_float2(1.f, 1.f));
+    return __fmul2_rn(x, q);
 }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -194,12 +208,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[st]);
             float pv[32];
+            float amax = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
                 const float2 x = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), soc2);
-                const float2 y = __fmul2_rn(make_float2(tanh_approx(x.x), tanh_approx(x.y)), cl2);
-                pv[i] = ex2_approx(y.x);
-                pv[i + 1] = ex2_approx(y.y);
+                pv[i] = x.x; pv[i + 1] = x.y;
+                amax = fmaxf(amax, fmaxf(fabsf(x.x), fabsf(x.y)));
+            }
+            if (__all_sync(0xffffffffu, amax <= TANH_POLY_MAX)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 y = __fmul2_rn(tanh_poly2(make_float2(pv[i], pv[i + 1])), cl2);
+                    pv[i] = ex2_approx(y.x);
+                    pv[i + 1] = ex2_approx(y.y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 y = __fmul2_rn(make_float2(tanh_approx(pv[i]), tanh_approx(pv[i + 1])), cl2);
+                    pv[i] = ex2_approx(y.x);
+                    pv[i + 1] = ex2_approx(y.y);
+                }
             }
             if (mbits != 0xffffffffu) {
 #pragma unroll
@@ -358,11 +387,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint64_t kmn = make_smem_desc_sw128(smem_u32(sK), 128 * 128, 1024);        // MN-major (B of dQ)
             const uint64_t pT = make_smem_desc_sw128(smem_u32(sP), 128 * 128, 1024);         // MN-major A (P^T)
             const uint64_t dsT = make_smem_desc_sw128(smem_u32(sDS), 128 * 128, 1024);       // MN-major A (dS^T)
-            for (int i = 0; i < nq; ++i) {
-                const int st = i & 1;
-                const uint32_t ph = i & 1;
-                mbar_wait(&qdo_full[st], (i >> 1) & 1);
-                mbar_wait(sdp_empty, ph ^ 1);
+            // S_t = Q_t K^T and dP_t = dO_t V^T. They are issued one query tile AHEAD of the dV/dK/dQ MMAs: the math warps copy
+            // S/dP to registers first thing (sdp_empty), so tile t+1's scores are ready the moment they finish tile t and the three
+            // accumulation MMAs of tile t run under the math of tile t+1 (issued in tile order the two groups serialised: ncu r3).
+            auto issue_sdp = [&](int t) {
+                const int st = t & 1;
+                mbar_wait(&qdo_full[st], (t >> 1) & 1);
+                mbar_wait(sdp_empty, (uint32_t)(t & 1) ^ 1u);
                 tc_fence_after();
                 const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + st * TILE16), 0, 1024);
                 const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sDO + st * TILE16), 0, 1024);
@@ -371,6 +402,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16(tDP, dodesc + (uint64_t)(k * 2), vdesc + (uint64_t)(k * 2), id_s, k > 0 ? 1u : 0u);
                 umma_commit(sdp_full);
+            };
+            issue_sdp(0);
+            for (int i = 0; i < nq; ++i) {
+                const int st = i & 1;
+                const uint32_t ph = i & 1;
+                if (i + 1 < nq) issue_sdp(i + 1);
                 mbar_wait(pds_full, ph);
                 mbar_wait(dq_empty, ph ^ 1);
                 tc_fence_after();
@@ -442,12 +479,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const float2 soc2 = make_float2(p.scale_over_clamp, p.scale_over_clamp), cl2 = make_float2(p.clamp * LOG2E_F, p.clamp * LOG2E_F);
                 const float2 nlse2 = make_float2(-lse2, -lse2), sc2 = make_float2(p.scale, p.scale), nsc2 = make_float2(-p.scale, -p.scale);
                 const float2 ks2 = make_float2(keep_scale, keep_scale), ndl2 = make_float2(-dl, -dl);
+                float amax = 0.f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) amax = fmaxf(amax, fabsf(__uint_as_float(rs[e])));
+                const bool small = __all_sync(0xffffffffu, amax * fabsf(p.scale_over_clamp) <= TANH_POLY_MAX);   // same rule as the forward
+                auto score_math = [&](auto use_poly) {
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
                     // packed fp32x2 math on the key pair (e, e+1); the 1/(1-p) of the dropped probabilities that feed dV is applied
                     // once to the dV accumulator in the epilogue
                     const float2 x = __fmul2_rn(make_float2(__uint_as_float(rs[e]), __uint_as_float(rs[e + 1])), soc2);
-                    const float2 th = make_float2(tanh_approx(x.x), tanh_approx(x.y));
+                    float2 th;
+                    if constexpr (decltype(use_poly)::value) th = tanh_poly2(x);
+                    else th = make_float2(tanh_approx(x.x), tanh_approx(x.y));
                     const float2 y = __ffma2_rn(th, cl2, nlse2);
                     float2 pe = make_float2(ex2_approx(y.x), ex2_approx(y.y));
                     if (!no_mask) {
@@ -471,6 +515,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     ppk[e >> 1] = pack_bf16(pd.x, pd.y);
                     dpk[e >> 1] = pack_bf16(dsv.x, dsv.y);
                 }
+                };
+                if (small) score_math(std::true_type{});     // warp-uniform
+                else score_math(std::false_type{});
             }
             tc_fence_before();
             __syncwarp();

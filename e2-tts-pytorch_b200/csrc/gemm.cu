@@ -252,6 +252,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int tn = (w / p.tiles_m) % p.tiles_n;
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
+            // ---- epilogue vectors of this warp's column half, fetched while the accumulator is still being produced:
+            //      plain path : lane l holds columns colh0 + 4l .. +3 (BN/2 columns -> BN/8 lanes)
+            //      GEGLU path : per 128-column group [64 u | 64 gate]: lanes 16*sub + 0..7 hold this warp's 32 u columns, +8..15 its 32 gates
+            float4 bsl = make_float4(0.f, 0.f, 0.f, 0.f);
+            int slice_col = -1;
+            if (!p.geglu) {
+                if (lane * 4 < BN / 2) slice_col = tn * BN + chalf * (BN / 2) + lane * 4;
+            } else {
+                if ((lane >> 4) < BN / 128) slice_col = tn * BN + (lane >> 4) * 128 + ((lane >> 3) & 1) * 64 + chalf * 32 + (lane & 7) * 4;
+            }
+            auto load_slice = [&](const float* vec, float fill) {
+                float4 o = make_float4(fill, fill, fill, fill);
+                if (slice_col >= 0 && slice_col < p.N) {
+                    if (slice_col + 4 <= p.N && ((reinterpret_cast<uintptr_t>(vec + slice_col) & 15) == 0)) {
+                        o = __ldg(reinterpret_cast<const float4*>(vec + slice_col));
+                    } else {
+                        o.x = __ldg(vec + slice_col);
+                        if (slice_col + 1 < p.N) o.y = __ldg(vec + slice_col + 1);
+                        if (slice_col + 2 < p.N) o.z = __ldg(vec + slice_col + 2);
+                        if (slice_col + 3 < p.N) o.w = __ldg(vec + slice_col + 3);
+                    }
+                }
+                return o;
+            };
+            if (p.bias) bsl = load_slice(p.bias, 0.f);
+            float4 csl_mh[MH];
+            bool csu_mh[MH];
+#pragma unroll
+            for (int mh = 0; mh < MH; ++mh) {
+                csl_mh[mh] = make_float4(1.f, 1.f, 1.f, 1.f);
+                csu_mh[mh] = false;
+                if (p.colscale) {
+                    const int rfirst = tm * BMT + mh * BM + q * 32, rlast = min(rfirst + 31, p.M - 1);
+                    if (rfirst < p.M && rfirst / p.rows_per_batch == rlast / p.rows_per_batch) {   // warp-uniform batch element
+                        csu_mh[mh] = true;
+                        csl_mh[mh] = load_slice(p.colscale + (long long)(rfirst / p.rows_per_batch) * p.N, 1.f);
+                    }
+                }
+            }
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
 #pragma unroll 1
@@ -261,6 +300,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t taddr = tmem_base + as * (MH * BN) + mh * BN + ((uint32_t)(q * 32) << 16);
             const bool masked = p.rowmask && row_ok && (p.rowmask[row] == 0);
             const float* cs = (p.colscale && row_ok) ? p.colscale + (long long)(row / p.rows_per_batch) * p.N : nullptr;
+            const float4 csl = (MH == 1 || mh == 0) ? csl_mh[0] : csl_mh[MH - 1];
+            const bool cs_uniform = (MH == 1 || mh == 0) ? csu_mh[0] : csu_mh[MH - 1];
 
             if (!p.geglu) {
                 uint8_t* stg = stg_base + ew * 4224;
@@ -276,31 +317,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (col0 >= p.N) continue;                       // warp-uniform
                     const int nvalid = min(32, p.N - col0);
                     const bool pair_full = !p.d_fp32 && (tn * BN + (c & ~1) * 32 + 64 <= p.N);   // warp-uniform: staged 128-byte rows
-                    if (!row_ok && !pair_full && !p.atomic_out) continue;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    // bias / gate vectors are warp-uniform: 16-byte loads (8 instead of 32 LSU instructions per chunk)
+                    // bias / gate vectors: the warp's slice was fetched before the accumulator wait (one float4 per lane) and is
+                    // broadcast with shuffles — a global load here would sit on the epilogue's critical path once per chunk
+                    const int sl = (c - chalf * (BN / 64)) * 8;   // first lane holding this chunk's 32 columns
                     if (p.bias) {
-                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + g);
-                                v[g * 4] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + col0 + j);
+                        for (int j = 0; j < 32; ++j) {
+                            const float comp = (j & 3) == 0 ? bsl.x : (j & 3) == 1 ? bsl.y : (j & 3) == 2 ? bsl.z : bsl.w;
+                            v[j] += __shfl_sync(0xffffffffu, comp, sl + (j >> 2));
                         }
                     }
-                    if (cs) {
-                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(cs) & 15) == 0)) {
+                    if (p.colscale) {
+                        if (cs_uniform) {
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + col0) + g);
-                                v[g * 4] *= c4.x; v[g * 4 + 1] *= c4.y; v[g * 4 + 2] *= c4.z; v[g * 4 + 3] *= c4.w;
+                            for (int j = 0; j < 32; ++j) {
+                                const float comp = (j & 3) == 0 ? csl.x : (j & 3) == 1 ? csl.y : (j & 3) == 2 ? csl.z : csl.w;
+                                v[j] *= __shfl_sync(0xffffffffu, comp, sl + (j >> 2));
                             }
-                        } else {
+                        } else if (cs) {   // the warp's 32 rows straddle two batch elements: per-lane gate rows
 #pragma unroll
                             for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] *= __ldg(cs + col0 + j);
                         }
@@ -348,7 +385,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         } else {
                             held[0] = pk[0]; held[1] = pk[1]; held[2] = pk[2]; held[3] = pk[3];
                         }
-                    } else {
+                    } else if (row_ok) {
                         __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + col0;
                         if (nvalid == 32) {
 #pragma unroll
@@ -380,13 +417,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float u[32], g[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { u[j] = __uint_as_float(ru[j]); g[j] = __uint_as_float(rg[j]); }
-                    if (p.bias) {   // packed bias, warp-uniform: 16-byte loads
+                    if (p.bias) {   // packed bias: slices fetched before the accumulator wait, broadcast by shuffle
 #pragma unroll
-                        for (int q4 = 0; q4 < 8; ++q4) {
-                            const float4 bu = __ldg(reinterpret_cast<const float4*>(p.bias + colp) + q4);
-                            const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + colp + 64) + q4);
-                            u[q4 * 4] += bu.x; u[q4 * 4 + 1] += bu.y; u[q4 * 4 + 2] += bu.z; u[q4 * 4 + 3] += bu.w;
-                            g[q4 * 4] += bg.x; g[q4 * 4 + 1] += bg.y; g[q4 * 4 + 2] += bg.z; g[q4 * 4 + 3] += bg.w;
+                        for (int j = 0; j < 32; ++j) {
+                            const float comp = (j & 3) == 0 ? bsl.x : (j & 3) == 1 ? bsl.y : (j & 3) == 2 ? bsl.z : bsl.w;
+                            u[j] += __shfl_sync(0xffffffffu, comp, sub * 16 + (j >> 2));
+                            g[j] += __shfl_sync(0xffffffffu, comp, sub * 16 + 8 + (j >> 2));
                         }
                     }
                     uint4 pu[4], pg[4], ph[4];

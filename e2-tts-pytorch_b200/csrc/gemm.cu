@@ -357,8 +357,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
                                 v[g * 8 + 6] += bf16_lo(u.w); v[g * 8 + 7] += bf16_hi(u.w);
                             }
-                        } else {
-                            for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(rp[j]);
+                        } else {   // (unrolled + predicated: a runtime trip count would index v[] dynamically and push it to local memory)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __bfloat162float(rp[j]);
                         }
                     }
                     if (p.d_fp32 && p.atomic_out) {
@@ -371,7 +372,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int g = 0; g < 8; ++g)
                                 *reinterpret_cast<float4*>(dp + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
                         } else {
-                            for (int j = 0; j < nvalid; ++j) dp[j] = v[j];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (j < nvalid) dp[j] = v[j];
                         }
                     } else if (pair_full) {
                         uint4 pk[4];
@@ -394,7 +396,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     make_uint4(pack_bf16(v[g * 8], v[g * 8 + 1]), pack_bf16(v[g * 8 + 2], v[g * 8 + 3]),
                                                pack_bf16(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16(v[g * 8 + 6], v[g * 8 + 7]));
                         } else {
-                            for (int j = 0; j < nvalid; ++j) dp[j] = __float2bfloat16(v[j]);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
                         }
                     }
                 }

@@ -298,25 +298,26 @@ __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(c
     }
 }
 
-// Backward, two kernels so that no per-element atomics are needed:
-//   (1) token kernel  : one warp per token — recompute the forward scalars, produce d_xres and a 40-float per-token
-//                       record (inv[4], d_wc[20], d_dc[4], alpha[:,0][4], c_norm, pad) plus the scalar parameter grads;
-//   (2) param kernel  : one thread per pair of feature columns, marching over a slab of tokens with the records in
-//                       shared memory — accumulates d(dynamic_alpha_fn), d(dynamic_beta_fn), d(norm.gamma), d(gain)
-//                       in registers; one global atomicAdd per column per block.
+// Backward:
+//   (1) token kernel   : one warp per token — recompute the forward scalars, produce d_xres, the scalar parameter grads, d(norm gain)
+//                        (register partial sums, one atomicAdd per column per block) and one bf16 row per (token, stream) of the
+//                        coefficient matrix C = inv * d(tanh argument);
+//   (2) tcgen05 GEMM   : G = R^T C over all (token, stream) rows (split-K), then hc_param_finalize_kernel turns G into
+//                        d(dynamic_alpha_fn), d(dynamic_beta_fn), d(norm.gamma).
 // grid.y = batch element: a block never straddles two batch elements (adaptive-gain gradient is per batch).
 constexpr int HC_TOK_PER_BLOCK = 64;
-constexpr int HC_REC = 40;
 #ifndef HC_BWD_MIN_BLOCKS
 #define HC_BWD_MIN_BLOCKS 1
 #endif
 
 template <int VPT, bool PF>
-__global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(const HcP p, float* __restrict__ rec) {
+__global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(const HcP p, __nv_bfloat16* __restrict__ cmat) {
     extern __shared__ float4 sp[];
     __shared__ float s_scal[32];
+    __shared__ float s_gng[VPT * 256];   // d(norm gain) partial sums of this block (one batch element), VPT*256 >= D
     __shared__ uint64_t bars[8][2];
     if (threadIdx.x < 32) s_scal[threadIdx.x] = 0.f;
+    for (int i = threadIdx.x; i < VPT * 256; i += 256) s_gng[i] = 0.f;
     const int D = p.D, nchunk = D >> 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -343,6 +344,14 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
     const LaneConst lc = lane_const(p, lane);
     float g_stat = 0.f, g_scale = 0.f;   // lane-owned: d(static_alpha[l] | static_beta[l-20]) and this lane's share of d(dynamic scale)
     const float invD = 1.f / (float)D;
+    f2 gng2[VPT][4];                     // d(norm gain) of this lane's columns, summed over the warp's tokens
+#pragma unroll
+    for (int v = 0; v < VPT; ++v)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gng2[v][j] = splat(0.f);
+    // where this lane's coefficient goes in the [T*S, 8] matrix handed to the parameter GEMM: row = stream, column = which tanh argument
+    const int c_row = lane < HS * HT ? lane / HT : (lane < HS * HT + HS ? lane - HS * HT : (lane - 24) >> 1);
+    const int c_col = lane < HS * HT ? lane % HT : (lane < HS * HT + HS ? HT : 6 + ((lane - 24) & 1));
 
     int it = 0;
     for (int n = n0 + warp; n < n1; n += 8, ++it) {
@@ -399,6 +408,7 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
                         load_gain8(ng + c * 8, g);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+                            gng2[v][j] = ffma2(fmul2(dm0[v][j], br[v][j]), splat(cn), gng2[v][j]);   // d gain += dy * normalised branch
                             dm0[v][j] = fmul2(g[j], dm0[v][j]);             // gain * dy
                             dot2 = ffma2(dm0[v][j], br[v][j], dot2);
                         }
@@ -458,18 +468,9 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
         g_stat += dval;
         g_scale += dval * st.myth;
         const float mycoef = dval * lc.scale * (1.f - st.myth * st.myth);   // d_wc[s][t] (resp. d_dc[s]); 0 in lanes >= 24
-        // per-token record for the parameter kernel: inv[4], d_wc[20], d_dc[4], alpha[:,0][4], c_norm
-        {
-            float a0 = st.alpha[0][0], iv = st.inv[0];
-#pragma unroll
-            for (int s = 1; s < HS; ++s) {
-                a0 = (lane == 24 + s) ? st.alpha[s][0] : a0;
-                iv = (lane == s) ? st.inv[s] : iv;
-            }
-            if (lane < 28) rec[(size_t)tok * HC_REC + 4 + lane] = lane < 24 ? mycoef : a0;
-            if (lane < HS) rec[(size_t)tok * HC_REC + lane] = iv;
-            if (lane == 0) rec[(size_t)tok * HC_REC + 32] = cn;
-        }
+        // row s of the coefficient matrix C[tok*S + s][8] = inv_s * { d_wc[s][0..4], d_dc[s], 0, 0 } (bf16): the parameter gradients
+        // d(dynamic_alpha_fn | dynamic_beta_fn | norm.gamma) are the GEMM  R^T C  over all (token, stream) rows (see hc_param_finalize)
+        cmat[((size_t)tok * HS + c_row) * 8 + c_col] = __float2bfloat16(mycoef * st.myinv);   // lanes >= 24 hold 0
         // ---- through n^ = r * inv * (gamma+1): u_s = sum_k coef[s][k] * P_k (P = the staged (gamma+1)-scaled A / b columns),
         //      d_r_s += inv_s * u_s - r_s * inv_s^3 / D * <u_s, r_s>.  <u_s, r_s> = sum_k coef[s][k] * <P_k, r_s>, and those raw dot
         //      products are what the forward reduction left in lanes 0..23 — no second pass over the features is needed.
@@ -511,6 +512,19 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
             }
         }
     }
+    if (p.norm_mode) {
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+            const int c = lane + 32 * v;
+            if (c < nchunk) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    atomicAdd(&s_gng[c * 8 + 2 * j], gng2[v][j].x);
+                    atomicAdd(&s_gng[c * 8 + 2 * j + 1], gng2[v][j].y);
+                }
+            }
+        }
+    }
     {
         if (lane < HS * HT + HS) atomicAdd(&s_scal[lane], g_stat);   // [0,20) static_alpha, [20,24) static_beta
         const float gas = warp_sum(lane < HS * HT ? g_scale : 0.f);
@@ -525,96 +539,31 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
     else if (threadIdx.x < 24) atomicAdd(p.g_sbeta + (threadIdx.x - 20), s_scal[threadIdx.x]);
     else if (threadIdx.x == 24) atomicAdd(p.g_ascale, s_scal[24]);
     else if (threadIdx.x == 25) atomicAdd(p.g_bscale, s_scal[25]);
+    if (p.norm_mode) {
+        float* dst = p.g_ng + (p.norm_mode == 2 ? (size_t)b * D : 0);
+        for (int i = threadIdx.x; i < D; i += 256) atomicAdd(dst + i, s_gng[i]);
+    }
 }
 
-constexpr int HC_PARAM_TOK = 128;   // tokens per block (4 groups of 32)
-constexpr int HC_PARAM_COLS = 128;  // feature columns per block (64 threads x 2)
-
-__global__ void __launch_bounds__(256, 2) hc_width_bwd_param_kernel(const HcP p, const float* __restrict__ rec) {
-    __shared__ float4 srec[HC_PARAM_TOK][9];   // 36 floats of a token record: inv[4], d_wc[20], d_dc[4], alpha0[4], c_norm, pad[3]
-    __shared__ float sred[8][HC_PARAM_COLS];
-    const int D = p.D, b = blockIdx.z;
-    const int n0 = blockIdx.x * HC_PARAM_TOK;
-    const int ntok = min(p.rows_per_batch - n0, HC_PARAM_TOK);
-    const long long tok0 = (long long)b * p.rows_per_batch + n0;
-    for (int i = threadIdx.x; i < ntok * 9; i += 256)
-        srec[i / 9][i % 9] = *reinterpret_cast<const float4*>(rec + (size_t)(tok0 + i / 9) * HC_REC + (i % 9) * 4);
-    for (int i = threadIdx.x; i < 8 * HC_PARAM_COLS; i += 256) sred[i / HC_PARAM_COLS][i % HC_PARAM_COLS] = 0.f;
-    __syncthreads();
-    const int cp = threadIdx.x & 63, tg = threadIdx.x >> 6;
-    const int col = blockIdx.y * HC_PARAM_COLS + cp * 2;
-    if (col < D) {
-        // the thread's two adjacent feature columns form one fp32x2 pair through the whole loop
-        f2 g1, bf, af[HT], gaf[HT], gbf = splat(0.f), ggam = splat(0.f), gng = splat(0.f);
-        g1 = make_float2(__ldg(p.gamma + col) + 1.f, __ldg(p.gamma + col + 1) + 1.f);
-        bf = make_float2(__ldg(p.bfn + col), __ldg(p.bfn + col + 1));
+// Parameter gradients from G[col][k] = sum_{token, stream} r[token, stream, col] * C[(token, stream)][k]  (fp32 [D, 8], produced by the
+// tcgen05 GEMM  R^T C):  with n^ = r * inv * (gamma + 1) and C = inv * d(tanh argument),
+//   d dynamic_alpha_fn[col][t] = (gamma+1) G[col][t],  d dynamic_beta_fn[col] = (gamma+1) G[col][5],
+//   d norm.gamma[col]          = sum_t alpha_fn[col][t] G[col][t] + beta_fn[col] G[col][5].
+// (The first versions marched 128-token slabs per thread pair on the CUDA cores: 48 us per call against ~15 us for the GEMM.)
+__global__ void __launch_bounds__(256) hc_param_finalize_kernel(const HcP p, const float* __restrict__ G) {
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col >= p.D) return;
+    const float4 g0 = *reinterpret_cast<const float4*>(G + (size_t)col * 8), g1v = *reinterpret_cast<const float4*>(G + (size_t)col * 8 + 4);
+    const float g[6] = {g0.x, g0.y, g0.z, g0.w, g1v.x, g1v.y};
+    const float gp1 = __ldg(p.gamma + col) + 1.f;
+    float dgam = __ldg(p.bfn + col) * g[5];
 #pragma unroll
-        for (int t = 0; t < HT; ++t) {
-            af[t] = make_float2(__ldg(p.afn + col * HT + t), __ldg(p.afn + (col + 1) * HT + t));
-            gaf[t] = splat(0.f);
-        }
-        const int nbeg = tg * 32, nend = min(ntok, nbeg + 32);
-        constexpr int PB = 8;   // tokens per batch: all 5 * PB loads of a batch are issued before its math (the loop is load-latency bound)
-        for (int nb = nbeg; nb < nend; nb += PB) {
-            uint32_t wr[PB][HS], wd[PB];
-#pragma unroll
-            for (int k = 0; k < PB; ++k) {
-                const int n = min(nb + k, nend - 1);
-                const size_t tok = (size_t)(tok0 + n);
-#pragma unroll
-                for (int s = 0; s < HS; ++s) wr[k][s] = __ldg(reinterpret_cast<const uint32_t*>(p.xres + (tok * HS + s) * D + col));
-                wd[k] = p.norm_mode ? __ldg(reinterpret_cast<const uint32_t*>(p.d_branch + tok * D + col)) : 0u;
-            }
-#pragma unroll
-            for (int k = 0; k < PB; ++k) {
-                const int n = nb + k;
-                if (n >= nend) break;
-                float rc[36];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    const float4 q = srec[n][i];   // same address in every lane: broadcast
-                    rc[i * 4] = q.x; rc[i * 4 + 1] = q.y; rc[i * 4 + 2] = q.z; rc[i * 4 + 3] = q.w;
-                }
-                const f2 dy = make_float2(bf16_lo(wd[k]), bf16_hi(wd[k]));
-                f2 bmix = splat(0.f);
-#pragma unroll
-                for (int s = 0; s < HS; ++s) {
-                    const f2 r = make_float2(bf16_lo(wr[k][s]), bf16_hi(wr[k][s]));
-                    const f2 rn = fmul2(r, splat(rc[s]));
-                    const f2 nh = fmul2(rn, g1);
-                    const f2 ddc = splat(rc[24 + s]);
-                    f2 dnh = fmul2(ddc, bf);
-#pragma unroll
-                    for (int t = 0; t < HT; ++t) {
-                        const f2 dwc = splat(rc[4 + s * HT + t]);
-                        dnh = ffma2(dwc, af[t], dnh);
-                        gaf[t] = ffma2(nh, dwc, gaf[t]);
-                    }
-                    gbf = ffma2(nh, ddc, gbf);
-                    ggam = ffma2(dnh, rn, ggam);
-                    bmix = ffma2(splat(rc[28 + s]), r, bmix);
-                }
-                gng = ffma2(fmul2(dy, splat(rc[32])), bmix, gng);
-            }
-        }
-        const int lc = cp * 2;
-#pragma unroll
-        for (int t = 0; t < HT; ++t) { atomicAdd(&sred[t][lc], gaf[t].x); atomicAdd(&sred[t][lc + 1], gaf[t].y); }
-        atomicAdd(&sred[5][lc], gbf.x); atomicAdd(&sred[5][lc + 1], gbf.y);
-        atomicAdd(&sred[6][lc], ggam.x); atomicAdd(&sred[6][lc + 1], ggam.y);
-        atomicAdd(&sred[7][lc], gng.x); atomicAdd(&sred[7][lc + 1], gng.y);
+    for (int t = 0; t < HT; ++t) {
+        p.g_afn[col * HT + t] += gp1 * g[t];
+        dgam += __ldg(p.afn + col * HT + t) * g[t];
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 8 * HC_PARAM_COLS; i += 256) {
-        const int k = i / HC_PARAM_COLS, c = blockIdx.y * HC_PARAM_COLS + (i % HC_PARAM_COLS);
-        if (c >= D) continue;
-        const float v = sred[k][i % HC_PARAM_COLS];
-        if (k < HT) atomicAdd(p.g_afn + c * HT + k, v);
-        else if (k == 5) atomicAdd(p.g_bfn + c, v);
-        else if (k == 6) atomicAdd(p.g_gamma + c, v);
-        else if (p.norm_mode == 1) atomicAdd(p.g_ng + c, v);
-        else if (p.norm_mode == 2) atomicAdd(p.g_ng + (size_t)b * D + c, v);
-    }
+    p.g_bfn[col] += gp1 * g[5];
+    p.g_gamma[col] += dgam;
 }
 
 // ------------------------------------------------------------------------------------------------ depth
@@ -745,25 +694,37 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     p.d_xres = (__nv_bfloat16*)a->d_xres;
     p.g_gamma = a->g_norm_gamma; p.g_afn = a->g_dynamic_alpha_fn; p.g_ascale = a->g_dynamic_alpha_scale; p.g_salpha = a->g_static_alpha;
     p.g_bfn = a->g_dynamic_beta_fn; p.g_bscale = a->g_dynamic_beta_scale; p.g_sbeta = a->g_static_beta; p.g_ng = a->g_norm_gain;
-    B200_REQUIRE(a->ws_records, "hc_width_bwd: missing per-token record workspace (T * 40 floats)");
+    B200_REQUIRE(a->ws_records, "hc_width_bwd: missing workspace (T * 40 floats)");
+    // workspace: coefficient matrix C bf16 [T*S, 8] (64 B per token), then G fp32 [D, 8]
+    __nv_bfloat16* cmat = reinterpret_cast<__nv_bfloat16*>(a->ws_records);
+    float* G = a->ws_records + (size_t)a->T * 16;
+    B200_REQUIRE((size_t)a->T * 24 >= (size_t)a->D * 8, "hc_width_bwd: workspace too small for D=%d at T=%lld", a->D, (long long)a->T);
     dim3 grid((a->rows_per_batch + HC_TOK_PER_BLOCK - 1) / HC_TOK_PER_BLOCK, a->T / a->rows_per_batch);
     const size_t smem_par = hc_param_smem(a->D);
     if (a->D <= 512 && hc_prefetch_enabled()) {
         const size_t smem = smem_par + (size_t)8 * 2 * (2 * HS + 1) * a->D * 2;   // + per-warp {r, d_res, d_branch} double buffers
         if (a->D <= 256) {
             if (int rc = set_smem(hc_width_bwd_kernel<1, true>, smem)) return rc;
-            hc_width_bwd_kernel<1, true><<<grid, 256, smem, st>>>(p, a->ws_records);
+            hc_width_bwd_kernel<1, true><<<grid, 256, smem, st>>>(p, cmat);
         } else {
             if (int rc = set_smem(hc_width_bwd_kernel<2, true>, smem)) return rc;
-            hc_width_bwd_kernel<2, true><<<grid, 256, smem, st>>>(p, a->ws_records);
+            hc_width_bwd_kernel<2, true><<<grid, 256, smem, st>>>(p, cmat);
         }
-    } else if (a->D <= 256) hc_width_bwd_kernel<1, false><<<grid, 256, smem_par, st>>>(p, a->ws_records);
-    else if (a->D <= 512) hc_width_bwd_kernel<2, false><<<grid, 256, smem_par, st>>>(p, a->ws_records);
-    else hc_width_bwd_kernel<4, false><<<grid, 256, smem_par, st>>>(p, a->ws_records);
+    } else if (a->D <= 256) hc_width_bwd_kernel<1, false><<<grid, 256, smem_par, st>>>(p, cmat);
+    else if (a->D <= 512) hc_width_bwd_kernel<2, false><<<grid, 256, smem_par, st>>>(p, cmat);
+    else hc_width_bwd_kernel<4, false><<<grid, 256, smem_par, st>>>(p, cmat);
     if (int rc = check_launch("hc_width_bwd_kernel")) return rc;
-    dim3 grid2((a->rows_per_batch + HC_PARAM_TOK - 1) / HC_PARAM_TOK, (a->D + HC_PARAM_COLS - 1) / HC_PARAM_COLS, a->T / a->rows_per_batch);
-    hc_width_bwd_param_kernel<<<grid2, 256, 0, st>>>(p, a->ws_records);
-    return check_launch("hc_width_bwd_param_kernel");
+    // G = R^T C on the tensor cores: A = residual streams [T*S, D] read MN-major, B = C [T*S, 8] MN-major, split-K over the tokens
+    b200_gemm_args g = {};
+    g.A = a->xres; g.lda = a->D; g.a_mn_major = 1;
+    g.B = cmat; g.ldb = 8; g.b_mn_major = 1;
+    g.M = a->D; g.N = 8; g.K = (int64_t)a->T * HS;
+    g.D = G; g.ldd = 8; g.d_fp32 = 1;
+    const int tiles = (a->D + 255) / 256;
+    g.split_k = num_sms() / tiles > 1 ? num_sms() / tiles : 2;   // >= 2: the split-K path zeroes and accumulates G
+    if (int rc = b200_gemm(&g, stream)) return rc;
+    hc_param_finalize_kernel<<<(a->D + 255) / 256, 256, 0, st>>>(p, G);
+    return check_launch("hc_param_finalize_kernel");
 }
 
 extern "C" int b200_hc_depth_fwd(const b200_hc_depth_args* a, b200_stream_t stream) {

@@ -36,29 +36,68 @@ __device__ __forceinline__ float act_bwd(int a, float z) {
 
 constexpr int SL_MAXB = 64;
 
-// one warp per output feature n: Z[b,n] for all b
-__global__ void __launch_bounds__(256) small_linear_fwd_kernel(const b200_small_linear_args a) {
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (n >= a.N) return;
-    const float* w = a.W + (size_t)n * a.K;
-    const float bias = a.bias ? a.bias[n] : 0.f;
-    const int ac = act_of(a.act, a.seg, n);
-    for (int b0 = 0; b0 < a.B; b0 += 8) {
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int k = lane; k < a.K; k += 32) {
-            const float wv = __ldg(w + k);
+// One warp per output feature n, all batch rows at once: the weight row streams through once (the first version looped
+// over 8-row batch chunks and re-read it), X is staged in shared memory when it fits. 16 partial sums per lane are combined
+// by recursive halving so that lane b ends up owning batch row b.
+constexpr int SL_XS_MAX = 12 * 1024;   // floats of X staged in smem (48 KB)
+
+__device__ __forceinline__ void sl_halve16(float (&v)[16], int lane) {   // on return lane l (mod 16) holds the 32-lane sum of v[l % 16] in v[0]
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (b0 + j < a.B) acc[j] += wv * __ldg(a.X + (size_t)(b0 + j) * a.K + k);
+    for (int o = 8; o > 0; o >>= 1) {
+        const bool hi = lane & o;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = hi ? v[i] : v[i + o];
+            const float keep = hi ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+__global__ void __launch_bounds__(256) small_linear_fwd_kernel(const b200_small_linear_args a, int n_per_warp, int x_in_smem) {
+    extern __shared__ __align__(16) float xs[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    if (x_in_smem) {
+        for (int i = threadIdx.x; i < a.B * a.K; i += 256) xs[i] = a.X[i];
+        __syncthreads();
+    }
+    const float* X = x_in_smem ? xs : a.X;
+    const int nbeg = (blockIdx.x * 8 + wl) * n_per_warp;
+    for (int n = nbeg; n < min(a.N, nbeg + n_per_warp); ++n) {
+        const float* w = a.W + (size_t)n * a.K;
+        const float bias = a.bias ? a.bias[n] : 0.f;
+        const int ac = act_of(a.act, a.seg, n);
+        for (int b0 = 0; b0 < a.B; b0 += 16) {
+            float acc[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float s = sl_warp_sum(acc[j]);
-            if (lane == 0 && b0 + j < a.B) {
-                const float z = s + bias;
-                if (a.Z) a.Z[yidx(a, b0 + j, n)] = z;
-                a.Y[yidx(a, b0 + j, n)] = act_fwd(ac, z);
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            const int nb = min(16, a.B - b0);
+            if ((a.K & 3) == 0) {
+                for (int k = lane * 4; k < a.K; k += 128) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < nb) {
+                            const float4 xv = *reinterpret_cast<const float4*>(X + (size_t)(b0 + j) * a.K + k);
+                            acc[j] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+                        }
+                    }
+                }
+            } else {
+                for (int k = lane; k < a.K; k += 32) {
+                    const float wv = __ldg(w + k);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < nb) acc[j] += wv * X[(size_t)(b0 + j) * a.K + k];
+                }
+            }
+            sl_halve16(acc, lane);
+            const int b = b0 + (lane & 15);
+            if (lane < 16 && b < a.B) {
+                const float z = acc[0] + bias;
+                if (a.Z) a.Z[yidx(a, b, n)] = z;
+                a.Y[yidx(a, b, n)] = act_fwd(ac, z);
             }
         }
     }
@@ -86,21 +125,54 @@ __global__ void __launch_bounds__(256) small_linear_bwd_w_kernel(const b200_smal
         a.dW[(size_t)n * a.K + k] = acc;
     }
 }
-// dX[b,k] += sum_{n in block range} dZ[b,n] W[n,k]   (dX zeroed by the host wrapper)
-__global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_small_linear_args a, int n_per_block) {
-    const int n0 = blockIdx.x * n_per_block, n1 = min(a.N, n0 + n_per_block);
-    for (int k = threadIdx.x; k < a.K; k += 256) {
-        for (int b0 = 0; b0 < a.B; b0 += 8) {
-            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int n = n0; n < n1; ++n) {
-                const float wv = __ldg(a.W + (size_t)n * a.K + k);
+// dX[b,k] += sum_{n in block slab} dZ[b,n] W[n,k]   (dX zeroed by the host wrapper)
+// The block's dZ slab [B][256] is staged in shared memory once (the first version re-derived the strided dZ index with an integer
+// division for every (n, b), walked W twice and finished with 16x more scalar atomics). Fast path: a thread owns four
+// consecutive k (16-byte W loads, 16-byte vector reductions into dX) and one of two 128-row halves of the slab.
+constexpr int SL_SLAB = 256;
+__global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_small_linear_args a) {
+    extern __shared__ __align__(16) float sdz[];   // [B][SL_SLAB]
+    const int n0 = blockIdx.x * SL_SLAB, n1 = min(a.N, n0 + SL_SLAB);
+    for (int i = threadIdx.x; i < a.B * SL_SLAB; i += 256) {
+        const int b = i / SL_SLAB, nn = i % SL_SLAB;
+        sdz[i] = (n0 + nn < n1) ? a.dZ[yidx(a, b, n0 + nn)] : 0.f;
+    }
+    __syncthreads();
+    if ((a.K & 3) == 0 && a.K <= 512 && ((reinterpret_cast<uintptr_t>(a.dX) | reinterpret_cast<uintptr_t>(a.W)) & 15) == 0) {
+        const int kq = threadIdx.x & 127, grp = threadIdx.x >> 7;
+        if (kq * 4 >= a.K) return;
+        for (int b0 = 0; b0 < a.B; b0 += 16) {
+            const int nb = min(16, a.B - b0);
+            float4 acc[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (b0 + j < a.B) acc[j] += wv * a.dZ[yidx(a, b0 + j, n)];
+            for (int j = 0; j < 16; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int nn = grp * 128; nn < grp * 128 + 128; nn += 4) {
+                float4 w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    w[u] = (n0 + nn + u < n1) ? __ldg(reinterpret_cast<const float4*>(a.W + (size_t)(n0 + nn + u) * a.K + kq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j < nb) {
+                        const float4 z = *reinterpret_cast<const float4*>(&sdz[(b0 + j) * SL_SLAB + nn]);   // broadcast read
+                        acc[j].x += w[0].x * z.x + w[1].x * z.y + w[2].x * z.z + w[3].x * z.w;
+                        acc[j].y += w[0].y * z.x + w[1].y * z.y + w[2].y * z.z + w[3].y * z.w;
+                        acc[j].z += w[0].z * z.x + w[1].z * z.y + w[2].z * z.z + w[3].z * z.w;
+                        acc[j].w += w[0].w * z.x + w[1].w * z.y + w[2].w * z.z + w[3].w * z.w;
+                    }
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (b0 + j < a.B) atomicAdd(a.dX + (size_t)(b0 + j) * a.K + k, acc[j]);
+            for (int j = 0; j < 16; ++j)
+                if (j < nb) red_add_v4(a.dX + (size_t)(b0 + j) * a.K + kq * 4, acc[j].x, acc[j].y, acc[j].z, acc[j].w);
+        }
+        return;
+    }
+    for (int k = threadIdx.x; k < a.K; k += 256) {   // generic shapes
+        for (int b = 0; b < a.B; ++b) {
+            float acc = 0.f;
+            for (int n = n0; n < n1; ++n) acc += __ldg(a.W + (size_t)n * a.K + k) * sdz[b * SL_SLAB + (n - n0)];
+            atomicAdd(a.dX + (size_t)b * a.K + k, acc);
         }
     }
 }
@@ -420,7 +492,21 @@ extern "C" int b200_small_linear_fwd(const b200_small_linear_args* a, b200_strea
     B200_REQUIRE(a->B > 0 && a->B <= SL_MAXB && a->N > 0 && a->K > 0, "small_linear: batch must be 1..%d", SL_MAXB);
     B200_REQUIRE(a->act >= 0 && a->act <= 5 && (a->act != 5 || a->seg > 0), "small_linear: bad activation");
     B200_REQUIRE(!a->seg_major || (a->seg > 0 && a->N % a->seg == 0), "small_linear: seg_major needs N %% seg == 0");
-    small_linear_fwd_kernel<<<(a->N + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    {
+        const int x_in_smem = ((long long)a->B * a->K <= SL_XS_MAX) ? 1 : 0;
+        const size_t smem = x_in_smem ? (size_t)a->B * a->K * sizeof(float) : 0;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(small_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_XS_MAX * (int)sizeof(float));
+            B200_REQUIRE(e == cudaSuccess, "small_linear_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            configured = true;
+        }
+        // enough outputs per warp to amortise the X staging, but at least ~2 blocks per SM when N is large
+        int npw = 1;
+        while (npw < 8 && (a->N + 8 * (npw * 2) - 1) / (8 * (npw * 2)) >= 2 * num_sms()) npw *= 2;
+        const int per_block = 8 * npw;
+        small_linear_fwd_kernel<<<(a->N + per_block - 1) / per_block, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a, npw, x_in_smem);
+    }
     return check_launch("small_linear_fwd_kernel");
 }
 extern "C" int b200_small_linear_bwd(const b200_small_linear_args* a, b200_stream_t stream) {
@@ -432,8 +518,14 @@ extern "C" int b200_small_linear_bwd(const b200_small_linear_args* a, b200_strea
     if (a->dX) {
         cudaError_t e = cudaMemsetAsync(a->dX, 0, (size_t)a->B * a->K * sizeof(float), st);
         B200_REQUIRE(e == cudaSuccess, "small_linear_bwd: memset: %s", cudaGetErrorString(e));
-        const int npb = 64;
-        small_linear_bwd_x_kernel<<<(a->N + npb - 1) / npb, 256, 0, st>>>(*a, npb);
+        const size_t smem = (size_t)a->B * SL_SLAB * sizeof(float);   // <= 64 KB
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e2 = cudaFuncSetAttribute(small_linear_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_MAXB * SL_SLAB * (int)sizeof(float));
+            B200_REQUIRE(e2 == cudaSuccess, "small_linear_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
+            configured = true;
+        }
+        small_linear_bwd_x_kernel<<<(a->N + SL_SLAB - 1) / SL_SLAB, 256, smem, st>>>(*a);
         return check_launch("small_linear_bwd_x_kernel");
     }
     return 0;

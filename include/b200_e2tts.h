@@ -128,7 +128,7 @@ typedef struct {
     void* d_xres;
     float *g_norm_gamma, *g_dynamic_alpha_fn, *g_dynamic_alpha_scale, *g_static_alpha, *g_dynamic_beta_fn, *g_dynamic_beta_scale,
         *g_static_beta, *g_norm_gain;
-    float* ws_records;   /* bwd workspace: T * 40 floats (per-token scalars handed from the token kernel to the parameter kernel) */
+    float* ws_records;   /* bwd workspace: T * 40 floats (bf16 coefficient matrix [T*S, 8] + fp32 [D, 8] result of the parameter GEMM) */
 } b200_hc_width_args;
 int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stream);
 int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stream);

@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(576, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const AttnTcP p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET, not by integer round-trip: the pointer keeps its shared-memory provenance, so tile / staging
+    // accesses compile to LDS / STS instead of generic LD / ST (+ a full MEMBAR before the async-proxy fence)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE16;          // [2]
     uint8_t* sV = sK + 2 * TILE16;      // [2]
@@ -323,7 +325,9 @@ __global__ void __launch_bounds__(576, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmDO, const AttnBwdTcP p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET, not by integer round-trip: the pointer keeps its shared-memory provenance, so tile / staging
+    // accesses compile to LDS / STS instead of generic LD / ST (+ a full MEMBAR before the async-proxy fence)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sK = smem;
     uint8_t* sV = sK + TILE16;
     uint8_t* sQ = sV + TILE16;           // [2]
@@ -483,7 +487,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 32; ++e) amax = fmaxf(amax, fabsf(__uint_as_float(rs[e])));
                 const bool small = __all_sync(0xffffffffu, amax * fabsf(p.scale_over_clamp) <= TANH_POLY_MAX);   // same rule as the forward
-                auto score_math = [&](auto use_poly) {
+                // one straight-line variant per (tanh path, masking, dropout) combination — all three are warp-uniform, and a
+                // runtime test inside the unrolled loop costs predicate juggling and stack traffic on every key pair (ncu r5)
+                auto score_math = [&](auto use_poly, auto masked, auto dropped) {
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
                     // packed fp32x2 math on the key pair (e, e+1); the 1/(1-p) of the dropped probabilities that feed dV is applied
@@ -493,31 +499,37 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     if constexpr (decltype(use_poly)::value) th = tanh_poly2(x);
                     else th = make_float2(tanh_approx(x.x), tanh_approx(x.y));
                     const float2 y = __ffma2_rn(th, cl2, nlse2);
-                    float2 pe = make_float2(ex2_approx(y.x), ex2_approx(y.y));
-                    if (!no_mask) {
-                        pe.x = (rvalid && ((mbits1 >> e) & 1u)) ? pe.x : 0.f;
-                        pe.y = (rvalid && ((mbits1 >> (e + 1)) & 1u)) ? pe.y : 0.f;
+                    float pex = ex2_approx(y.x), pey = ex2_approx(y.y);
+                    if constexpr (decltype(masked)::value) {
+                        pex = (rvalid && ((mbits1 >> e) & 1u)) ? pex : 0.f;
+                        pey = (rvalid && ((mbits1 >> (e + 1)) & 1u)) ? pey : 0.f;
                     }
                     const float2 ds = __ffma2_rn(__fmul2_rn(th, nsc2), th, sc2);   // (1 - tanh^2) * scale = d(clamped logit)/d(raw score)
-                    float2 dp = make_float2(__uint_as_float(rd[e]), __uint_as_float(rd[e + 1]));
-                    float2 pd = pe;
+                    const float dpx = __uint_as_float(rd[e]), dpy = __uint_as_float(rd[e + 1]);
                     float2 t;
-                    if (p.dropout_p > 0.f) {
+                    if constexpr (decltype(dropped)::value) {
                         const uint32_t h = hash_pair32(seedmix, pbase + (e >> 1));
                         const bool k0_ = (h & 0xffffu) >= p.drop_thresh, k1_ = (h >> 16) >= p.drop_thresh;
-                        dp.x = k0_ ? dp.x : 0.f; dp.y = k1_ ? dp.y : 0.f;
-                        pd.x = k0_ ? pd.x : 0.f; pd.y = k1_ ? pd.y : 0.f;      // dV uses the dropped probabilities, dS the un-dropped ones
-                        t = __ffma2_rn(dp, ks2, ndl2);
+                        t = __ffma2_rn(make_float2(k0_ ? dpx : 0.f, k1_ ? dpy : 0.f), ks2, ndl2);
+                        ppk[e >> 1] = pack_bf16(k0_ ? pex : 0.f, k1_ ? pey : 0.f);   // dV uses the dropped probabilities, dS the un-dropped ones
                     } else {
-                        t = __fadd2_rn(dp, ndl2);
+                        t = __fadd2_rn(make_float2(dpx, dpy), ndl2);
+                        ppk[e >> 1] = pack_bf16(pex, pey);
                     }
-                    const float2 dsv = __fmul2_rn(__fmul2_rn(pe, t), ds);
-                    ppk[e >> 1] = pack_bf16(pd.x, pd.y);
+                    const float2 dsv = __fmul2_rn(__fmul2_rn(make_float2(pex, pey), t), ds);
                     dpk[e >> 1] = pack_bf16(dsv.x, dsv.y);
                 }
                 };
-                if (small) score_math(std::true_type{});     // warp-uniform
-                else score_math(std::false_type{});
+                using T_ = std::true_type;
+                using F_ = std::false_type;
+                const bool drop = p.dropout_p > 0.f;
+                if (small) {
+                    if (no_mask) { if (drop) score_math(T_{}, F_{}, T_{}); else score_math(T_{}, F_{}, F_{}); }
+                    else { if (drop) score_math(T_{}, T_{}, T_{}); else score_math(T_{}, T_{}, F_{}); }
+                } else {
+                    if (no_mask) { if (drop) score_math(F_{}, F_{}, T_{}); else score_math(F_{}, F_{}, F_{}); }
+                    else { if (drop) score_math(F_{}, T_{}, T_{}); else score_math(F_{}, T_{}, F_{}); }
+                }
             }
             tc_fence_before();
             __syncwarp();

@@ -96,7 +96,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
     const int w_first = blockIdx.x / CG, w_step = gridDim.x / CG;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET, not by integer round-trip: the pointer keeps its shared-memory provenance, so tile / staging
+    // accesses compile to LDS / STS instead of generic LD / ST (+ a full MEMBAR before the async-proxy fence)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smA = smem;
     uint8_t* smB = smem + kStages * S::A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);

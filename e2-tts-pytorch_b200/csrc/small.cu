@@ -129,24 +129,24 @@ __global__ void __launch_bounds__(256) small_linear_bwd_w_kernel(const b200_smal
 // The block's dZ slab [B][256] is staged in shared memory once (the first version re-derived the strided dZ index with an integer
 // division for every (n, b), walked W twice and finished with 16x more scalar atomics). Fast path: a thread owns four
 // consecutive k (16-byte W loads, 16-byte vector reductions into dX) and one of two 128-row halves of the slab.
-constexpr int SL_SLAB = 256;
-__global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_small_linear_args a) {
-    extern __shared__ __align__(16) float sdz[];   // [B][SL_SLAB]
-    const int n0 = blockIdx.x * SL_SLAB, n1 = min(a.N, n0 + SL_SLAB);
-    for (int i = threadIdx.x; i < a.B * SL_SLAB; i += 256) {
-        const int b = i / SL_SLAB, nn = i % SL_SLAB;
+constexpr int SL_SLAB = 256;   // largest slab of output features per block (a multiple of 8; smaller slabs when N is small)
+__global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_small_linear_args a, int slab) {
+    extern __shared__ __align__(16) float sdz[];   // [B][slab]
+    const int n0 = blockIdx.x * slab, n1 = min(a.N, n0 + slab);
+    for (int i = threadIdx.x; i < a.B * slab; i += 256) {
+        const int b = i / slab, nn = i % slab;
         sdz[i] = (n0 + nn < n1) ? a.dZ[yidx(a, b, n0 + nn)] : 0.f;
     }
     __syncthreads();
     if ((a.K & 3) == 0 && a.K <= 512 && ((reinterpret_cast<uintptr_t>(a.dX) | reinterpret_cast<uintptr_t>(a.W)) & 15) == 0) {
-        const int kq = threadIdx.x & 127, grp = threadIdx.x >> 7;
+        const int kq = threadIdx.x & 127, grp = threadIdx.x >> 7, half = slab >> 1;
         if (kq * 4 >= a.K) return;
         for (int b0 = 0; b0 < a.B; b0 += 16) {
             const int nb = min(16, a.B - b0);
             float4 acc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int nn = grp * 128; nn < grp * 128 + 128; nn += 4) {
+            for (int nn = grp * half; nn < grp * half + half; nn += 4) {
                 float4 w[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_smal
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (j < nb) {
-                        const float4 z = *reinterpret_cast<const float4*>(&sdz[(b0 + j) * SL_SLAB + nn]);   // broadcast read
+                        const float4 z = *reinterpret_cast<const float4*>(&sdz[(b0 + j) * slab + nn]);   // broadcast read
                         acc[j].x += w[0].x * z.x + w[1].x * z.y + w[2].x * z.z + w[3].x * z.w;
                         acc[j].y += w[0].y * z.x + w[1].y * z.y + w[2].y * z.z + w[3].y * z.w;
                         acc[j].z += w[0].z * z.x + w[1].z * z.y + w[2].z * z.z + w[3].z * z.w;
@@ -168,11 +168,28 @@ __global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_smal
         }
         return;
     }
-    for (int k = threadIdx.x; k < a.K; k += 256) {   // generic shapes
-        for (int b = 0; b < a.B; ++b) {
-            float acc = 0.f;
-            for (int n = n0; n < n1; ++n) acc += __ldg(a.W + (size_t)n * a.K + k) * sdz[b * SL_SLAB + (n - n0)];
-            atomicAdd(a.dX + (size_t)b * a.K + k, acc);
+    // generic shapes (e.g. the K = dim + 1 input of the time MLP): a thread owns one k column, 16 batch rows in registers
+    for (int k = threadIdx.x; k < a.K; k += 256) {
+        for (int b0 = 0; b0 < a.B; b0 += 16) {
+            const int nb = min(16, a.B - b0);
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            for (int nn = 0; nn < slab; nn += 4) {
+                float w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) w[u] = (n0 + nn + u < n1) ? __ldg(a.W + (size_t)(n0 + nn + u) * a.K + k) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j < nb) {
+                        const float4 z = *reinterpret_cast<const float4*>(&sdz[(b0 + j) * slab + nn]);
+                        acc[j] += w[0] * z.x + w[1] * z.y + w[2] * z.z + w[3] * z.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nb) atomicAdd(a.dX + (size_t)(b0 + j) * a.K + k, acc[j]);
         }
     }
 }
@@ -518,14 +535,16 @@ extern "C" int b200_small_linear_bwd(const b200_small_linear_args* a, b200_strea
     if (a->dX) {
         cudaError_t e = cudaMemsetAsync(a->dX, 0, (size_t)a->B * a->K * sizeof(float), st);
         B200_REQUIRE(e == cudaSuccess, "small_linear_bwd: memset: %s", cudaGetErrorString(e));
-        const size_t smem = (size_t)a->B * SL_SLAB * sizeof(float);   // <= 64 KB
+        int slab = SL_SLAB;   // fewer features per block when N is small, so that the slabs still cover the GPU
+        while (slab > 32 && (a->N + slab - 1) / slab < num_sms()) slab >>= 1;
+        const size_t smem = (size_t)a->B * slab * sizeof(float);   // <= 64 KB
         static bool configured = false;
         if (!configured) {
             cudaError_t e2 = cudaFuncSetAttribute(small_linear_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_MAXB * SL_SLAB * (int)sizeof(float));
             B200_REQUIRE(e2 == cudaSuccess, "small_linear_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
             configured = true;
         }
-        small_linear_bwd_x_kernel<<<(a->N + SL_SLAB - 1) / SL_SLAB, 256, smem, st>>>(*a);
+        small_linear_bwd_x_kernel<<<(a->N + slab - 1) / slab, 256, smem, st>>>(*a, slab);
         return check_launch("small_linear_bwd_x_kernel");
     }
     return 0;

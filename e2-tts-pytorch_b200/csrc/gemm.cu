@@ -509,7 +509,28 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements; box = 64 x box_outer, 128B swizzle.
+// A descriptor is a pure function of (pointer, extents, pitch, box): the caching allocator hands the same addresses back every
+// training step, so a small per-thread direct-mapped cache removes ~1000 driver encode calls per step from the host critical path.
+struct MapKey { const void* ptr; int64_t inner, outer, ld; int box; };
+struct MapSlot { MapKey k; CUtensorMap m; bool valid; };
+static int make_map_uncached(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer);
 static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+    constexpr int kSlots = 512;
+    static thread_local MapSlot cache[kSlots];
+    uint64_t h = reinterpret_cast<uintptr_t>(ptr) >> 4;
+    h = (h ^ (uint64_t)inner * 0x9E3779B97F4A7C15ull ^ (uint64_t)outer * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)ld * 0x165667B19E3779F9ull ^ (uint64_t)box_outer) * 0xFF51AFD7ED558CCDull;
+    MapSlot& sl = cache[(h >> 40) % kSlots];
+    if (sl.valid && sl.k.ptr == ptr && sl.k.inner == inner && sl.k.outer == outer && sl.k.ld == ld && sl.k.box == box_outer) {
+        *m = sl.m;
+        return 0;
+    }
+    if (int rc = make_map_uncached(m, ptr, inner, outer, ld, box_outer)) return rc;
+    sl.k = MapKey{ptr, inner, outer, ld, box_outer};
+    sl.m = *m;
+    sl.valid = true;
+    return 0;
+}
+static int make_map_uncached(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
     PFN_encodeTiled enc = get_encode_fn();
     B200_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
     B200_REQUIRE((ld % 8) == 0, "gemm: row pitch %lld not a multiple of 8 elements", (long long)ld);

@@ -230,8 +230,10 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float 
 // half >= thresh, thresh = p * 65536. idx = row_id * drop_stride + key with drop_stride even, so (idx >> 1) pairs keys
 // (2k, 2k+1) of one query row; only the low 32 bits of the pair index are hashed (the pattern repeats after 2^33 scores).
 __device__ __forceinline__ uint32_t hash_pair32(uint32_t seedmix, uint32_t pair) {
+    // one multiply-xorshift round after the golden-ratio counter step: 6 integer ops per PAIR of dropout decisions (the two-round
+    // murmur finaliser used first was 9, and the softmax / GEGLU threads that call this are ALU-pipe bound)
     uint32_t x = pair * 0x9E3779B1u + seedmix;
-    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 16;
     return x;
 }
 __device__ __forceinline__ uint32_t seed_mix32(uint64_t seed) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA77u); }

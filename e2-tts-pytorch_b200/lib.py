@@ -94,9 +94,12 @@ def last_error():
     return load().b200_last_error().decode()
 
 
+_PLAIN = (int, float, bool, type(None))
+
+
 def _ptr(v):
-    if v is None:
-        return None
+    if v.__class__ in _PLAIN:      # scalars and NULL pass through (checked first: this runs ~13k times per training step)
+        return v
     if hasattr(v, 'data_ptr'):
         return v.data_ptr()
     return v
@@ -105,19 +108,25 @@ def _ptr(v):
 def make_args(struct_name, **kw):
     s = STRUCTS[struct_name]()
     for k, v in kw.items():
-        setattr(s, k, _ptr(v))
+        setattr(s, k, v if v.__class__ in _PLAIN else _ptr(v))
     return s
+
+
+def make_args_positional(struct_name, field_names, values):
+    """Fast path for hot call sites: `values` in header field order (checked once per call site against `field_names`)."""
+    cls = STRUCTS[struct_name]
+    if not getattr(cls, '_order_checked_' + str(len(field_names)), False):
+        declared = [f for f, _ in STRUCT_FIELDS[struct_name]][:len(field_names)]
+        if declared != list(field_names):
+            raise RuntimeError(f'{struct_name}: header field order {declared} != binding order {list(field_names)}')
+        setattr(cls, '_order_checked_' + str(len(field_names)), True)
+    return cls(*[v if v.__class__ in _PLAIN else _ptr(v) for v in values])
 
 
 def call(fn_name, *args):
     """Call a C-ABI entry point; tensors are passed as raw device pointers; raises on a non-zero code."""
     lib = load()
-    conv = []
-    for a in args:
-        if isinstance(a, ctypes.Structure):
-            conv.append(ctypes.byref(a))
-        else:
-            conv.append(_ptr(a))
+    conv = [a if a.__class__ in _PLAIN else (ctypes.byref(a) if isinstance(a, ctypes.Structure) else _ptr(a)) for a in args]
     rc = getattr(lib, fn_name)(*conv)
     if rc != 0:
         raise RuntimeError(f'{fn_name} failed (rc={rc}): {last_error()}')

@@ -37,13 +37,17 @@ def gemm(A, B, M, N, K, *, lda=None, ldb=None, A2=None, lda2=0, K1=0, a_mn=False
         ldd = n_out if out_fp32 else (n_out + 7) // 8 * 8
     if out is None:
         out = torch.empty((M, ldd), device=dev, dtype=F32 if out_fp32 else BF16)
-    args = lib.make_args(
-        'b200_gemm_args', A=A, lda=lda if lda is not None else (M if a_mn else K), A2=A2, lda2=lda2, K1=K1,
-        B=B, ldb=ldb if ldb is not None else (N if b_mn else K), M=M, N=N, K=K, a_mn_major=int(a_mn), b_mn_major=int(b_mn),
-        D=out, ldd=ldd, d_fp32=int(out_fp32), D2=D2, ldd2=ldd2, bias=bias, colscale=colscale, rows_per_batch=rows_per_batch,
-        rowmask=rowmask, resid=resid, ldr=ldr, geglu=int(geglu), dropout_p=float(dropout_p), seed=int(seed), split_k=int(split_k))
+    args = lib.make_args_positional('b200_gemm_args', _GEMM_FIELDS, (
+        A, lda if lda is not None else (M if a_mn else K), A2, lda2, K1,
+        B, ldb if ldb is not None else (N if b_mn else K), M, N, K, int(a_mn), int(b_mn),
+        out, ldd, int(out_fp32), D2, ldd2, bias, colscale, rows_per_batch,
+        rowmask, resid, ldr, int(geglu), float(dropout_p), int(seed), int(split_k)))
     lib.call('b200_gemm', args, _stream())
     return out
+
+
+_GEMM_FIELDS = ('A', 'lda', 'A2', 'lda2', 'K1', 'B', 'ldb', 'M', 'N', 'K', 'a_mn_major', 'b_mn_major', 'D', 'ldd', 'd_fp32', 'D2', 'ldd2',
+                'bias', 'colscale', 'rows_per_batch', 'rowmask', 'resid', 'ldr', 'geglu', 'dropout_p', 'seed', 'split_k')
 
 
 def _split_for(M, N, K):

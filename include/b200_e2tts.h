@@ -64,7 +64,8 @@ typedef struct {
     const void* resid; int64_t ldr;
     int32_t geglu; float dropout_p; uint64_t seed;
     int32_t split_k;
-    int32_t force_tile;   /* 0 = auto, 1 = 128 x 128 CTA tiles, 2 = 256 x 128 CTA tiles (two MMAs per k-step share one B tile) */
+    int32_t force_tile;   /* 0 = auto, 1 = 128 x 128 CTA tiles, 2 = 256 x 128 CTA tiles (two MMAs per k-step share one B tile),
+                           * 3 = CTA pair (cta_group::2): 2 x (128 x 256), each CTA stages half of the B tile; auto picks it for M >= 512, N >= 256 */
 } b200_gemm_args;
 int b200_gemm(const b200_gemm_args* a, b200_stream_t stream);
 

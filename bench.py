@@ -217,6 +217,7 @@ def run_gpu(args):
         prof['flops'] += 2.0 * M * Nn * K
         return out
 
+    step_mode, graph_note, eager_ms = 'eager', None, None
     with ClockSampler(local) as clk:
         n0 = lib.launch_count()
         ms_dev = timed(lambda: step(dev_mel, False), args.steps)
@@ -228,6 +229,26 @@ def run_gpu(args):
             step(dev_mel, False)
         torch.cuda.synchronize()
         ops.gemm = orig_gemm
+        # -- the same step through pkg.GraphedTrainStep (forward + backward captured in one CUDA graph): identical kernels and work,
+        #    no per-launch host cost. Single-GPU only (DDP's bucketed all-reduce is not captured); falls back to the eager numbers.
+        if world == 1 and not args.no_graph:
+            try:
+                eager_loss = step(dev_mel, True)
+                graphed = pkg.GraphedTrainStep(model, dev_mel, text=text_dev)
+                g_loss = float(graphed().item())
+                if not (g_loss == g_loss and 0.5 * eager_loss <= g_loss <= 2.0 * eager_loss):
+                    raise RuntimeError(f'graphed loss {g_loss} vs eager {eager_loss}')
+                for _ in range(3):
+                    graphed()
+                ms_g = timed(lambda: graphed(), args.steps)
+                ms_g_e2e = timed(lambda: graphed(host_mel).item(), args.steps)
+                if ms_g < ms_dev:
+                    eager_ms, step_mode = ms_dev, 'cuda_graph'
+                    ms_dev, ms_e2e, launches = ms_g, ms_g_e2e, graphed.launches_per_step
+                else:
+                    graph_note = f'captured but not faster ({ms_g:.2f} ms)'
+            except Exception as e:  # noqa: BLE001 - any capture problem: keep the eager measurement
+                graph_note = f'unavailable: {type(e).__name__}: {str(e)[:120]}'
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof['events'])
     if os.environ.get('B200_GEMM_BREAKDOWN') and rank == 0:
         agg = {}
@@ -257,7 +278,10 @@ def run_gpu(args):
         'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': cfg['name'], 'per_gpu_batch': B, 'seq_len': N, 'global_batch': world * B, 'parallelism': f'dp{world}',
                    'dropout': args.dropout, 'text_cond': 'on every step', 'weights': 'random init', 'optimizer_step': 'not part of the metric (fwd+bwd)',
-                   'l2': 'per-step working set (~10 GB of activations) >> 126 MB L2, no flush needed'},
+                   'l2': 'per-step working set (~10 GB of activations) >> 126 MB L2, no flush needed',
+                   'step': ('E2TTS forward + loss.backward() replayed through e2_tts_pytorch_b200.GraphedTrainStep (one CUDA graph, same kernels)'
+                            if step_mode == 'cuda_graph' else 'E2TTS forward + loss.backward(), eager launches'),
+                   **({'eager_ms_per_step': eager_ms} if eager_ms is not None else {}), **({'cuda_graph': graph_note} if graph_note else {})},
         'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': 'mel-frames/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': host_mel.numel() * 4, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'clocks': clk.summary(),
@@ -283,6 +307,7 @@ def main():
     ap.add_argument('--config', type=int, default=2, choices=[2, 3])
     ap.add_argument('--dropout', type=float, default=0.1)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time the eager step only (skip the CUDA-graph replay of the same step)')
     ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_worker:

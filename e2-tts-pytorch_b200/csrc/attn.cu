@@ -111,6 +111,7 @@ struct AttnP {
     float scale, clamp, inv_clamp, dropout_p, keep_scale;
     unsigned int drop_thresh; int drop_stride;
     unsigned long long seed;
+    const unsigned long long* seed_dev;
     // backward
     const __nv_bfloat16 *dog, *dO;
     const float* delta;
@@ -194,8 +195,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
                 l0 += p0; l1 += p1;
                 if (p.dropout_p > 0.f) {
                     const unsigned long long key = (unsigned long long)(kt * AT + nt * 8 + 2 * t + e);
-                    p0 = dropout_keep16(p.seed, drop_base0 + key, p.drop_thresh) ? p0 * p.keep_scale : 0.f;
-                    p1 = dropout_keep16(p.seed, drop_base1 + key, p.drop_thresh) ? p1 * p.keep_scale : 0.f;
+                    p0 = dropout_keep16(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull), drop_base0 + key, p.drop_thresh) ? p0 * p.keep_scale : 0.f;
+                    p1 = dropout_keep16(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull), drop_base1 + key, p.drop_thresh) ? p1 * p.keep_scale : 0.f;
                 }
                 s[nt][e] = p0; s[nt][2 + e] = p1;
             }
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnP p) {
                 float dpe = dp[nt][e];
                 if (p.dropout_p > 0.f) {
                     const unsigned long long base = (e < 2) ? drop_base0 : drop_base1;
-                    dpe = dropout_keep16(p.seed, base + (unsigned long long)key, p.drop_thresh) ? dpe * p.keep_scale : 0.f;
+                    dpe = dropout_keep16(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull), base + (unsigned long long)key, p.drop_thresh) ? dpe * p.keep_scale : 0.f;
                 }
                 s[nt][e] = pr * (dpe - dl) * (1.f - th * th) * p.scale;
             }
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnP p) {
                 float prd = pr;
                 if (p.dropout_p > 0.f) {
                     const unsigned long long idx = (bh * p.Np + (unsigned long long)qn) * (unsigned long long)p.drop_stride + (unsigned long long)((e < 2) ? key0 : key1);
-                    const bool keep = dropout_keep16(p.seed, idx, p.drop_thresh);
+                    const bool keep = dropout_keep16(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull), idx, p.drop_thresh);
                     dpe = keep ? dpe * p.keep_scale : 0.f;
                     prd = keep ? pr * p.keep_scale : 0.f;
                 }
@@ -465,7 +466,7 @@ static int fill_common(AttnP& p, int B, int H, int Np, float scale, float clamp,
     B200_REQUIRE(clamp > 0.f, "attention: softclamp value must be > 0 (reference always clamps, e2_tts.py:548-551)");
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout must be in [0,1)");
     p.B = B; p.H = H; p.Np = Np; p.scale = scale; p.clamp = clamp; p.inv_clamp = 1.f / clamp;
-    p.dropout_p = dropout_p; p.seed = seed;
+    p.dropout_p = dropout_p; p.seed = seed; p.seed_dev = seed_dev_ptr();
     p.drop_thresh = (unsigned int)(dropout_p * 65536.f);
     p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
     p.drop_stride = (Np + 1) & ~1;

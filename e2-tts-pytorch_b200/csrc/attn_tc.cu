@@ -35,6 +35,7 @@ struct AttnTcP {
     unsigned int drop_thresh;       // keep iff 16-bit hash >= thresh
     int drop_stride;                // even row pitch of the dropout counter space
     unsigned long long seed;
+    const unsigned long long* seed_dev;   // optional device addend of the seed (CUDA-graph replays)
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -191,7 +192,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int qi = q0 + row;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + part;
-        const uint32_t seedmix = seed_mix32(p.seed);
+        const uint32_t seedmix = seed_mix32(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull));
         const unsigned long long drop_row = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride;
         const float2 soc2 = make_float2(p.scale_over_clamp, p.scale_over_clamp);
         const float2 cl2 = make_float2(p.clamp * LOG2E_F, p.clamp * LOG2E_F);
@@ -319,6 +320,7 @@ struct AttnBwdTcP {
     float scale, scale_over_clamp, clamp, dropout_p, keep_scale;
     unsigned int drop_thresh; int drop_stride;
     unsigned long long seed;
+    const unsigned long long* seed_dev;   // optional device addend of the seed (CUDA-graph replays)
 };
 
 __global__ void __launch_bounds__(576, 1)
@@ -440,7 +442,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const unsigned int mbits1 = p.maskbits[(size_t)b * p.mask_words + kt * 4 + part];
         const bool all_valid = mbits1 == 0xffffffffu;
-        const uint32_t seedmix = seed_mix32(p.seed);
+        const uint32_t seedmix = seed_mix32(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull));
         const float keep_scale = p.keep_scale;
 
         float* dq_stg = reinterpret_cast<float*>(sDS + PTILE + 256) + (mw & 7) * (32 * 33);
@@ -645,7 +647,7 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     p.dropout_p = a->dropout_p;
     p.drop_thresh = (unsigned int)(a->dropout_p * 65536.f);
     p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
-    p.seed = a->seed;
+    p.seed = a->seed; p.seed_dev = seed_dev_ptr();
     p.drop_stride = (a->Np + 1) & ~1;
     CUtensorMap tq, tk, tv;
     const long long rows = (long long)a->B * a->H * a->Np;
@@ -693,7 +695,7 @@ extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) 
     p.drop_thresh = (unsigned int)(a->dropout_p * 65536.f);
     p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
     p.drop_stride = (a->Np + 1) & ~1;
-    p.seed = a->seed;
+    p.seed = a->seed; p.seed_dev = seed_dev_ptr();
     CUtensorMap tq, tk, tv, tdo;
     const long long rows = (long long)a->B * a->H * a->Np;
     if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows) || make_head_map(&tdo, a->ws_dO, rows)) return -1;

@@ -12,6 +12,10 @@ namespace b200 {
 
 extern thread_local char g_err[512];
 extern std::atomic<uint64_t> g_launches;
+// Optional device-resident addend of every dropout seed (b200_set_dropout_seed_device): lets a captured CUDA graph draw fresh
+// dropout masks on every replay — the host-side seed is a kernel argument and therefore frozen at capture time.
+extern std::atomic<const unsigned long long*> g_seed_dev;
+inline const unsigned long long* seed_dev_ptr() { return g_seed_dev.load(std::memory_order_relaxed); }
 
 #define B200_FAIL(...)                                   \
     do {                                                 \

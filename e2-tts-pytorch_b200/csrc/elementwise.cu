@@ -324,14 +324,14 @@ __global__ void __launch_bounds__(256) qkv_post_bwd_kernel(const QkvP p) {
 // projection (column sums of dug, packed order) is accumulated in the same pass (db must be zeroed by the caller).
 constexpr int GB_ROWS = 256;   // rows per block (8 row lanes x 32)
 __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh, const __nv_bfloat16* ug, __nv_bfloat16* dug, float* db, long long T,
-                                                         int inner, float dropout_p, unsigned long long seed) {
+                                                         int inner, float dropout_p, unsigned long long seed, const unsigned long long* seed_dev) {
     __shared__ float red[8][32][17];
     const int nchunk = inner >> 3;
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     const uint32_t thr = (uint32_t)(dropout_p * 65536.f);
     const float ks = dropout_p > 0.f ? 65536.f / (65536.f - (float)thr) : 1.f;
-    const uint32_t seedmix = seed_mix32(seed);
+    const uint32_t seedmix = seed_mix32(seed + (seed_dev ? __ldg(seed_dev) : 0ull));
     float su[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c < nchunk) {
         const int hcol = c * 8;
@@ -770,7 +770,7 @@ extern "C" int b200_geglu_bwd(const void* dh, const void* ug, void* dug, float* 
     B200_REQUIRE(dh && ug && dug && T > 0 && inner > 0 && (inner % 64) == 0, "geglu_bwd: inner must be a multiple of 64");
     dim3 grid((inner / 8 + 31) / 32, (unsigned)((T + GB_ROWS - 1) / GB_ROWS));
     geglu_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        (const __nv_bfloat16*)dh, (const __nv_bfloat16*)ug, (__nv_bfloat16*)dug, db_packed, T, inner, dropout_p, seed);
+        (const __nv_bfloat16*)dh, (const __nv_bfloat16*)ug, (__nv_bfloat16*)dug, db_packed, T, inner, dropout_p, seed, seed_dev_ptr());
     return check_launch("geglu_bwd_kernel");
 }
 

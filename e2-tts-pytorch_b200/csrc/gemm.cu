@@ -35,6 +35,7 @@ struct GemmParams {
     const unsigned char* rowmask;
     const void* resid; long long ldr;
     int geglu; float dropout_p; unsigned long long seed;
+    const unsigned long long* seed_dev;   // optional device addend of the seed (CUDA-graph replays)
     int atomic_out;
 };
 
@@ -454,7 +455,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (p.dropout_p > 0.f) {
                         // hidden-unit pairs (2k, 2k+1) of one row share a 32-bit hash; N/2 is even, so (row * N/2 + hcol) >> 1 pairs them
                         const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned long long)(p.N / 2) + hcol0) >> 1);
-                        const uint32_t seedmix = seed_mix32(p.seed);
+                        const uint32_t seedmix = seed_mix32(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull));
                         const uint32_t thr = (uint32_t)(p.dropout_p * 65536.f);
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
@@ -618,7 +619,7 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
     p.D2 = a->D2; p.ldd2 = a->ldd2;
     p.bias = a->bias; p.colscale = a->colscale; p.rows_per_batch = (int)(a->rows_per_batch > 0 ? a->rows_per_batch : 1);
     p.rowmask = a->rowmask; p.resid = a->resid; p.ldr = a->ldr;
-    p.geglu = a->geglu; p.dropout_p = a->dropout_p; p.seed = a->seed;
+    p.geglu = a->geglu; p.dropout_p = a->dropout_p; p.seed = a->seed; p.seed_dev = seed_dev_ptr();
     if (p.atomic_out) {
         B200_REQUIRE(a->d_fp32, "gemm: split-K requires an fp32 output");
         B200_REQUIRE(!a->bias && !a->colscale && !a->rowmask && !a->resid && !a->geglu, "gemm: split-K supports no epilogue");

@@ -69,6 +69,12 @@ typedef struct {
 } b200_gemm_args;
 int b200_gemm(const b200_gemm_args* a, b200_stream_t stream);
 
+/* Optional device-resident addend of every dropout seed (GEGLU dropout in b200_gemm / b200_geglu_bwd, attention dropout):
+ * effective seed = args.seed + *dev_seed. A captured CUDA graph freezes kernel arguments, so the per-step randomness of a graphed
+ * training step (e2_tts_pytorch_b200.GraphedTrainStep; the reference draws a fresh torch RNG state every step, trainer.py) comes from
+ * this one device word, rewritten before each replay. The pointer is sampled at launch (process-global); NULL (default) disables it. */
+int b200_set_dropout_seed_device(const uint64_t* dev_seed);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused softclamped attention, head_dim 64 (x-transformers Attend as configured by the reference: A.4
  * steps 4-5, call sites e2_tts.py:875, :911). q,k,v,o: bf16 [B,H,Np,64]; keymask: u8 [B,Np] (1 = keep) or

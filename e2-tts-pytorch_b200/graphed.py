@@ -50,6 +50,9 @@ class GraphedTrainStep:
         finally:
             lib.call('b200_set_dropout_seed_device', None)
         self.launches_per_step = lib.launch_count() - n0   # kernel nodes of ours in the graph (they all run on every replay)
+        # the gradient tensors the graph writes into: re-attached after every replay in case the training loop dropped them
+        # (optimizer.zero_grad(set_to_none=True)); each replay OVERWRITES them, exactly like backward() into empty .grad fields
+        self._grads = [(p, p.grad) for p in self.model.parameters() if p.grad is not None]
 
     def _eager(self):
         out = self.model(self.mel, text=self.text, lens=self.lens)
@@ -71,4 +74,7 @@ class GraphedTrainStep:
         self._seed_host.random_(0, 2 ** 62)
         self._seed_dev.copy_(self._seed_host, non_blocking=True)
         self.graph.replay()
+        for p, g in self._grads:
+            if p.grad is not g:
+                p.grad = g
         return self.out.loss

@@ -162,6 +162,9 @@ def run_gpu(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    graph_ddp = world > 1 and args.graph_ddp
+    if graph_ddp:   # EXPERIMENTAL (off by default, not yet validated on hardware): capture the DDP step, NCCL all-reduce included
+        os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')   # the watchdog's event queries would invalidate the capture
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(0)
@@ -170,7 +173,14 @@ def run_gpu(args):
     model.cond_drop_prob = 0.0  # text conditioning on every step: the expensive branch, identical graph on every rank
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        if graph_ddp:   # PyTorch's recipe for whole-backward capture under DDP: construct DDP on a side stream
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+            torch.cuda.current_stream(dev).wait_stream(side)
+        else:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     B, N = cfg['batch'], cfg['seq']
     torch.manual_seed(rank)
     host_mel = torch.randn(B, N, 100).pin_memory()
@@ -231,10 +241,10 @@ def run_gpu(args):
         ops.gemm = orig_gemm
         # -- the same step through pkg.GraphedTrainStep (forward + backward captured in one CUDA graph): identical kernels and work,
         #    no per-launch host cost. Single-GPU only (DDP's bucketed all-reduce is not captured); falls back to the eager numbers.
-        if world == 1 and not args.no_graph:
+        if (world == 1 and not args.no_graph) or graph_ddp:
             try:
                 eager_loss = step(dev_mel, True)
-                graphed = pkg.GraphedTrainStep(model, dev_mel, text=text_dev)
+                graphed = pkg.GraphedTrainStep(net, dev_mel, text=text_dev, warmup=11 if world > 1 else 3)
                 g_loss = float(graphed().item())
                 if not (g_loss == g_loss and 0.5 * eager_loss <= g_loss <= 2.0 * eager_loss):
                     raise RuntimeError(f'graphed loss {g_loss} vs eager {eager_loss}')
@@ -308,6 +318,7 @@ def main():
     ap.add_argument('--dropout', type=float, default=0.1)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time the eager step only (skip the CUDA-graph replay of the same step)')
+    ap.add_argument('--graph-ddp', action='store_true', help='EXPERIMENTAL: also capture the N > 1 DDP step (NCCL all-reduce inside the graph)')
     ap.add_argument('--cpu-worker', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_worker:

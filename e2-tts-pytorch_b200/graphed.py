@@ -21,14 +21,15 @@ from . import lib
 
 class GraphedTrainStep:
     def __init__(self, model, mel, *, text=None, lens=None, warmup=3):
-        if model.training and 0.0 < float(model.cond_drop_prob) < 1.0:
+        inner = getattr(model, 'module', model)   # a DistributedDataParallel wrapper is called as is; its attributes live on .module
+        if inner.training and 0.0 < float(inner.cond_drop_prob) < 1.0:
             raise ValueError('GraphedTrainStep: cond_drop_prob must be 0 or 1 (the text-drop branch is decided on the host)')
         if not mel.is_cuda:
             raise ValueError('GraphedTrainStep: inputs must live on the GPU')
         self.model = model
         dev = mel.device
         self.mel = mel.clone()
-        self.text = text.clone() if torch.is_tensor(text) else (model.tokenizer(text).to(dev) if isinstance(text, list) else None)
+        self.text = text.clone() if torch.is_tensor(text) else (inner.tokenizer(text).to(dev) if isinstance(text, list) else None)
         self.lens = lens.clone() if torch.is_tensor(lens) else None
         self._seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)

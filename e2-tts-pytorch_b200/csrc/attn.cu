@@ -7,8 +7,9 @@
 // m16n8k16 tensor-core tiles fed by cp.async double-buffered, XOR-swizzled shared memory.
 // Backward = recompute: a per-row prep kernel (dO = dOg*gate, delta = <dO,O>, d_gate), a dQ kernel
 // (query-stationary) and a dK/dV kernel (key-stationary), including the (1 - tanh^2) softclamp factor.
-// NOTE: this round's attention uses the legacy mma.sync tensor path; the tcgen05/TMEM port
-// is the next optimisation step. The GEMMs (gemm.cu) are tcgen05.
+// NOTE: these mma.sync kernels were the bring-up path. The product path is the tcgen05/TMEM kernels in attn_tc.cu;
+// the entry points here are `*_legacy`: cross-checks for the tests, and the online-softmax fallback of b200_attn_fwd for
+// softclamp values > 64 (the tcgen05 forward exponentiates without a running maximum). attn_bwd_prep_kernel is shared.
 #include "common.cuh"
 #include "ptx.cuh"
 

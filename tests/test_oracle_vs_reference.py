@@ -35,3 +35,87 @@ def test_melspec_vs_torchaudio():
     ref = load_reference()
     wave = torch.randn(1, 256 * 10 + 17)
     assert (ref.MelSpec()(wave) - O.melspec(wave)).abs().max() < 1e-3
+
+
+def test_text_dropped_branch_vs_reference():
+    """cond_drop (e2_tts.py:1530-1534, :1263-1264): the text stream is skipped, its parameters receive no gradient."""
+    ref = load_reference()
+    torch.manual_seed(21)
+    kw = dict(dim=128, depth=2, heads=4)
+    model = ref.E2TTS(transformer=dict(dropout=0., max_seq_len=128, **kw), use_vocos=False)
+    model.load_state_dict(O.randomize_zero_init(model.state_dict(), seed=21))
+    mel = torch.randn(3, 64, 100)
+    lens_t = torch.tensor([64, 40, 17])
+    text = ['one', 'two words', '']
+    out, rec = run_reference_forward(ref, model, mel, text, lens=lens_t, drop_text_cond=True)
+    out.loss.backward()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    o = O.e2tts_forward(sd, O.TransformerCfg(**kw), mel, O.list_str_to_tensor(text), lens=lens_t, drop_text_cond=True, **rec)
+    o['loss'].backward()
+    assert abs(float(o['loss']) - float(out.loss)) <= 1e-5 * abs(float(out.loss))
+    assert rel_l2(o['pred'], out.pred_flow) < 1e-4
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+        else:
+            assert (p.grad - sd[k].grad).abs().max() <= 2e-4 * p.grad.abs().max() + 1e-7, k
+
+
+@pytest.mark.parametrize('steps,cfg_strength,duration', [(4, 1.0, 48), (3, 0.0, 40), (5, 2.5, [50, 37])])
+def test_sample_vs_reference(steps, cfg_strength, duration):
+    """E2TTS.sample (:1332-1466): midpoint grid, CFG with the APG orthogonal projection (:1303-1330, :113-124), the
+    cond mask / duration logic (:1376-1405) — same y0 injected into the oracle."""
+    ref = load_reference()
+    torch.manual_seed(31)
+    kw = dict(dim=128, depth=2, heads=2)
+    model = ref.E2TTS(transformer=dict(dropout=0., max_seq_len=128, **kw), use_vocos=False)
+    model.load_state_dict(O.randomize_zero_init(model.state_dict(), seed=31))
+    model.eval()
+    cond = torch.randn(2, 20, 100)
+    text = ['Hello', 'Goodbye then']
+    dur = torch.tensor(duration) if isinstance(duration, list) else duration
+    holder = {}
+
+    class Rec:
+        def __getattr__(self, n):
+            return getattr(torch, n)
+
+        def randn_like(self, *a, **k):
+            holder['y0'] = torch.randn_like(*a, **k)
+            return holder['y0'].clone()
+
+    ref.torch = Rec()
+    try:
+        with torch.no_grad():
+            want = model.sample(cond, text=text, duration=dur, steps=steps, cfg_strength=cfg_strength, return_raw_output=True)
+    finally:
+        ref.torch = torch
+    with torch.no_grad():
+        got = O.e2tts_sample(model.state_dict(), O.TransformerCfg(**kw), cond, O.list_str_to_tensor(text), duration=dur, y0=holder['y0'],
+                             steps=steps, cfg_strength=cfg_strength)
+    assert got.shape == want.shape
+    assert rel_l2(got, want) < 1e-4
+
+
+def test_duration_predictor_vs_reference():
+    """DurationPredictor.forward (:1042-1113): random prefix mask, masked mean pool, softplus head, L1-on-frames loss."""
+    ref = load_reference()
+    torch.manual_seed(41)
+    kw = dict(dim=128, depth=2, heads=2)
+    dp = ref.DurationPredictor(transformer=dict(dropout=0., max_seq_len=128, **kw))
+    dp.load_state_dict(O.randomize_zero_init(dp.state_dict(), seed=41))
+    mel = torch.randn(3, 72, 100)
+    lens_t = torch.tensor([72, 50, 31])
+    text = ['abc', 'hello world', 'x']
+    torch.manual_seed(5)
+    loss = dp(mel, text=text, lens=lens_t)
+    loss.backward()
+    torch.manual_seed(5)
+    rand_frac = mel.new_zeros(3).uniform_(0, 1)   # the draw of e2_tts.py:1082 under the same seed
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in dp.state_dict().items()}
+    got = O.duration_forward(sd, O.TransformerCfg(cond_on_time=False, **kw), mel, O.list_str_to_tensor(text), lens=lens_t, rand_frac=rand_frac)
+    assert abs(float(got) - float(loss)) <= 1e-4 * abs(float(loss))
+    got.backward()
+    for k, p in dp.named_parameters():
+        if p.grad is not None:
+            assert (p.grad - sd[k].grad).abs().max() <= 5e-4 * p.grad.abs().max() + 1e-6, k

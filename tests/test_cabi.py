@@ -69,3 +69,28 @@ def test_tokenizer_and_mask_helpers(pkg):
     assert pkg.lens_to_mask(torch.tensor([2, 3]), 3).tolist() == [[True, True, False], [True, True, True]]
     m = pkg.mask_from_frac_lengths(torch.tensor([10, 6]), torch.tensor([0.7, 1.0]), 10)
     assert m.sum(-1).tolist() == [7, 6] and not m[1, 6:].any()
+
+
+def test_graphed_train_step_validates_its_arguments(pkg):
+    """GraphedTrainStep (CUDA-graph replay of forward + backward) refuses what it cannot capture — checked without a GPU."""
+    import pytest
+    import torch
+    m = pkg.E2TTS(transformer=dict(dim=128, depth=2, heads=2), use_vocos=False)
+    m.cond_drop_prob = 0.0
+    with pytest.raises(ValueError, match='GPU'):
+        pkg.GraphedTrainStep(m, torch.randn(2, 32, 100))
+    m.cond_drop_prob = 0.25   # the text-drop coin is a host-side branch: it would be frozen into the graph
+    with pytest.raises(ValueError, match='cond_drop_prob'):
+        pkg.GraphedTrainStep(m, torch.randn(2, 32, 100))
+
+
+def test_positional_struct_marshalling_checks_the_header_order(pkg):
+    """ops.gemm fills b200_gemm_args positionally (hot path): the binding verifies the order against the parsed header."""
+    import pytest
+    from e2_tts_pytorch_b200 import lib, ops
+    declared = [f for f, _ in lib.STRUCT_FIELDS['b200_gemm_args']]
+    assert tuple(declared[:len(ops._GEMM_FIELDS)]) == ops._GEMM_FIELDS
+    s = lib.make_args_positional('b200_gemm_args', ops._GEMM_FIELDS, [None, 8] + [0] * (len(ops._GEMM_FIELDS) - 2))
+    assert s.lda == 8 and s.force_tile == 0
+    with pytest.raises(RuntimeError, match='field order'):
+        lib.make_args_positional('b200_gemm_args', ('lda', 'A'), (8, None))

@@ -123,6 +123,7 @@ struct AttnP {
 
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ __align__(128) uint8_t sm[];
     const uint32_t sQ = smem_u32(sm), sK = sQ + TILE_B, sV = sK + 2 * TILE_B;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnP p) {
 // ------------------------------------------------------------------------------------------------ backward prep
 // one 8-lane group per (b, h, n): dO = dOg * gate, d_gate = <dOg, O>, delta = gate * d_gate
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const AttnP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const long long gidx = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long rowid = gidx >> 3;
     const int c = (int)(gidx & 7);
@@ -275,6 +277,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const AttnP p) {
 // shared logic: recompute clamped logits / probabilities for a 16x64 accumulator block
 // ------------------------------------------------------------------------------------------------ dQ
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ __align__(128) uint8_t sm[];
     const uint32_t sQ = smem_u32(sm), sDO = sQ + TILE_B, sK = sDO + TILE_B, sV = sK + 2 * TILE_B;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -359,6 +362,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnP p) {
 
 // ------------------------------------------------------------------------------------------------ dK, dV
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ __align__(128) uint8_t sm[];
     const uint32_t sK = smem_u32(sm), sV = sK + TILE_B, sQ = sV + TILE_B, sDO = sQ + 2 * TILE_B;
     float* s_lse = reinterpret_cast<float*>(sm + 6 * TILE_B);   // [2][64]
@@ -488,7 +492,7 @@ extern "C" int b200_attn_fwd_legacy(const b200_attn_fwd_args* a, b200_stream_t s
     p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
     p.keymask = a->keymask; p.gate = a->gate; p.o = (__nv_bfloat16*)a->o; p.og = (__nv_bfloat16*)a->og; p.lse = a->lse;
     dim3 grid((a->Np + AT - 1) / AT, a->H, a->B);
-    attn_fwd_kernel<<<grid, 128, 5 * TILE_B, st>>>(p);
+    B200_LAUNCH(attn_fwd_kernel, grid, 128, 5 * TILE_B, st, p);
     return check_launch("attn_fwd_kernel");
 }
 
@@ -499,7 +503,7 @@ int launch_attn_bwd_prep(const b200_attn_bwd_args* a, cudaStream_t st) {
     p.gate = a->gate; p.o = (__nv_bfloat16*)a->o; p.dog = (const __nv_bfloat16*)a->d_og; p.dO_out = (__nv_bfloat16*)a->ws_dO;
     p.delta_out = a->ws_delta; p.dgate = a->d_gate;
     const long long rows = (long long)a->B * a->H * a->Np;
-    attn_bwd_prep_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(p);
+    B200_LAUNCH(attn_bwd_prep_kernel, (unsigned)((rows * 8 + 255) / 256), 256, 0, st, p);
     return check_launch("attn_bwd_prep_kernel");
 }
 }  // namespace b200
@@ -517,7 +521,7 @@ extern "C" int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t s
     p.dO = (const __nv_bfloat16*)a->ws_dO; p.delta = a->ws_delta;
     p.dq = (__nv_bfloat16*)a->dq; p.dk = (__nv_bfloat16*)a->dk; p.dv = (__nv_bfloat16*)a->dv;
     const long long rows = (long long)a->B * a->H * a->Np;
-    attn_bwd_prep_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(p);
+    B200_LAUNCH(attn_bwd_prep_kernel, (unsigned)((rows * 8 + 255) / 256), 256, 0, st, p);
     if (int rc = check_launch("attn_bwd_prep_kernel")) return rc;
     dim3 grid((a->Np + AT - 1) / AT, a->H, a->B);
     static bool configured = false;
@@ -526,8 +530,8 @@ extern "C" int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t s
         cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_B);
         configured = true;
     }
-    attn_bwd_dq_kernel<<<grid, 128, 6 * TILE_B, st>>>(p);
+    B200_LAUNCH(attn_bwd_dq_kernel, grid, 128, 6 * TILE_B, st, p);
     if (int rc = check_launch("attn_bwd_dq_kernel")) return rc;
-    attn_bwd_dkv_kernel<<<grid, 128, 6 * TILE_B + 1024, st>>>(p);
+    B200_LAUNCH(attn_bwd_dkv_kernel, grid, 128, 6 * TILE_B + 1024, st, p);
     return check_launch("attn_bwd_dkv_kernel");
 }

@@ -70,6 +70,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 // key-validity bitmask: bit (n % 32) of word n / 32 is set iff key n participates (n < Np and mask[b, n] != 0)
 __global__ void attn_maskbits_kernel(const unsigned char* mask, unsigned int* bits, int B, int Np, int words) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= B * words) return;
     const int b = w / words, w0 = (w % words) * 32;
@@ -128,6 +129,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tS = tmem_base, tO = tmem_base + 256;   // S[2] at +0/+128, O at +256 (64 columns, accumulated over all key tiles)
+    pdl_wait();   // prologue above overlaps the previous kernel's tail (ptx.cuh)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -143,6 +145,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_arrive_expect_tx(&v_full[st], TILE16);
                 tma_load_2d(sV + st * TILE16, &tmV, &v_full[st], 0, row_base + j * TKV);
             }
+            pdl_launch_dependents();
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -366,6 +369,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
+    pdl_wait();   // prologue above overlaps the previous kernel's tail (ptx.cuh)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -381,6 +385,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tma_load_2d(sQ + st * TILE16, &tmQ, &qdo_full[st], 0, row_base + qt_i * TQ);
                 tma_load_2d(sDO + st * TILE16, &tmDO, &qdo_full[st], 0, row_base + qt_i * TQ);
             }
+            pdl_launch_dependents();
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -638,7 +643,7 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     p.maskbits = reinterpret_cast<const unsigned int*>(a->ws_maskbits);
     {
         const int total = a->B * p.mask_words;
-        attn_maskbits_kernel<<<(total + 127) / 128, 128, 0, st>>>(a->keymask, reinterpret_cast<unsigned int*>(a->ws_maskbits), a->B, a->Np, p.mask_words);
+        B200_LAUNCH(attn_maskbits_kernel, (total + 127) / 128, 128, 0, st, a->keymask, reinterpret_cast<unsigned int*>(a->ws_maskbits), a->B, a->Np, p.mask_words);
         if (int rc = check_launch("attn_maskbits_kernel")) return rc;
     }
     p.gate = a->gate; p.o = (__nv_bfloat16*)a->o; p.og = (__nv_bfloat16*)a->og; p.lse = a->lse;
@@ -660,7 +665,7 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
         configured = true;
     }
     dim3 grid((a->Np + TQ - 1) / TQ, a->H, a->B);
-    attn_fwd_tc_kernel<<<grid, 576, smem, st>>>(tq, tk, tv, p);
+    B200_LAUNCH(attn_fwd_tc_kernel, grid, 576, smem, st, tq, tk, tv, p);
     return check_launch("attn_fwd_tc_kernel");
 }
 
@@ -681,7 +686,7 @@ extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) 
     p.maskbits = reinterpret_cast<const unsigned int*>(a->ws_maskbits);
     {
         const int total = a->B * p.mask_words;
-        attn_maskbits_kernel<<<(total + 127) / 128, 128, 0, st>>>(a->keymask, reinterpret_cast<unsigned int*>(a->ws_maskbits), a->B, a->Np, p.mask_words);
+        B200_LAUNCH(attn_maskbits_kernel, (total + 127) / 128, 128, 0, st, a->keymask, reinterpret_cast<unsigned int*>(a->ws_maskbits), a->B, a->Np, p.mask_words);
         if (int rc = check_launch("attn_maskbits_kernel")) return rc;
     }
     const size_t nelem = (size_t)a->B * a->H * a->Np * DH;
@@ -707,6 +712,6 @@ extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) 
         configured = true;
     }
     dim3 grid(p.nq, a->H, a->B);
-    attn_bwd_tc_kernel<<<grid, 576, smem, st>>>(tq, tk, tv, tdo, p);
+    B200_LAUNCH(attn_bwd_tc_kernel, grid, 576, smem, st, tq, tk, tv, tdo, p);
     return check_launch("attn_bwd_tc_kernel");
 }

@@ -30,6 +30,7 @@ __device__ __forceinline__ int pack_row(const b200_pack_desc& d, int r) {
     return r < inner ? (r >> 6) * 128 + (r & 63) : ((r - inner) >> 6) * 128 + 64 + ((r - inner) & 63);
 }
 __global__ void __launch_bounds__(256) pack_weights_kernel(const b200_pack_desc* descs) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const b200_pack_desc d = descs[blockIdx.y];
     if ((d.cols & 3) || (d.col_off & 3) || (d.ld_dst & 3)) {  // scalar path (1-D biases, odd widths)
         const long long total = (long long)d.rows * d.cols;
@@ -63,6 +64,7 @@ struct StemP {
     int B, N, C, Cp;
 };
 __global__ void __launch_bounds__(256) stem_prepare_kernel(const StemP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const long long total = (long long)p.B * p.N * p.Cp * 2;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int col = (int)(i % (2 * p.Cp));
@@ -100,6 +102,7 @@ struct AsmP {
     float *d_tok, *d_abs_pos, *d_registers;
 };
 __global__ void __launch_bounds__(256) assemble_fwd_kernel(const AsmP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int nchunk = p.D >> 3;
     const long long total = (long long)p.B * (p.R + p.N) * nchunk;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(256) assemble_fwd_kernel(const AsmP p) {
 }
 // thread per (position, chunk): loops over batch; sums the S stream gradients
 __global__ void __launch_bounds__(256) assemble_bwd_kernel(const AsmP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int nchunk = p.D >> 3;
     const long long total = (long long)(p.R + p.N) * nchunk;
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(256) assemble_bwd_kernel(const AsmP p) {
 // embedding gradient: grid (vocab row, token slab); a block scans its slab for its id and adds its partial row
 // (the hot filler id 0 is spread over all slabs instead of one serial block). d_emb is zeroed by the host wrapper.
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* d_tok, const int* ids, float* d_emb, int ntok, int D, int slab) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int v = blockIdx.x;
     const int t0 = blockIdx.y * slab, t1 = min(ntok, t0 + slab);
     __shared__ int hits[256];
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* d_tok, cons
 
 // ------------------------------------------------------------------------------------------------ rotary table
 __global__ void rotary_table_kernel(float* cs, float* sn, int Np, int half) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Np * half) return;
     const int n = i / half, j = i % half;
@@ -218,6 +224,7 @@ struct QkvP {
     int dq_fp32;
 };
 __global__ void __launch_bounds__(256) qkv_post_fwd_kernel(const QkvP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const long long total = (long long)p.B * p.Np * p.H * 8;
     const int I = p.H * 64;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -252,6 +259,7 @@ __global__ void __launch_bounds__(256) qkv_post_fwd_kernel(const QkvP p) {
     }
 }
 __global__ void __launch_bounds__(256) qkv_post_bwd_kernel(const QkvP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const long long total = (long long)p.B * p.Np * p.H * 8;
     const int I = p.H * 64;
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -325,6 +333,7 @@ __global__ void __launch_bounds__(256) qkv_post_bwd_kernel(const QkvP p) {
 constexpr int GB_ROWS = 256;   // rows per block (8 row lanes x 32)
 __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh, const __nv_bfloat16* ug, __nv_bfloat16* dug, float* db, long long T,
                                                          int inner, float dropout_p, unsigned long long seed, const unsigned long long* seed_dev) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     __shared__ float red[8][32][17];
     const int nchunk = inner >> 3;
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -393,6 +402,7 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh,
 template <int CL>
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ X, long long T, int ncols, int ld,
                                                      float* __restrict__ out, int rows_per_block) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     constexpr int RL = 256 / CL;
     __shared__ float red[8][CL * 8];
     const int cg = threadIdx.x % CL, rl = threadIdx.x / CL;
@@ -452,6 +462,7 @@ struct FnP {
 };
 template <int VPT>
 __global__ void __launch_bounds__(256) final_norm_fwd_kernel(const FnP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int lane = threadIdx.x & 31, nchunk = p.D >> 3;
     const long long ntok = (long long)p.B * p.N;
     for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < ntok; row += (long long)gridDim.x * 8) {
@@ -490,6 +501,7 @@ __global__ void __launch_bounds__(256) final_norm_fwd_kernel(const FnP p) {
 }
 template <int VPT>
 __global__ void __launch_bounds__(256) final_norm_bwd_kernel(const FnP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float sg[];  // [D]
     for (int i = threadIdx.x; i < p.D; i += 256) sg[i] = 0.f;
     __syncthreads();
@@ -555,6 +567,7 @@ struct LossP {
     const float* dloss; __nv_bfloat16* dpred; int ldp;
 };
 __global__ void __launch_bounds__(256) flow_loss_fwd_kernel(const LossP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     float acc = 0.f, cnt = 0.f;
     const long long total = p.rows * p.C;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -578,8 +591,12 @@ __global__ void __launch_bounds__(256) flow_loss_fwd_kernel(const LossP p) {
         atomicAdd(p.sums + 1, c);
     }
 }
-__global__ void flow_loss_finalize_kernel(const float* sums, float* loss, int C) { *loss = sums[0] / (sums[1] * (float)C); }
+__global__ void flow_loss_finalize_kernel(const float* sums, float* loss, int C) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
+    *loss = sums[0] / (sums[1] * (float)C);
+}
 __global__ void __launch_bounds__(256) flow_loss_bwd_kernel(const LossP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const float scale = 2.f * (*p.dloss) / (p.sums[1] * (float)p.C);
     const long long total = p.rows * p.ldp;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -603,6 +620,7 @@ __global__ void __launch_bounds__(256) rowgate_bwd_kernel(const __nv_bfloat16* _
                                                            const float* __restrict__ cs, const unsigned char* __restrict__ mask,
                                                            __nv_bfloat16* __restrict__ dz, float* __restrict__ d_cs,
                                                            float* __restrict__ d_bias, int rows_per_batch, int D, int rows_per_block) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float sacc[];  // [D] gate sums, then [D] bias sums
     float* sbias = sacc + D;
     const int b = blockIdx.y;
@@ -667,6 +685,7 @@ __global__ void __launch_bounds__(256) rowgate_bwd_kernel(const __nv_bfloat16* _
 
 // fp32 -> bf16 cast with row pitch (used for small host-provided matrices)
 __global__ void cast_rows_kernel(const float* src, __nv_bfloat16* dst, long long rows, int cols, int ld) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const long long total = rows * ld;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int c = (int)(i % ld);
@@ -686,7 +705,7 @@ using namespace b200;
 
 extern "C" int b200_pack_weights(const b200_pack_desc* descs_dev, int32_t n, b200_stream_t stream) {
     B200_REQUIRE(descs_dev && n > 0, "pack_weights: empty table");
-    pack_weights_kernel<<<dim3(32, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(descs_dev);
+    B200_LAUNCH(pack_weights_kernel, dim3(32, n), 256, 0, reinterpret_cast<cudaStream_t>(stream), descs_dev);
     return check_launch("pack_weights_kernel");
 }
 
@@ -694,7 +713,7 @@ extern "C" int b200_stem_prepare(const b200_stem_args* a, b200_stream_t stream) 
     B200_REQUIRE(a && a->A && ((a->x1 && a->x0 && a->times && a->span) || (a->x_in && a->cond_in)), "stem_prepare: null pointer");
     B200_REQUIRE(a->C > 0 && a->Cp >= a->C && (a->Cp % 64) == 0, "stem_prepare: Cp must be a multiple of 64 >= C");
     StemP p{a->x1, a->x0, a->times, a->x_in, a->cond_in, a->span, (__nv_bfloat16*)a->A, a->cond_out, a->B, a->N, a->C, a->Cp};
-    stem_prepare_kernel<<<grid_for((long long)a->B * a->N * a->Cp * 2), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    B200_LAUNCH(stem_prepare_kernel, grid_for((long long)a->B * a->N * a->Cp * 2), 256, 0, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("stem_prepare_kernel");
 }
 
@@ -710,7 +729,7 @@ extern "C" int b200_assemble_fwd(const b200_assemble_args* a, b200_stream_t stre
     if (fill_asm(p, a)) return -1;
     B200_REQUIRE(a->out, "assemble_fwd: null output");
     p.out = (__nv_bfloat16*)a->out;
-    assemble_fwd_kernel<<<grid_for((long long)a->B * (a->R + a->N) * (a->D / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    B200_LAUNCH(assemble_fwd_kernel, grid_for((long long)a->B * (a->R + a->N) * (a->D / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("assemble_fwd_kernel");
 }
 extern "C" int b200_assemble_bwd(const b200_assemble_args* a, b200_stream_t stream) {
@@ -719,7 +738,7 @@ extern "C" int b200_assemble_bwd(const b200_assemble_args* a, b200_stream_t stre
     B200_REQUIRE(a->d_out, "assemble_bwd: null d_out");
     p.d_out = (const __nv_bfloat16*)a->d_out; p.d_h = (__nv_bfloat16*)a->d_h; p.d_tok = a->d_tok; p.d_abs_pos = a->d_abs_pos; p.d_registers = a->d_registers;
     const long long total = (long long)(a->R + a->N) * (a->D / 8);
-    assemble_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    B200_LAUNCH(assemble_bwd_kernel, (unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("assemble_bwd_kernel");
 }
 extern "C" int b200_embed_bwd(const float* d_tok, const int32_t* ids, float* d_emb, int32_t ntok, int32_t D, int32_t vocab, b200_stream_t stream) {
@@ -728,12 +747,12 @@ extern "C" int b200_embed_bwd(const float* d_tok, const int32_t* ids, float* d_e
     cudaError_t e = cudaMemsetAsync(d_emb, 0, (size_t)vocab * D * sizeof(float), st);
     B200_REQUIRE(e == cudaSuccess, "embed_bwd: memset: %s", cudaGetErrorString(e));
     const int slab = 1024;
-    embed_bwd_kernel<<<dim3(vocab, (ntok + slab - 1) / slab), 256, 0, st>>>(d_tok, ids, d_emb, ntok, D, slab);
+    B200_LAUNCH(embed_bwd_kernel, dim3(vocab, (ntok + slab - 1) / slab), 256, 0, st, d_tok, ids, d_emb, ntok, D, slab);
     return check_launch("embed_bwd_kernel");
 }
 extern "C" int b200_rotary_table(float* cos_out, float* sin_out, int32_t Np, int32_t dim_head, b200_stream_t stream) {
     B200_REQUIRE(cos_out && sin_out && Np > 0 && dim_head == 64, "rotary_table: only dim_head 64 is built");
-    rotary_table_kernel<<<(Np * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cos_out, sin_out, Np, 32);
+    B200_LAUNCH(rotary_table_kernel, (Np * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream), cos_out, sin_out, Np, 32);
     return check_launch("rotary_table_kernel");
 }
 
@@ -751,7 +770,7 @@ extern "C" int b200_qkv_post_fwd(const b200_qkv_post_args* a, b200_stream_t stre
     if (fill_qkv(p, a)) return -1;
     B200_REQUIRE(a->q && a->k && a->v, "qkv_post_fwd: null output");
     p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
-    qkv_post_fwd_kernel<<<grid_for((long long)a->B * a->Np * a->H * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    B200_LAUNCH(qkv_post_fwd_kernel, grid_for((long long)a->B * a->Np * a->H * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("qkv_post_fwd_kernel");
 }
 extern "C" int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stream) {
@@ -761,7 +780,7 @@ extern "C" int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stre
     p.dq = (const __nv_bfloat16*)a->dq; p.dk = (const __nv_bfloat16*)a->dk; p.dv = (const __nv_bfloat16*)a->dv; p.d_gate = a->d_gate;
     p.d_qkvg = (__nv_bfloat16*)a->d_qkvg; p.d_vfirst = (__nv_bfloat16*)a->d_vfirst; p.dq_fp32 = a->dq_fp32; p.dv_extra = (const __nv_bfloat16*)a->dv_extra;
     const long long total = (long long)a->B * a->Np * a->H * 8;
-    qkv_post_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    B200_LAUNCH(qkv_post_bwd_kernel, (unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("qkv_post_bwd_kernel");
 }
 
@@ -769,7 +788,7 @@ extern "C" int b200_geglu_bwd(const void* dh, const void* ug, void* dug, float* 
                               b200_stream_t stream) {
     B200_REQUIRE(dh && ug && dug && T > 0 && inner > 0 && (inner % 64) == 0, "geglu_bwd: inner must be a multiple of 64");
     dim3 grid((inner / 8 + 31) / 32, (unsigned)((T + GB_ROWS - 1) / GB_ROWS));
-    geglu_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH(geglu_bwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
         (const __nv_bfloat16*)dh, (const __nv_bfloat16*)ug, (__nv_bfloat16*)dug, db_packed, T, inner, dropout_p, seed, seed_dev_ptr());
     return check_launch("geglu_bwd_kernel");
 }
@@ -790,11 +809,11 @@ extern "C" int b200_colsum(const void* X, int64_t T, int32_t ncols, int32_t ld, 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const __nv_bfloat16* x = (const __nv_bfloat16*)X;
     switch (cl) {
-        case 32: colsum_kernel<32><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
-        case 16: colsum_kernel<16><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
-        case 8: colsum_kernel<8><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
-        case 4: colsum_kernel<4><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
-        default: colsum_kernel<2><<<grid, 256, 0, st>>>(x, T, ncols, ld, out, (int)rows_per_block); break;
+        case 32: B200_LAUNCH(colsum_kernel<32>, grid, 256, 0, st, x, T, ncols, ld, out, (int)rows_per_block); break;
+        case 16: B200_LAUNCH(colsum_kernel<16>, grid, 256, 0, st, x, T, ncols, ld, out, (int)rows_per_block); break;
+        case 8: B200_LAUNCH(colsum_kernel<8>, grid, 256, 0, st, x, T, ncols, ld, out, (int)rows_per_block); break;
+        case 4: B200_LAUNCH(colsum_kernel<4>, grid, 256, 0, st, x, T, ncols, ld, out, (int)rows_per_block); break;
+        default: B200_LAUNCH(colsum_kernel<2>, grid, 256, 0, st, x, T, ncols, ld, out, (int)rows_per_block); break;
     }
     return check_launch("colsum_kernel");
 }
@@ -805,9 +824,9 @@ extern "C" int b200_final_norm_fwd(const b200_final_norm_args* a, b200_stream_t 
     FnP p{(const __nv_bfloat16*)a->xres, a->g, (__nv_bfloat16*)a->y, a->B, a->N, a->R, a->D, a->S, nullptr, nullptr, nullptr};
     const int grid = (int)min(((long long)a->B * a->N + 7) / 8, (long long)num_sms() * 8);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (a->D <= 256) final_norm_fwd_kernel<1><<<grid, 256, 0, st>>>(p);
-    else if (a->D <= 512) final_norm_fwd_kernel<2><<<grid, 256, 0, st>>>(p);
-    else final_norm_fwd_kernel<4><<<grid, 256, 0, st>>>(p);
+    if (a->D <= 256) B200_LAUNCH(final_norm_fwd_kernel<1>, grid, 256, 0, st, p);
+    else if (a->D <= 512) B200_LAUNCH(final_norm_fwd_kernel<2>, grid, 256, 0, st, p);
+    else B200_LAUNCH(final_norm_fwd_kernel<4>, grid, 256, 0, st, p);
     return check_launch("final_norm_fwd_kernel");
 }
 extern "C" int b200_final_norm_bwd(const b200_final_norm_args* a, b200_stream_t stream) {
@@ -817,9 +836,9 @@ extern "C" int b200_final_norm_bwd(const b200_final_norm_args* a, b200_stream_t 
     const int grid = (int)min(((long long)a->B * (a->N + a->R) + 7) / 8, (long long)num_sms() * 4);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t smem = (size_t)a->D * 4;
-    if (a->D <= 256) final_norm_bwd_kernel<1><<<grid, 256, smem, st>>>(p);
-    else if (a->D <= 512) final_norm_bwd_kernel<2><<<grid, 256, smem, st>>>(p);
-    else final_norm_bwd_kernel<4><<<grid, 256, smem, st>>>(p);
+    if (a->D <= 256) B200_LAUNCH(final_norm_bwd_kernel<1>, grid, 256, smem, st, p);
+    else if (a->D <= 512) B200_LAUNCH(final_norm_bwd_kernel<2>, grid, 256, smem, st, p);
+    else B200_LAUNCH(final_norm_bwd_kernel<4>, grid, 256, smem, st, p);
     return check_launch("final_norm_bwd_kernel");
 }
 
@@ -829,15 +848,15 @@ extern "C" int b200_flow_loss_fwd(const b200_flow_loss_args* a, b200_stream_t st
     cudaError_t e = cudaMemsetAsync(a->sums, 0, 2 * sizeof(float), st);
     B200_REQUIRE(e == cudaSuccess, "flow_loss_fwd: memset: %s", cudaGetErrorString(e));
     LossP p{a->pred, a->x1, a->x0, a->span, a->sums, a->pred_data, a->rows, a->C, nullptr, nullptr, 0};
-    flow_loss_fwd_kernel<<<grid_for(a->rows * a->C), 256, 0, st>>>(p);
+    B200_LAUNCH(flow_loss_fwd_kernel, grid_for(a->rows * a->C), 256, 0, st, p);
     if (int rc = check_launch("flow_loss_fwd_kernel")) return rc;
-    flow_loss_finalize_kernel<<<1, 1, 0, st>>>(a->sums, a->loss, a->C);
+    B200_LAUNCH(flow_loss_finalize_kernel, 1, 1, 0, st, a->sums, a->loss, a->C);
     return check_launch("flow_loss_finalize_kernel");
 }
 extern "C" int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t stream) {
     B200_REQUIRE(a && a->pred && a->x1 && a->x0 && a->span && a->sums && a->dloss && a->dpred && a->ldp >= a->C && (a->ldp % 8) == 0, "flow_loss_bwd: bad arguments");
     LossP p{a->pred, a->x1, a->x0, a->span, a->sums, nullptr, a->rows, a->C, a->dloss, (__nv_bfloat16*)a->dpred, a->ldp};
-    flow_loss_bwd_kernel<<<grid_for(a->rows * a->ldp), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    B200_LAUNCH(flow_loss_bwd_kernel, grid_for(a->rows * a->ldp), 256, 0, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("flow_loss_bwd_kernel");
 }
 
@@ -847,13 +866,13 @@ extern "C" int b200_rowgate_bwd(const void* dy, const void* y, const float* cs, 
     B200_REQUIRE(!cs || (y && d_cs), "rowgate_bwd: gate backward needs y and d_cs");
     const int rpb = 64;
     dim3 grid((rows_per_batch + rpb - 1) / rpb, B);
-    rowgate_bwd_kernel<<<grid, 256, (size_t)D * 8, reinterpret_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH(rowgate_bwd_kernel, grid, 256, (size_t)D * 8, reinterpret_cast<cudaStream_t>(stream), 
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, cs, mask, (__nv_bfloat16*)dz, d_cs, d_bias, rows_per_batch, D, rpb);
     return check_launch("rowgate_bwd_kernel");
 }
 
 extern "C" int b200_cast_rows(const float* src, void* dst, int64_t rows, int32_t cols, int32_t ld, b200_stream_t stream) {
     B200_REQUIRE(src && dst && rows > 0 && cols > 0 && ld >= cols, "cast_rows: bad arguments");
-    cast_rows_kernel<<<grid_for(rows * ld), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, (__nv_bfloat16*)dst, rows, cols, ld);
+    B200_LAUNCH(cast_rows_kernel, grid_for(rows * ld), 256, 0, reinterpret_cast<cudaStream_t>(stream), src, (__nv_bfloat16*)dst, rows, cols, ld);
     return check_launch("cast_rows_kernel");
 }

@@ -137,6 +137,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) may overlap the tail of the previous kernel (ptx.cuh)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -187,6 +188,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
+            pdl_launch_dependents();   // all operand loads are issued: the next kernel's CTAs may start their prologue
             if constexpr (CG == 2) {
                 // the leader's commits multicast into this CTA's empty barriers: let the last ones land before the CTA may exit
                 for (int i = 0; i < kStages; ++i) {
@@ -560,10 +562,12 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUte
     if constexpr (CG == 2) {
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // only counted when B200_PDL=1 (common.cuh)
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
         static int pairs = 0;   // co-resident 2-CTA clusters (one CTA per SM): the persistent grid
         if (!pairs) {
             cfg.gridDim = dim3(2 * (num_sms() / 2));
@@ -578,7 +582,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUte
         return check_launch("gemm_tcgen05_kernel<pair>");
     }
     const int grid = p.num_work < num_sms() ? p.num_work : num_sms();
-    kern<<<grid, kGemmThreads, S::TOTAL, st>>>(tA, tA2, tB, p);
+    B200_LAUNCH(kern, grid, kGemmThreads, S::TOTAL, st, tA, tA2, tB, p);
     return check_launch("gemm_tcgen05_kernel");
 }
 

@@ -212,6 +212,7 @@ __device__ __forceinline__ void load_gain8(const float* g, f2 (&o)[4]) {   // 8 
 // long-scoreboard stalls (profiles/r1g_ncu_full_hc_width_*).
 template <int VPT, bool PF>
 __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(const HcP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float4 sp[];
     __shared__ uint64_t bars[8][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -312,6 +313,7 @@ constexpr int HC_TOK_PER_BLOCK = 64;
 
 template <int VPT, bool PF>
 __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(const HcP p, __nv_bfloat16* __restrict__ cmat) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float4 sp[];
     __shared__ float s_scal[32];
     __shared__ float s_gng[VPT * 256];   // d(norm gain) partial sums of this block (one batch element), VPT*256 >= D
@@ -551,6 +553,7 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
 //   d norm.gamma[col]          = sum_t alpha_fn[col][t] G[col][t] + beta_fn[col] G[col][5].
 // (The first versions marched 128-token slabs per thread pair on the CUDA cores: 48 us per call against ~15 us for the GEMM.)
 __global__ void __launch_bounds__(256) hc_param_finalize_kernel(const HcP p, const float* __restrict__ G) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int col = blockIdx.x * 256 + threadIdx.x;
     if (col >= p.D) return;
     const float4 g0 = *reinterpret_cast<const float4*>(G + (size_t)col * 8), g1v = *reinterpret_cast<const float4*>(G + (size_t)col * 8 + 4);
@@ -579,6 +582,7 @@ struct HdP {
 
 // out[t,s,:] = res[t,s,:] + beta[t,s] * y[t,:]     (one 16-byte chunk of y per thread, all 4 streams)
 __global__ void __launch_bounds__(256) hc_depth_fwd_kernel(const HdP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int nchunk = p.D >> 3;
     const long long total = (long long)p.T * nchunk;
     for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
@@ -602,6 +606,7 @@ __global__ void __launch_bounds__(256) hc_depth_fwd_kernel(const HdP p) {
 
 // d_y[t,:] = sum_s beta[t,s] d_out[t,s,:];  d_beta[t,s] = <d_out[t,s,:], y[t,:]>   (one warp per token)
 __global__ void __launch_bounds__(256) hc_depth_bwd_kernel(const HdP p) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int lane = threadIdx.x & 31;
     const int nchunk = p.D >> 3;
     const long long nwarps = (long long)gridDim.x * 8;
@@ -669,17 +674,17 @@ extern "C" int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stre
         const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 2);
         if (a->D <= 256) {
             if (int rc = set_smem(hc_width_fwd_kernel<1, true>, smem)) return rc;
-            hc_width_fwd_kernel<1, true><<<grid, 256, smem, st>>>(p);
+            B200_LAUNCH((hc_width_fwd_kernel<1, true>), grid, 256, smem, st, p);
         } else {
             if (int rc = set_smem(hc_width_fwd_kernel<2, true>, smem)) return rc;
-            hc_width_fwd_kernel<2, true><<<grid, 256, smem, st>>>(p);
+            B200_LAUNCH((hc_width_fwd_kernel<2, true>), grid, 256, smem, st, p);
         }
         return check_launch("hc_width_fwd_kernel");
     }
     const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 8);
-    if (a->D <= 256) hc_width_fwd_kernel<1, false><<<grid, 256, smem_par, st>>>(p);
-    else if (a->D <= 512) hc_width_fwd_kernel<2, false><<<grid, 256, smem_par, st>>>(p);
-    else hc_width_fwd_kernel<4, false><<<grid, 256, smem_par, st>>>(p);
+    if (a->D <= 256) B200_LAUNCH((hc_width_fwd_kernel<1, false>), grid, 256, smem_par, st, p);
+    else if (a->D <= 512) B200_LAUNCH((hc_width_fwd_kernel<2, false>), grid, 256, smem_par, st, p);
+    else B200_LAUNCH((hc_width_fwd_kernel<4, false>), grid, 256, smem_par, st, p);
     return check_launch("hc_width_fwd_kernel");
 }
 
@@ -705,14 +710,14 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
         const size_t smem = smem_par + (size_t)8 * 2 * (2 * HS + 1) * a->D * 2;   // + per-warp {r, d_res, d_branch} double buffers
         if (a->D <= 256) {
             if (int rc = set_smem(hc_width_bwd_kernel<1, true>, smem)) return rc;
-            hc_width_bwd_kernel<1, true><<<grid, 256, smem, st>>>(p, cmat);
+            B200_LAUNCH((hc_width_bwd_kernel<1, true>), grid, 256, smem, st, p, cmat);
         } else {
             if (int rc = set_smem(hc_width_bwd_kernel<2, true>, smem)) return rc;
-            hc_width_bwd_kernel<2, true><<<grid, 256, smem, st>>>(p, cmat);
+            B200_LAUNCH((hc_width_bwd_kernel<2, true>), grid, 256, smem, st, p, cmat);
         }
-    } else if (a->D <= 256) hc_width_bwd_kernel<1, false><<<grid, 256, smem_par, st>>>(p, cmat);
-    else if (a->D <= 512) hc_width_bwd_kernel<2, false><<<grid, 256, smem_par, st>>>(p, cmat);
-    else hc_width_bwd_kernel<4, false><<<grid, 256, smem_par, st>>>(p, cmat);
+    } else if (a->D <= 256) B200_LAUNCH((hc_width_bwd_kernel<1, false>), grid, 256, smem_par, st, p, cmat);
+    else if (a->D <= 512) B200_LAUNCH((hc_width_bwd_kernel<2, false>), grid, 256, smem_par, st, p, cmat);
+    else B200_LAUNCH((hc_width_bwd_kernel<4, false>), grid, 256, smem_par, st, p, cmat);
     if (int rc = check_launch("hc_width_bwd_kernel")) return rc;
     // G = R^T C on the tensor cores: A = residual streams [T*S, D] read MN-major, B = C [T*S, 8] MN-major, split-K over the tokens
     b200_gemm_args g = {};
@@ -723,7 +728,7 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     const int tiles = (a->D + 255) / 256;
     g.split_k = num_sms() / tiles > 1 ? num_sms() / tiles : 2;   // >= 2: the split-K path zeroes and accumulates G
     if (int rc = b200_gemm(&g, stream)) return rc;
-    hc_param_finalize_kernel<<<(a->D + 255) / 256, 256, 0, st>>>(p, G);
+    B200_LAUNCH(hc_param_finalize_kernel, (a->D + 255) / 256, 256, 0, st, p, G);
     return check_launch("hc_param_finalize_kernel");
 }
 
@@ -735,7 +740,7 @@ extern "C" int b200_hc_depth_fwd(const b200_hc_depth_args* a, b200_stream_t stre
     p.res = (const __nv_bfloat16*)a->res; p.y = (const __nv_bfloat16*)a->y; p.beta = a->beta; p.out = (__nv_bfloat16*)a->out; p.T = a->T; p.D = a->D;
     const long long total = (long long)a->T * (a->D / 8);
     const int grid = (int)min((total + 255) / 256, (long long)num_sms() * 16);
-    hc_depth_fwd_kernel<<<grid, 256, 0, st>>>(p);
+    B200_LAUNCH(hc_depth_fwd_kernel, grid, 256, 0, st, p);
     return check_launch("hc_depth_fwd_kernel");
 }
 
@@ -747,6 +752,6 @@ extern "C" int b200_hc_depth_bwd(const b200_hc_depth_args* a, b200_stream_t stre
     p.y = (const __nv_bfloat16*)a->y; p.beta = a->beta; p.T = a->T; p.D = a->D;
     p.d_out = (const __nv_bfloat16*)a->d_out; p.d_y = (__nv_bfloat16*)a->d_y; p.d_beta = a->d_beta;
     const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 8);
-    hc_depth_bwd_kernel<<<grid, 256, 0, st>>>(p);
+    B200_LAUNCH(hc_depth_bwd_kernel, grid, 256, 0, st, p);
     return check_launch("hc_depth_bwd_kernel");
 }

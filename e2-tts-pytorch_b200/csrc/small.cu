@@ -56,6 +56,7 @@ __device__ __forceinline__ void sl_halve16(float (&v)[16], int lane) {   // on r
 }
 
 __global__ void __launch_bounds__(256) small_linear_fwd_kernel(const b200_small_linear_args a, int n_per_warp, int x_in_smem) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ __align__(16) float xs[];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     if (x_in_smem) {
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) small_linear_fwd_kernel(const b200_small_
 }
 // one warp per output feature n: dZ[:,n], dbias[n], dW[n,:]
 __global__ void __launch_bounds__(256) small_linear_bwd_w_kernel(const b200_small_linear_args a) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     __shared__ float sdz[8][SL_MAXB];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int n = blockIdx.x * 8 + wl;
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(256) small_linear_bwd_w_kernel(const b200_smal
 // consecutive k (16-byte W loads, 16-byte vector reductions into dX) and one of two 128-row halves of the slab.
 constexpr int SL_SLAB = 256;   // largest slab of output features per block (a multiple of 8; smaller slabs when N is small)
 __global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_small_linear_args a, int slab) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ __align__(16) float sdz[];   // [B][slab]
     const int n0 = blockIdx.x * slab, n1 = min(a.N, n0 + slab);
     for (int i = threadIdx.x; i < a.B * slab; i += 256) {
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(256) small_linear_bwd_x_kernel(const b200_smal
 }
 
 __global__ void fourier_embed_kernel(const float* times, const float* w, float* out, int B, int half) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     const int b = i / half, j = i % half;
@@ -236,6 +240,7 @@ __device__ __forceinline__ void conv_rows(const float (&w)[31], const float (*sr
 // row validity (inside the sequence and not masked) is staged once per tile so that no global load sits behind a branch
 // on another global load (the first version chained mask -> dy loads per row and was latency-bound: ncu r1).
 __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const b200_dwconv_args a) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     __shared__ float xs[CV_TN + 2 * CV_HALO][CV_TC];
     __shared__ unsigned char sok[CV_TN + 2 * CV_HALO];
     const int n0 = blockIdx.x * CV_TN, c0 = blockIdx.y * CV_TC, b = blockIdx.z;
@@ -279,6 +284,7 @@ constexpr int CV_TILES_PER_BLOCK = 4;   // n-tiles marched by one block: weight/
 constexpr int CV_P1 = 96;               // phase-1 rows (tile + halo each side = 94, padded to 8 x 12)
 
 __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const b200_dwconv_args a) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float sm[];
     float (*xs)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm);                              // [CV_P1 + 30] rows, token n0 - 30 + r
     float (*dps)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (CV_P1 + 30) * CV_TC);       // [CV_P1] rows, token n0 - 15 + r
@@ -386,6 +392,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const b200_dwconv_ar
 
 // ------------------------------------------------------------------------------------------------ masked mean
 __global__ void __launch_bounds__(256) masked_mean_fwd_kernel(const __nv_bfloat16* x, const unsigned char* mask, float* out, int N, int D) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int b = blockIdx.y, d = blockIdx.x * 256 + threadIdx.x;
     if (d >= D) return;
     float acc = 0.f, den = 0.f;
@@ -396,6 +403,7 @@ __global__ void __launch_bounds__(256) masked_mean_fwd_kernel(const __nv_bfloat1
     out[(size_t)b * D + d] = acc / fmaxf(den, 1.f);
 }
 __global__ void __launch_bounds__(256) masked_mean_bwd_kernel(const float* dout, const unsigned char* mask, __nv_bfloat16* dx, int N, int D) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     __shared__ float sden;
     const int b = blockIdx.y;
     if (threadIdx.x == 0) {
@@ -416,10 +424,12 @@ __global__ void __launch_bounds__(256) masked_mean_bwd_kernel(const float* dout,
 // ------------------------------------------------------------------------------------------------ ODE / CFG helpers
 // out = y + a * f  (fixed-grid midpoint / Euler update, torchdiffeq semantics A.7)
 __global__ void __launch_bounds__(256) axpy_kernel(const float* y, const float* f, float a, float* out, long long n) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = y[i] + a * f[i];
 }
 // per-sample fp64 reductions for the APG projection (e2_tts.py:113-124): red[b] = (<pred - null, pred>, <pred, pred>)
 __global__ void __launch_bounds__(256) cfg_reduce_kernel(const float* pred, const float* null_pred, double* red, long long per) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int b = blockIdx.y;
     const float* p = pred + (size_t)b * per;
     const float* q = null_pred + (size_t)b * per;
@@ -443,6 +453,7 @@ __global__ void __launch_bounds__(256) cfg_reduce_kernel(const float* pred, cons
 // out = pred + (orth + par * keep) * strength, par = (<upd, unit>) unit, unit = pred / max(||pred||, 1e-12)
 __global__ void __launch_bounds__(256) cfg_apply_kernel(const float* pred, const float* null_pred, const double* red, float* out, long long per,
                                                          float strength, int remove_parallel, float keep) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     const int b = blockIdx.y;
     const double nrm = fmax(sqrt(red[2 * b + 1]), 1e-12);
     const double coef = red[2 * b] / (nrm * nrm);   // <upd, unit> / ||pred||
@@ -465,6 +476,7 @@ __global__ void __launch_bounds__(256) cfg_apply_kernel(const float* pred, const
 // (index (k*n) mod n_fft), magnitude, dense mel filterbank, log. Output [B, n_mels, frames] like the reference.
 __global__ void __launch_bounds__(256) melspec_kernel(const float* wave, const float* window, const float* fb, float* out, int nw, int n_fft,
                                                        int hop, int n_mels, int frames) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float msm[];
     float* xs = msm;                 // [n_fft]
     float* cs = xs + n_fft;          // [n_fft]
@@ -522,7 +534,7 @@ extern "C" int b200_small_linear_fwd(const b200_small_linear_args* a, b200_strea
         int npw = 1;
         while (npw < 8 && (a->N + 8 * (npw * 2) - 1) / (8 * (npw * 2)) >= 2 * num_sms()) npw *= 2;
         const int per_block = 8 * npw;
-        small_linear_fwd_kernel<<<(a->N + per_block - 1) / per_block, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a, npw, x_in_smem);
+        B200_LAUNCH(small_linear_fwd_kernel, (a->N + per_block - 1) / per_block, 256, smem, reinterpret_cast<cudaStream_t>(stream), *a, npw, x_in_smem);
     }
     return check_launch("small_linear_fwd_kernel");
 }
@@ -530,7 +542,7 @@ extern "C" int b200_small_linear_bwd(const b200_small_linear_args* a, b200_strea
     B200_REQUIRE(a && a->X && a->W && a->Z && a->dY && a->dZ && a->dW, "small_linear_bwd: null pointer");
     B200_REQUIRE(a->B > 0 && a->B <= SL_MAXB && a->N > 0 && a->K > 0, "small_linear: batch must be 1..%d", SL_MAXB);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    small_linear_bwd_w_kernel<<<(a->N + 7) / 8, 256, 0, st>>>(*a);
+    B200_LAUNCH(small_linear_bwd_w_kernel, (a->N + 7) / 8, 256, 0, st, *a);
     if (int rc = check_launch("small_linear_bwd_w_kernel")) return rc;
     if (a->dX) {
         cudaError_t e = cudaMemsetAsync(a->dX, 0, (size_t)a->B * a->K * sizeof(float), st);
@@ -544,14 +556,14 @@ extern "C" int b200_small_linear_bwd(const b200_small_linear_args* a, b200_strea
             B200_REQUIRE(e2 == cudaSuccess, "small_linear_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
             configured = true;
         }
-        small_linear_bwd_x_kernel<<<(a->N + slab - 1) / slab, 256, smem, st>>>(*a, slab);
+        B200_LAUNCH(small_linear_bwd_x_kernel, (a->N + slab - 1) / slab, 256, smem, st, *a, slab);
         return check_launch("small_linear_bwd_x_kernel");
     }
     return 0;
 }
 extern "C" int b200_fourier_embed(const float* times, const float* weights, float* out, int32_t B, int32_t half, b200_stream_t stream) {
     B200_REQUIRE(times && weights && out && B > 0 && half > 0, "fourier_embed: bad arguments");
-    fourier_embed_kernel<<<(B * half + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(times, weights, out, B, half);
+    B200_LAUNCH(fourier_embed_kernel, (B * half + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream), times, weights, out, B, half);
     return check_launch("fourier_embed_kernel");
 }
 
@@ -565,7 +577,7 @@ extern "C" int b200_dwconv_fwd(const b200_dwconv_args* a, b200_stream_t stream) 
     if (check_conv(a)) return -1;
     B200_REQUIRE(a->y, "dwconv_fwd: null output");
     dim3 grid((a->Np + CV_TN - 1) / CV_TN, (a->D + CV_TC - 1) / CV_TC, a->B);
-    dwconv_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    B200_LAUNCH(dwconv_fwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), *a);
     return check_launch("dwconv_fwd_kernel");
 }
 extern "C" int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream) {
@@ -579,25 +591,25 @@ extern "C" int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream) 
     }
     const int ntiles = (a->Np + CV_TN - 1) / CV_TN;
     dim3 grid((ntiles + CV_TILES_PER_BLOCK - 1) / CV_TILES_PER_BLOCK, (a->D + CV_TC - 1) / CV_TC, a->B);
-    dwconv_bwd_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    B200_LAUNCH(dwconv_bwd_kernel, grid, 256, smem, reinterpret_cast<cudaStream_t>(stream), *a);
     return check_launch("dwconv_bwd_kernel");
 }
 
 extern "C" int b200_masked_mean_fwd(const void* x, const uint8_t* mask, float* out, int32_t B, int32_t N, int32_t D, b200_stream_t stream) {
     B200_REQUIRE(x && out && B > 0 && N > 0 && D > 0, "masked_mean_fwd: bad arguments");
-    masked_mean_fwd_kernel<<<dim3((D + 255) / 256, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)x, mask, out, N, D);
+    B200_LAUNCH(masked_mean_fwd_kernel, dim3((D + 255) / 256, B), 256, 0, reinterpret_cast<cudaStream_t>(stream), (const __nv_bfloat16*)x, mask, out, N, D);
     return check_launch("masked_mean_fwd_kernel");
 }
 extern "C" int b200_masked_mean_bwd(const float* dout, const uint8_t* mask, void* dx, int32_t B, int32_t N, int32_t D, b200_stream_t stream) {
     B200_REQUIRE(dout && dx && B > 0 && N > 0 && D > 0, "masked_mean_bwd: bad arguments");
-    masked_mean_bwd_kernel<<<dim3(64, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dout, mask, (__nv_bfloat16*)dx, N, D);
+    B200_LAUNCH(masked_mean_bwd_kernel, dim3(64, B), 256, 0, reinterpret_cast<cudaStream_t>(stream), dout, mask, (__nv_bfloat16*)dx, N, D);
     return check_launch("masked_mean_bwd_kernel");
 }
 
 extern "C" int b200_axpy(const float* y, const float* f, float a, float* out, int64_t n, b200_stream_t stream) {
     B200_REQUIRE(y && f && out && n > 0, "axpy: bad arguments");
     const long long g = (n + 255) / 256;
-    axpy_kernel<<<(unsigned)(g > 148 * 16 ? 148 * 16 : g), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, f, a, out, n);
+    B200_LAUNCH(axpy_kernel, (unsigned)(g > 148 * 16 ? 148 * 16 : g), 256, 0, reinterpret_cast<cudaStream_t>(stream), y, f, a, out, n);
     return check_launch("axpy_kernel");
 }
 extern "C" int b200_cfg_combine(const float* pred, const float* null_pred, double* ws_red, float* out, int32_t B, int64_t per_sample,
@@ -607,9 +619,9 @@ extern "C" int b200_cfg_combine(const float* pred, const float* null_pred, doubl
     cudaError_t e = cudaMemsetAsync(ws_red, 0, (size_t)B * 2 * sizeof(double), st);
     B200_REQUIRE(e == cudaSuccess, "cfg_combine: memset: %s", cudaGetErrorString(e));
     const int gx = (int)((per_sample + 256 * 8 - 1) / (256 * 8));
-    cfg_reduce_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, st>>>(pred, null_pred, ws_red, per_sample);
+    B200_LAUNCH(cfg_reduce_kernel, dim3(gx < 1 ? 1 : gx, B), 256, 0, st, pred, null_pred, ws_red, per_sample);
     if (int rc = check_launch("cfg_reduce_kernel")) return rc;
-    cfg_apply_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, st>>>(pred, null_pred, ws_red, out, per_sample, cfg_strength, remove_parallel, keep_parallel_frac);
+    B200_LAUNCH(cfg_apply_kernel, dim3(gx < 1 ? 1 : gx, B), 256, 0, st, pred, null_pred, ws_red, out, per_sample, cfg_strength, remove_parallel, keep_parallel_frac);
     return check_launch("cfg_apply_kernel");
 }
 extern "C" int b200_melspec(const float* wave, const float* window, const float* fb, float* out, int32_t B, int32_t nw, int32_t n_fft,
@@ -620,6 +632,6 @@ extern "C" int b200_melspec(const float* wave, const float* window, const float*
     const size_t smem = (size_t)(3 * n_fft + n_fft / 2 + 1) * sizeof(float);
     static bool configured = false;
     if (!configured) { cudaFuncSetAttribute(melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); configured = true; }
-    melspec_kernel<<<dim3(frames, B), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(wave, window, fb, out, nw, n_fft, hop, n_mels, frames);
+    B200_LAUNCH(melspec_kernel, dim3(frames, B), 256, smem, reinterpret_cast<cudaStream_t>(stream), wave, window, fb, out, nw, n_fft, hop, n_mels, frames);
     return check_launch("melspec_kernel");
 }

@@ -9,7 +9,8 @@ from .modules import (  # noqa: E402,F401
     E2TTS, DurationPredictor, Transformer, MelSpec, E2TTSReturn, LossBreakdown, inject_randomness,
     list_str_to_tensor, lens_to_mask, mask_from_frac_lengths,
 )
-from . import lib, ops  # noqa: E402,F401
+from . import lib, ops, optim  # noqa: E402,F401
 from .graphed import GraphedTrainStep  # noqa: E402,F401
+from .optim import GradSync, FusedAdoptEMA  # noqa: E402,F401
 
-__all__ = ['E2TTS', 'DurationPredictor', 'Transformer', 'MelSpec', 'E2TTSReturn', 'LossBreakdown', 'inject_randomness', 'GraphedTrainStep']
+__all__ = ['E2TTS', 'DurationPredictor', 'Transformer', 'MelSpec', 'E2TTSReturn', 'LossBreakdown', 'inject_randomness', 'GraphedTrainStep', 'GradSync', 'FusedAdoptEMA']

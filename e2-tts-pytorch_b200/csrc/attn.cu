@@ -465,13 +465,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnP p) {
     }
 }
 
-static int fill_common(AttnP& p, int B, int H, int Np, float scale, float clamp, float dropout_p, uint64_t seed) {
+static int fill_common(AttnP& p, int B, int H, int Np, float scale, float clamp, float dropout_p, uint64_t seed, const uint64_t* seed_dev) {
     B200_REQUIRE(B > 0 && H > 0 && Np > 0, "attention: empty problem");
     B200_REQUIRE(B <= 65535 && H <= 65535, "attention: batch/heads exceed grid limits");
     B200_REQUIRE(clamp > 0.f, "attention: softclamp value must be > 0 (reference always clamps, e2_tts.py:548-551)");
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout must be in [0,1)");
     p.B = B; p.H = H; p.Np = Np; p.scale = scale; p.clamp = clamp; p.inv_clamp = 1.f / clamp;
-    p.dropout_p = dropout_p; p.seed = seed; p.seed_dev = seed_dev_ptr();
+    p.dropout_p = dropout_p; p.seed = seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
     p.drop_thresh = (unsigned int)(dropout_p * 65536.f);
     p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
     p.drop_stride = (Np + 1) & ~1;
@@ -488,7 +488,7 @@ extern "C" int b200_attn_fwd_legacy(const b200_attn_fwd_args* a, b200_stream_t s
     B200_REQUIRE(a && a->q && a->k && a->v && a->o && a->og && a->lse, "attn_fwd: null pointer");
     B200_REQUIRE(a->dim_head == 64, "attn_fwd: only dim_head 64 is built (got %d)", a->dim_head);
     AttnP p{};
-    if (fill_common(p, a->B, a->H, a->Np, a->scale, a->softclamp, a->dropout_p, a->seed)) return -1;
+    if (fill_common(p, a->B, a->H, a->Np, a->scale, a->softclamp, a->dropout_p, a->seed, a->seed_dev)) return -1;
     p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
     p.keymask = a->keymask; p.gate = a->gate; p.o = (__nv_bfloat16*)a->o; p.og = (__nv_bfloat16*)a->og; p.lse = a->lse;
     dim3 grid((a->Np + AT - 1) / AT, a->H, a->B);
@@ -499,7 +499,7 @@ extern "C" int b200_attn_fwd_legacy(const b200_attn_fwd_args* a, b200_stream_t s
 namespace b200 {
 int launch_attn_bwd_prep(const b200_attn_bwd_args* a, cudaStream_t st) {
     AttnP p{};
-    if (fill_common(p, a->B, a->H, a->Np, a->scale, a->softclamp, a->dropout_p, a->seed)) return -1;
+    if (fill_common(p, a->B, a->H, a->Np, a->scale, a->softclamp, a->dropout_p, a->seed, a->seed_dev)) return -1;
     p.gate = a->gate; p.o = (__nv_bfloat16*)a->o; p.dog = (const __nv_bfloat16*)a->d_og; p.dO_out = (__nv_bfloat16*)a->ws_dO;
     p.delta_out = a->ws_delta; p.dgate = a->d_gate;
     const long long rows = (long long)a->B * a->H * a->Np;
@@ -514,7 +514,7 @@ extern "C" int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t s
     B200_REQUIRE(a && a->q && a->k && a->v && a->o && a->d_og && a->lse && a->ws_dO && a->ws_delta && a->dq && a->dk && a->dv, "attn_bwd: null pointer");
     B200_REQUIRE(a->dim_head == 64, "attn_bwd: only dim_head 64 is built (got %d)", a->dim_head);
     AttnP p{};
-    if (fill_common(p, a->B, a->H, a->Np, a->scale, a->softclamp, a->dropout_p, a->seed)) return -1;
+    if (fill_common(p, a->B, a->H, a->Np, a->scale, a->softclamp, a->dropout_p, a->seed, a->seed_dev)) return -1;
     p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
     p.keymask = a->keymask; p.gate = a->gate; p.o = (__nv_bfloat16*)a->o; p.lse = const_cast<float*>(a->lse);
     p.dog = (const __nv_bfloat16*)a->d_og; p.dO_out = (__nv_bfloat16*)a->ws_dO; p.delta_out = a->ws_delta; p.dgate = a->d_gate;
@@ -524,12 +524,9 @@ extern "C" int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t s
     B200_LAUNCH(attn_bwd_prep_kernel, (unsigned)((rows * 8 + 255) / 256), 256, 0, st, p);
     if (int rc = check_launch("attn_bwd_prep_kernel")) return rc;
     dim3 grid((a->Np + AT - 1) / AT, a->H, a->B);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_B + 1024);
-        cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TILE_B);
-        configured = true;
-    }
+    static DeviceOnce once_dkv, once_dq;
+    B200_REQUIRE(set_max_smem_once(once_dkv, attn_bwd_dkv_kernel, 6 * TILE_B + 1024) == cudaSuccess &&
+                 set_max_smem_once(once_dq, attn_bwd_dq_kernel, 6 * TILE_B) == cudaSuccess, "attn_bwd_legacy: cudaFuncSetAttribute failed");
     B200_LAUNCH(attn_bwd_dq_kernel, grid, 128, 6 * TILE_B, st, p);
     if (int rc = check_launch("attn_bwd_dq_kernel")) return rc;
     B200_LAUNCH(attn_bwd_dkv_kernel, grid, 128, 6 * TILE_B + 1024, st, p);

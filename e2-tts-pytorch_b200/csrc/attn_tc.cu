@@ -652,18 +652,15 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     p.dropout_p = a->dropout_p;
     p.drop_thresh = (unsigned int)(a->dropout_p * 65536.f);
     p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
-    p.seed = a->seed; p.seed_dev = seed_dev_ptr();
+    p.seed = a->seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(a->seed_dev);
     p.drop_stride = (a->Np + 1) & ~1;
     CUtensorMap tq, tk, tv;
     const long long rows = (long long)a->B * a->H * a->Np;
     if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows)) return -1;
     const int smem = 5 * TILE16 + 2 * PTILE + 256 + 4096 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        B200_REQUIRE(e == cudaSuccess, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    static DeviceOnce once;
+    cudaError_t e = set_max_smem_once(once, attn_fwd_tc_kernel, smem);
+    B200_REQUIRE(e == cudaSuccess, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     dim3 grid((a->Np + TQ - 1) / TQ, a->H, a->B);
     B200_LAUNCH(attn_fwd_tc_kernel, grid, 576, smem, st, tq, tk, tv, p);
     return check_launch("attn_fwd_tc_kernel");
@@ -700,17 +697,14 @@ extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) 
     p.drop_thresh = (unsigned int)(a->dropout_p * 65536.f);
     p.keep_scale = 65536.f / (65536.f - (float)p.drop_thresh);
     p.drop_stride = (a->Np + 1) & ~1;
-    p.seed = a->seed; p.seed_dev = seed_dev_ptr();
+    p.seed = a->seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(a->seed_dev);
     CUtensorMap tq, tk, tv, tdo;
     const long long rows = (long long)a->B * a->H * a->Np;
     if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows) || make_head_map(&tdo, a->ws_dO, rows)) return -1;
     const int smem = 6 * TILE16 + 2 * PTILE + 256 + 8 * 32 * 33 * 4 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        B200_REQUIRE(e2 == cudaSuccess, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
-        configured = true;
-    }
+    static DeviceOnce once;
+    cudaError_t e2 = set_max_smem_once(once, attn_bwd_tc_kernel, smem);
+    B200_REQUIRE(e2 == cudaSuccess, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
     dim3 grid(p.nq, a->H, a->B);
     B200_LAUNCH(attn_bwd_tc_kernel, grid, 576, smem, st, tq, tk, tv, tdo, p);
     return check_launch("attn_bwd_tc_kernel");

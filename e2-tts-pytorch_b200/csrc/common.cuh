@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "../../include/b200_e2tts.h"
 
@@ -13,10 +14,6 @@ namespace b200 {
 
 extern thread_local char g_err[512];
 extern std::atomic<uint64_t> g_launches;
-// Optional device-resident addend of every dropout seed (b200_set_dropout_seed_device): lets a captured CUDA graph draw fresh
-// dropout masks on every replay — the host-side seed is a kernel argument and therefore frozen at capture time.
-extern std::atomic<const unsigned long long*> g_seed_dev;
-inline const unsigned long long* seed_dev_ptr() { return g_seed_dev.load(std::memory_order_relaxed); }
 
 #define B200_FAIL(...)                                   \
     do {                                                 \
@@ -69,15 +66,35 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
         else kern<<<grid, block, smem, st>>>(__VA_ARGS__);                             \
     } while (0)
 
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 inline int num_sms() {
-    static int n = 0;
+    static std::atomic<int> cache[kMaxDevices];
+    const int dev = current_device();
+    int n = cache[dev].load(std::memory_order_relaxed);
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
     return n;
+}
+// One-time, per-device kernel attribute (cudaFuncSetAttribute applies to the current device's context): SURVEY §8b asks for
+// std::once_flag-guarded initialisation because autograd / DDP call the library from several threads.
+struct DeviceOnce {
+    std::once_flag flag[kMaxDevices];
+    cudaError_t err[kMaxDevices] = {};
+};
+template <typename K>
+inline cudaError_t set_max_smem_once(DeviceOnce& once, K kern, int bytes) {
+    const int dev = current_device();
+    std::call_once(once.flag[dev], [&] { once.err[dev] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+    return once.err[dev];
 }
 
 }  // namespace b200

@@ -565,10 +565,11 @@ struct LossP {
     const float *pred, *x1, *x0; const unsigned char* span; float* sums; float* pred_data;
     long long rows; int C;
     const float* dloss; __nv_bfloat16* dpred; int ldp;
+    const float* vel_target; float vel_weight; float* loss_parts;   // velocity-consistency term (e2_tts.py:1556-1576), optional
 };
 __global__ void __launch_bounds__(256) flow_loss_fwd_kernel(const LossP p) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
-    float acc = 0.f, cnt = 0.f;
+    float acc = 0.f, cnt = 0.f, accv = 0.f;
     const long long total = p.rows * p.C;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const long long row = i / p.C;
@@ -578,22 +579,31 @@ __global__ void __launch_bounds__(256) flow_loss_fwd_kernel(const LossP p) {
             const float d = pr - (p.x1[i] - a0);
             acc += d * d;
             if (i % p.C == 0) cnt += 1.f;
+            if (p.vel_target) {
+                const float dv = pr - p.vel_target[i];
+                accv += dv * dv;
+            }
         }
     }
-    acc = warp_sum(acc); cnt = warp_sum(cnt);
-    __shared__ float sa[8], sc[8];
-    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = acc; sc[threadIdx.x >> 5] = cnt; }
+    acc = warp_sum(acc); cnt = warp_sum(cnt); accv = warp_sum(accv);
+    __shared__ float sa[8], sc[8], sv[8];
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = acc; sc[threadIdx.x >> 5] = cnt; sv[threadIdx.x >> 5] = accv; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float a = 0.f, c = 0.f;
-        for (int k = 0; k < 8; ++k) { a += sa[k]; c += sc[k]; }
+        float a = 0.f, c = 0.f, v = 0.f;
+        for (int k = 0; k < 8; ++k) { a += sa[k]; c += sc[k]; v += sv[k]; }
         atomicAdd(p.sums, a);
         atomicAdd(p.sums + 1, c);
+        if (p.vel_target) atomicAdd(p.sums + 2, v);
     }
 }
-__global__ void flow_loss_finalize_kernel(const float* sums, float* loss, int C) {
+// loss = flow + vel_weight * velocity (e2_tts.py:1586-1589); loss_parts (optional) = {flow, velocity} for the LossBreakdown
+__global__ void flow_loss_finalize_kernel(const float* sums, float* loss, int C, int has_vel, float vel_weight, float* loss_parts) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
-    *loss = sums[0] / (sums[1] * (float)C);
+    const float den = sums[1] * (float)C;
+    const float flow = sums[0] / den, vel = has_vel ? sums[2] / den : 0.f;
+    *loss = flow + vel_weight * vel;
+    if (loss_parts) { loss_parts[0] = flow; loss_parts[1] = vel; }
 }
 __global__ void __launch_bounds__(256) flow_loss_bwd_kernel(const LossP p) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
@@ -605,7 +615,9 @@ __global__ void __launch_bounds__(256) flow_loss_bwd_kernel(const LossP p) {
         float v = 0.f;
         if (c < p.C && p.span[row]) {
             const size_t s = (size_t)row * p.C + c;
-            v = (p.pred[s] - (p.x1[s] - p.x0[s])) * scale;
+            v = p.pred[s] - (p.x1[s] - p.x0[s]);
+            if (p.vel_target) v += p.vel_weight * (p.pred[s] - p.vel_target[s]);
+            v *= scale;
         }
         p.dpred[i] = __float2bfloat16(v);
     }
@@ -669,7 +681,8 @@ __global__ void __launch_bounds__(256) rowgate_bwd_kernel(const __nv_bfloat16* _
         }
         if (cs) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(&sacc[cc * 8 + j], acc[j] / s8[j]);
+            for (int j = 0; j < 8; ++j)   // d_cs = sum dy * z with z = y / cs: a gate that underflowed to 0 zeroed y as well (0/0), its gradient is taken as 0
+                atomicAdd(&sacc[cc * 8 + j], fabsf(s8[j]) > 1e-30f ? acc[j] / s8[j] : 0.f);
         }
         if (d_bias) {
 #pragma unroll
@@ -785,11 +798,11 @@ extern "C" int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stre
 }
 
 extern "C" int b200_geglu_bwd(const void* dh, const void* ug, void* dug, float* db_packed, int64_t T, int32_t inner, float dropout_p, uint64_t seed,
-                              b200_stream_t stream) {
+                              const uint64_t* seed_dev, b200_stream_t stream) {
     B200_REQUIRE(dh && ug && dug && T > 0 && inner > 0 && (inner % 64) == 0, "geglu_bwd: inner must be a multiple of 64");
     dim3 grid((inner / 8 + 31) / 32, (unsigned)((T + GB_ROWS - 1) / GB_ROWS));
     B200_LAUNCH(geglu_bwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
-        (const __nv_bfloat16*)dh, (const __nv_bfloat16*)ug, (__nv_bfloat16*)dug, db_packed, T, inner, dropout_p, seed, seed_dev_ptr());
+        (const __nv_bfloat16*)dh, (const __nv_bfloat16*)ug, (__nv_bfloat16*)dug, db_packed, T, inner, dropout_p, seed, reinterpret_cast<const unsigned long long*>(seed_dev));
     return check_launch("geglu_bwd_kernel");
 }
 
@@ -845,17 +858,17 @@ extern "C" int b200_final_norm_bwd(const b200_final_norm_args* a, b200_stream_t 
 extern "C" int b200_flow_loss_fwd(const b200_flow_loss_args* a, b200_stream_t stream) {
     B200_REQUIRE(a && a->pred && a->x1 && a->x0 && a->span && a->sums && a->loss, "flow_loss_fwd: null pointer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(a->sums, 0, 2 * sizeof(float), st);
+    cudaError_t e = cudaMemsetAsync(a->sums, 0, 4 * sizeof(float), st);
     B200_REQUIRE(e == cudaSuccess, "flow_loss_fwd: memset: %s", cudaGetErrorString(e));
-    LossP p{a->pred, a->x1, a->x0, a->span, a->sums, a->pred_data, a->rows, a->C, nullptr, nullptr, 0};
+    LossP p{a->pred, a->x1, a->x0, a->span, a->sums, a->pred_data, a->rows, a->C, nullptr, nullptr, 0, a->vel_target, a->vel_weight, a->loss_parts};
     B200_LAUNCH(flow_loss_fwd_kernel, grid_for(a->rows * a->C), 256, 0, st, p);
     if (int rc = check_launch("flow_loss_fwd_kernel")) return rc;
-    B200_LAUNCH(flow_loss_finalize_kernel, 1, 1, 0, st, a->sums, a->loss, a->C);
+    B200_LAUNCH(flow_loss_finalize_kernel, 1, 1, 0, st, a->sums, a->loss, a->C, a->vel_target != nullptr, a->vel_weight, a->loss_parts);
     return check_launch("flow_loss_finalize_kernel");
 }
 extern "C" int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t stream) {
     B200_REQUIRE(a && a->pred && a->x1 && a->x0 && a->span && a->sums && a->dloss && a->dpred && a->ldp >= a->C && (a->ldp % 8) == 0, "flow_loss_bwd: bad arguments");
-    LossP p{a->pred, a->x1, a->x0, a->span, a->sums, nullptr, a->rows, a->C, a->dloss, (__nv_bfloat16*)a->dpred, a->ldp};
+    LossP p{a->pred, a->x1, a->x0, a->span, a->sums, nullptr, a->rows, a->C, a->dloss, (__nv_bfloat16*)a->dpred, a->ldp, a->vel_target, a->vel_weight, nullptr};
     B200_LAUNCH(flow_loss_bwd_kernel, grid_for(a->rows * a->ldp), 256, 0, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("flow_loss_bwd_kernel");
 }

@@ -553,11 +553,10 @@ template <int BN, bool A_MN, bool B_MN, int MH, int CG = 1>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const GemmParams& p, cudaStream_t st) {
     using S = GemmSmem<BN, MH, CG>;
     auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, MH, CG>;
-    static bool configured = false;  // idempotent attribute; racing first calls set the same value
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    static DeviceOnce once;   // one flag per template instantiation and device
+    {
+        cudaError_t e = set_max_smem_once(once, kern, S::TOTAL);
         B200_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
     }
     if constexpr (CG == 2) {
         cudaLaunchConfig_t cfg = {};
@@ -568,13 +567,15 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUte
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // only counted when B200_PDL=1 (common.cuh)
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        static int pairs = 0;   // co-resident 2-CTA clusters (one CTA per SM): the persistent grid
+        static std::atomic<int> pairs_cache[kMaxDevices];   // co-resident 2-CTA clusters (one CTA per SM): the persistent grid, per device
+        int pairs = pairs_cache[current_device()].load(std::memory_order_relaxed);
         if (!pairs) {
             cfg.gridDim = dim3(2 * (num_sms() / 2));
             int n = 0;
             cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
             B200_REQUIRE(e == cudaSuccess && n > 0, "gemm: cudaOccupancyMaxActiveClusters: %s (%d)", cudaGetErrorString(e), n);
             pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+            pairs_cache[current_device()].store(pairs, std::memory_order_relaxed);
         }
         cfg.gridDim = dim3(2 * (p.num_work < pairs ? p.num_work : pairs));
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA, tA2, tB, p);
@@ -623,7 +624,7 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
     p.D2 = a->D2; p.ldd2 = a->ldd2;
     p.bias = a->bias; p.colscale = a->colscale; p.rows_per_batch = (int)(a->rows_per_batch > 0 ? a->rows_per_batch : 1);
     p.rowmask = a->rowmask; p.resid = a->resid; p.ldr = a->ldr;
-    p.geglu = a->geglu; p.dropout_p = a->dropout_p; p.seed = a->seed; p.seed_dev = seed_dev_ptr();
+    p.geglu = a->geglu; p.dropout_p = a->dropout_p; p.seed = a->seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(a->seed_dev);
     if (p.atomic_out) {
         B200_REQUIRE(a->d_fp32, "gemm: split-K requires an fp32 output");
         B200_REQUIRE(!a->bias && !a->colscale && !a->rowmask && !a->resid && !a->geglu, "gemm: split-K supports no epilogue");

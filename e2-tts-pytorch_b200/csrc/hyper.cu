@@ -638,10 +638,15 @@ static bool hc_prefetch_enabled() {
     static const bool on = !(getenv("B200_HC_PREFETCH") && atoi(getenv("B200_HC_PREFETCH")) == 0);   // developer A/B switch, default on
     return on;
 }
+// the dynamic shared-memory ceiling of a token kernel depends on D, which a process may vary between calls (text / audio streams):
+// raise it once per (kernel instantiation, device) to the kernel's maximum instead of per call (once_flag-guarded init)
 template <typename K>
 static int set_smem(K kern, size_t bytes) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);   // idempotent
-    B200_REQUIRE(e == cudaSuccess, "hyper-connections: cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
+    static DeviceOnce once;   // one per instantiation of this template = per kernel
+    constexpr int kMax = 200 * 1024;
+    B200_REQUIRE(bytes <= (size_t)kMax, "hyper-connections: %zu B of shared memory exceed the kernel's ceiling", bytes);
+    cudaError_t e = set_max_smem_once(once, kern, kMax);
+    B200_REQUIRE(e == cudaSuccess, "hyper-connections: cudaFuncSetAttribute(%d B): %s", kMax, cudaGetErrorString(e));
     return 0;
 }
 

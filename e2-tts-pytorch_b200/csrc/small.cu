@@ -524,12 +524,9 @@ extern "C" int b200_small_linear_fwd(const b200_small_linear_args* a, b200_strea
     {
         const int x_in_smem = ((long long)a->B * a->K <= SL_XS_MAX) ? 1 : 0;
         const size_t smem = x_in_smem ? (size_t)a->B * a->K * sizeof(float) : 0;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(small_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_XS_MAX * (int)sizeof(float));
-            B200_REQUIRE(e == cudaSuccess, "small_linear_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            configured = true;
-        }
+        static DeviceOnce once;
+        cudaError_t e = set_max_smem_once(once, small_linear_fwd_kernel, SL_XS_MAX * (int)sizeof(float));
+        B200_REQUIRE(e == cudaSuccess, "small_linear_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         // enough outputs per warp to amortise the X staging, but at least ~2 blocks per SM when N is large
         int npw = 1;
         while (npw < 8 && (a->N + 8 * (npw * 2) - 1) / (8 * (npw * 2)) >= 2 * num_sms()) npw *= 2;
@@ -550,12 +547,9 @@ extern "C" int b200_small_linear_bwd(const b200_small_linear_args* a, b200_strea
         int slab = SL_SLAB;   // fewer features per block when N is small, so that the slabs still cover the GPU
         while (slab > 32 && (a->N + slab - 1) / slab < num_sms()) slab >>= 1;
         const size_t smem = (size_t)a->B * slab * sizeof(float);   // <= 64 KB
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e2 = cudaFuncSetAttribute(small_linear_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_MAXB * SL_SLAB * (int)sizeof(float));
-            B200_REQUIRE(e2 == cudaSuccess, "small_linear_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
-            configured = true;
-        }
+        static DeviceOnce once;
+        cudaError_t e2 = set_max_smem_once(once, small_linear_bwd_x_kernel, SL_MAXB * SL_SLAB * (int)sizeof(float));
+        B200_REQUIRE(e2 == cudaSuccess, "small_linear_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
         B200_LAUNCH(small_linear_bwd_x_kernel, (a->N + slab - 1) / slab, 256, smem, st, *a, slab);
         return check_launch("small_linear_bwd_x_kernel");
     }
@@ -584,11 +578,8 @@ extern "C" int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream) 
     if (check_conv(a)) return -1;
     B200_REQUIRE(a->dy && a->dx && a->dweight && a->dbias, "dwconv_bwd: null pointer");
     const size_t smem = (size_t)(2 * CV_P1 + 30 + 32) * CV_TC * sizeof(float) + 128;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static DeviceOnce once;
+    B200_REQUIRE(set_max_smem_once(once, dwconv_bwd_kernel, (int)smem) == cudaSuccess, "dwconv_bwd: cudaFuncSetAttribute failed");
     const int ntiles = (a->Np + CV_TN - 1) / CV_TN;
     dim3 grid((ntiles + CV_TILES_PER_BLOCK - 1) / CV_TILES_PER_BLOCK, (a->D + CV_TC - 1) / CV_TC, a->B);
     B200_LAUNCH(dwconv_bwd_kernel, grid, 256, smem, reinterpret_cast<cudaStream_t>(stream), *a);
@@ -630,8 +621,8 @@ extern "C" int b200_melspec(const float* wave, const float* window, const float*
     B200_REQUIRE(n_fft >= 64 && (n_fft & (n_fft - 1)) == 0 && n_fft <= 4096 && hop > 0 && nw > n_fft / 2, "melspec: n_fft must be a power of two <= 4096 and the wave longer than n_fft/2");
     const int frames = 1 + nw / hop;
     const size_t smem = (size_t)(3 * n_fft + n_fft / 2 + 1) * sizeof(float);
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); configured = true; }
+    static DeviceOnce once;
+    B200_REQUIRE(set_max_smem_once(once, melspec_kernel, 64 * 1024) == cudaSuccess, "melspec: cudaFuncSetAttribute failed");
     B200_LAUNCH(melspec_kernel, dim3(frames, B), 256, smem, reinterpret_cast<cudaStream_t>(stream), wave, window, fb, out, nw, n_fft, hop, n_mels, frames);
     return check_launch("melspec_kernel");
 }

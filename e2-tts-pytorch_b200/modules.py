@@ -35,6 +35,22 @@ def default(v, d):
     return v if exists(v) else d
 
 
+def _on_module_device(fn):
+    """Run a public entry point with the CUDA device of the module's parameters current, so that the raw-pointer kernel launches
+    (ops.py: torch.cuda.current_stream()) go to that device's stream even when the process-wide current device is another GPU.
+    (Backward runs on the autograd engine's per-device threads, which set the device themselves.)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda' or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 def _unsupported(name, value, ref):
     raise NotImplementedError(
         f'{name}={value!r} is a non-default research switch of the reference ({ref}) for which no B200 kernel is built; '
@@ -323,6 +339,9 @@ class Transformer(Module):
         self._pack = None
         self._packed = None
         self._rot = {}
+        # optional int64 device word added to every dropout seed when the kernels RUN (include/b200_e2tts.h "dropout seeds"):
+        # set by GraphedTrainStep, whose captured graph would otherwise replay the same dropout masks on every step
+        self._seed_dev = None
 
     # ------------------------------------------------------------------ packed operands
     def _apply(self, fn, *a, **k):
@@ -331,8 +350,8 @@ class Transformer(Module):
         return out
 
     def __deepcopy__(self, memo):  # EMA(model) deep-copies the module (trainer.py:170-174): caches are per instance
-        pack, packed, rot = self._pack, self._packed, self._rot
-        self._pack, self._packed, self._rot = None, None, {}
+        pack, packed, rot, seed_dev = self._pack, self._packed, self._rot, self._seed_dev
+        self._pack, self._packed, self._rot, self._seed_dev = None, None, {}, None
         try:
             cls = self.__class__
             new = cls.__new__(cls)
@@ -341,7 +360,7 @@ class Transformer(Module):
             for k, v in self.__dict__.items():
                 new.__dict__[k] = copy.deepcopy(v, memo)
         finally:
-            self._pack, self._packed, self._rot = pack, packed, rot
+            self._pack, self._packed, self._rot, self._seed_dev = pack, packed, rot, seed_dev
         return new
 
     def _build_pack(self):
@@ -454,14 +473,14 @@ class Transformer(Module):
             og, v = ops.Attention.apply(br, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_v_head_gate.weight,
                                         attn.to_v_head_gate.bias, mix[0].weight if mix is not None else None,
                                         mix[0].bias if mix is not None else None, vf if mix is not None else None,
-                                        pk['qkv'], cs, sn, mask_u8, B, Np, H, p_drop, next_seed(), SOFTCLAMP)
+                                        pk['qkv'], cs, sn, mask_u8, B, Np, H, p_drop, next_seed(), SOFTCLAMP, self._seed_dev)
             y = ops.OutProj.apply(og, attn.to_out.weight, pk['out'], colscale, mask_u8, B, Np)
             return ops.HcDepth.apply(rest, y, beta), (v if vf is None else vf)
 
         def sub_ff(res, hcm, gain, mode, ff, pk, colscale):
             br, rest, beta = ops.HcWidth.apply(res, *hcm.params(), gain, mode, Np)
             y = ops.FeedForward.apply(br, ff.ff[0].proj.weight, ff.ff[0].proj.bias, ff.ff[2].weight, ff.ff[2].bias,
-                                      pk['w1'], pk['b1'], pk['w2'], colscale, B, Np, p_drop, next_seed())
+                                      pk['w1'], pk['b1'], pk['w2'], colscale, B, Np, p_drop, next_seed(), self._seed_dev)
             return ops.HcDepth.apply(rest, y, beta)
 
         for i, ((speech, text), (shc, thc)) in enumerate(zip(self.layers, self.hyper_conns)):
@@ -497,6 +516,7 @@ class Transformer(Module):
             mask_u8 = F.pad(mask, (self.num_registers, 0), value=True).to(torch.uint8).contiguous()
         return Np, mask_u8
 
+    @_on_module_device
     def forward(self, x, times=None, mask=None, text_embed=None):
         """Reference signature (e2_tts.py:731-737): x (b, n, d) -> (b, n, d)."""
         assert x.ndim == 3, '`has_freq_axis` is not supported by the B200 build'
@@ -633,6 +653,7 @@ class DurationPredictor(Module):
         self._wpack = None
         return out
 
+    @_on_module_device
     def forward(self, x, *, text=None, lens=None, return_loss=True):
         if x.ndim == 2:  # raw wave (:1052-1055; the reference's `== self.dim` assert is a known bug, Appendix C)
             x = self.mel_spec(x).transpose(1, 2)
@@ -781,6 +802,7 @@ class E2TTS(Module):
         y = self.transformer._forward_from_h(h, B, N, times, mask, text_ids=ids, text_embed_module=self.embed_text)
         return y, pk
 
+    @_on_module_device
     def transformer_with_pred_head(self, x, cond, times, mask=None, text=None, drop_text_cond=None, return_drop_text_cond=False):
         """e2_tts.py:1250-1301."""
         B, N, C = x.shape
@@ -807,10 +829,15 @@ class E2TTS(Module):
         return ops.cfg_combine(pred, null_pred, float(cfg_strength), bool(remove_parallel_component), float(keep_parallel_frac))
 
     @torch.no_grad()
+    @_on_module_device
     def sample(self, cond, *, text=None, lens=None, duration=None, steps=32, cfg_strength=1., cfg_null_model=None, max_duration=4096,
                vocoder=None, return_raw_output=None, save_to_filename=None):
         """e2_tts.py:1332-1466. Fixed-grid ODE on t = linspace(0, 1, steps) (torchdiffeq semantics)."""
         self.eval()
+        if not (exists(return_raw_output) and return_raw_output) and not exists(vocoder) and (self._use_vocos_requested or exists(save_to_filename)):
+            # fail BEFORE the ODE loop (124 transformer passes at the defaults), not after it
+            raise NotImplementedError('Vocos decoding / audio saving needs the pretrained vocoder from the HF hub and is out of scope '
+                                      '(SURVEY.md §2 row 10): call sample(..., return_raw_output=True), pass `vocoder=`, or build E2TTS(use_vocos=False)')
         if cond.ndim == 2:
             cond = self.mel_spec(cond).transpose(1, 2)
             assert cond.shape[-1] == self.num_channels
@@ -857,16 +884,12 @@ class E2TTS(Module):
             return out
         if exists(vocoder):
             return vocoder(out.transpose(1, 2))
-        if self._use_vocos_requested or exists(save_to_filename):
-            raise NotImplementedError('Vocos decoding / audio saving needs the pretrained vocoder from the HF hub and is out of scope '
-                                      '(SURVEY.md §2 row 10): call sample(..., return_raw_output=True) or pass `vocoder=`')
         return out
 
+    @_on_module_device
     def forward(self, inp, *, text=None, times=None, lens=None, velocity_consistency_model=None, velocity_consistency_delta=1e-5):
         """Flow-matching training objective, e2_tts.py:1468-1595. Returns E2TTSReturn(loss, cond, pred_flow, pred_data, breakdown)."""
         need_velocity_loss = exists(velocity_consistency_model) and self.velocity_consistency_weight > 0.
-        if need_velocity_loss:
-            _unsupported('velocity_consistency_model', 'set', 'e2_tts.py:1556-1576 ("next" row of SURVEY §8f)')
         if inp.ndim == 2:
             inp = self.mel_spec(inp).transpose(1, 2)
             assert inp.shape[-1] == self.num_channels
@@ -888,9 +911,20 @@ class E2TTS(Module):
         times = _rng.draw('times', lambda: torch.rand((B,), dtype=x1.dtype, device=dev))
         drop_text_cond = _rng.draw('drop_text_cond', lambda: self.training and pyrandom.random() < self.cond_drop_prob)
         span_u8 = rand_span_mask.to(torch.uint8).contiguous()
+        times = times.to(F32).contiguous()
+        vel_target = None
+        if need_velocity_loss:   # :1556-1576 — the EMA model's prediction at t + delta on the same (x0, x1, cond, text-drop coin), no grad
+            vcm = velocity_consistency_model
+            with torch.no_grad():
+                t_d = times + velocity_consistency_delta
+                vpk = vcm._packed()
+                A_d, _ = ops.stem_prepare(B, N, C, vpk['Cp'], x1=x1, x0=x0, times=t_d, span=span_u8)
+                y_d, vpk = vcm._embed(A_d, B, N, t_d, mask, text, drop_text_cond, vpk)
+                vel_target = ops.PredHead.apply(y_d, vcm.to_pred.weight, vcm.to_pred.bias, vpk['pred'])
         pk = self._packed()
-        A, cond = ops.stem_prepare(B, N, C, pk['Cp'], x1=x1, x0=x0, times=times.to(F32).contiguous(), span=span_u8, want_cond=True)
+        A, cond = ops.stem_prepare(B, N, C, pk['Cp'], x1=x1, x0=x0, times=times, span=span_u8, want_cond=True)
         y, pk = self._embed(A, B, N, times, mask, text, drop_text_cond, pk)
-        loss, pred, pred_data = ops.FlowLossHead.apply(y, self.to_pred.weight, self.to_pred.bias, pk['pred'], x1, x0, span_u8)
-        breakdown = LossBreakdown(loss, self.zero)
+        loss, pred, pred_data, parts = ops.FlowLossHead.apply(y, self.to_pred.weight, self.to_pred.bias, pk['pred'], x1, x0, span_u8, vel_target,
+                                                              float(self.velocity_consistency_weight) if need_velocity_loss else 0.0)
+        breakdown = LossBreakdown(parts[0], parts[1] if need_velocity_loss else self.zero)
         return E2TTSReturn(loss, cond, pred.view(B, N, C), pred_data.view(B, N, C), breakdown)

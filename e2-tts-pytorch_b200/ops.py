@@ -29,7 +29,7 @@ def _c(t):
 
 def gemm(A, B, M, N, K, *, lda=None, ldb=None, A2=None, lda2=0, K1=0, a_mn=False, b_mn=False, out=None, ldd=None,
          out_fp32=False, D2=None, ldd2=0, bias=None, colscale=None, rows_per_batch=0, rowmask=None, resid=None, ldr=0,
-         geglu=False, dropout_p=0.0, seed=0, split_k=1):
+         geglu=False, dropout_p=0.0, seed=0, split_k=1, force_tile=0, seed_dev=None):
     """D[M,N] = epilogue(sum_k A[m,k] B[n,k]) on the tcgen05 GEMM (include/b200_e2tts.h: b200_gemm)."""
     dev = A.device
     n_out = N // 2 if geglu else N
@@ -41,13 +41,13 @@ def gemm(A, B, M, N, K, *, lda=None, ldb=None, A2=None, lda2=0, K1=0, a_mn=False
         A, lda if lda is not None else (M if a_mn else K), A2, lda2, K1,
         B, ldb if ldb is not None else (N if b_mn else K), M, N, K, int(a_mn), int(b_mn),
         out, ldd, int(out_fp32), D2, ldd2, bias, colscale, rows_per_batch,
-        rowmask, resid, ldr, int(geglu), float(dropout_p), int(seed), int(split_k)))
+        rowmask, resid, ldr, int(geglu), float(dropout_p), int(seed), int(split_k), int(force_tile), seed_dev))
     lib.call('b200_gemm', args, _stream())
     return out
 
 
 _GEMM_FIELDS = ('A', 'lda', 'A2', 'lda2', 'K1', 'B', 'ldb', 'M', 'N', 'K', 'a_mn_major', 'b_mn_major', 'D', 'ldd', 'd_fp32', 'D2', 'ldd2',
-                'bias', 'colscale', 'rows_per_batch', 'rowmask', 'resid', 'ldr', 'geglu', 'dropout_p', 'seed', 'split_k')
+                'bias', 'colscale', 'rows_per_batch', 'rowmask', 'resid', 'ldr', 'geglu', 'dropout_p', 'seed', 'split_k', 'force_tile', 'seed_dev')
 
 
 def _split_for(M, N, K):
@@ -234,24 +234,24 @@ class AttnCore(Function):
     """Softclamped, key-masked, head-gated flash attention (A.4 steps 4-5). Returns the gated, head-merged output."""
 
     @staticmethod
-    def forward(ctx, q, k, v, gate, mask, dropout_p, seed, softclamp):
+    def forward(ctx, q, k, v, gate, mask, dropout_p, seed, softclamp, seed_dev):
         B, H, Np, dh = q.shape
         o = torch.empty_like(q)
         og = torch.empty((B * Np, H * dh), device=q.device, dtype=BF16)
         lse = torch.empty((B, H, Np), device=q.device, dtype=F32)
         ws = torch.empty(((Np + 127) // 128) * 4 * B, device=q.device, dtype=torch.int32)
         a = lib.make_args('b200_attn_fwd_args', q=q, k=k, v=v, keymask=mask, gate=gate, o=o, og=og, lse=lse, B=B, H=H, Np=Np,
-                          dim_head=dh, scale=dh ** -0.5, softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws)
+                          dim_head=dh, scale=dh ** -0.5, softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws, seed_dev=seed_dev)
         lib.call(ATTN_FWD_ENTRY, a, _stream())
         ctx.save_for_backward(q, k, v, gate, mask, o, lse)
-        ctx.meta = (dropout_p, seed, softclamp)
+        ctx.meta = (dropout_p, seed, softclamp, seed_dev)
         return og
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_og):
         q, k, v, gate, mask, o, lse = ctx.saved_tensors
-        dropout_p, seed, softclamp = ctx.meta
+        dropout_p, seed, softclamp, seed_dev = ctx.meta
         B, H, Np, dh = q.shape
         legacy = ATTN_BWD_ENTRY.endswith('legacy')
         dq = torch.empty(q.shape, device=q.device, dtype=BF16 if legacy else F32)   # tcgen05 backward accumulates dq in fp32
@@ -261,9 +261,9 @@ class AttnCore(Function):
         ws = torch.empty(((Np + 127) // 128) * 4 * B, device=q.device, dtype=torch.int32)
         a = lib.make_args('b200_attn_bwd_args', q=q, k=k, v=v, o=o, d_og=_c(d_og), keymask=mask, gate=gate, lse=lse, ws_dO=ws_dO,
                           ws_delta=ws_delta, d_gate=d_gate, dq=dq, dk=dk, dv=dv, B=B, H=H, Np=Np, dim_head=dh, scale=dh ** -0.5,
-                          softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws)
+                          softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws, seed_dev=seed_dev)
         lib.call(ATTN_BWD_ENTRY, a, _stream())
-        return dq, dk, dv, d_gate, None, None, None, None
+        return dq, dk, dv, d_gate, None, None, None, None, None
 
 
 class Attention(Function):
@@ -273,7 +273,7 @@ class Attention(Function):
     One autograd node: q/k/v never enter the graph, and dq stays fp32 from the attention backward into the rotary inverse."""
 
     @staticmethod
-    def forward(ctx, xn, wq, wk, wv, wg, bg, wm, bm, v_first, wpack, cs, sn, mask, B, Np, H, dropout_p, seed, softclamp):
+    def forward(ctx, xn, wq, wk, wv, wg, bg, wm, bm, v_first, wpack, cs, sn, mask, B, Np, H, dropout_p, seed, softclamp, seed_dev):
         T, Din = xn.shape
         I = H * 64
         dev = xn.device
@@ -291,17 +291,17 @@ class Attention(Function):
         lse = torch.empty((B, H, Np), device=dev, dtype=F32)
         ws = torch.empty(((Np + 127) // 128) * 4 * B, device=dev, dtype=torch.int32)
         a = lib.make_args('b200_attn_fwd_args', q=q, k=k, v=v, keymask=mask, gate=gate, o=o, og=og, lse=lse, B=B, H=H, Np=Np,
-                          dim_head=64, scale=0.125, softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws)
+                          dim_head=64, scale=0.125, softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws, seed_dev=seed_dev)
         lib.call(ATTN_FWD_ENTRY, a, _stream())
         ctx.save_for_backward(xn, qkvg, gate, v_first, wpack, cs, sn, bg, bm, q, k, v, o, lse, mask)
-        ctx.meta = (B, Np, H, ncat, ld, has_mix, dropout_p, seed, softclamp)
+        ctx.meta = (B, Np, H, ncat, ld, has_mix, dropout_p, seed, softclamp, seed_dev)
         return og, v
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_og, d_v_extra):
         xn, qkvg, gate, v_first, wpack, cs, sn, bg, bm, q, k, v, o, lse, mask = ctx.saved_tensors
-        B, Np, H, ncat, ld, has_mix, dropout_p, seed, softclamp = ctx.meta
+        B, Np, H, ncat, ld, has_mix, dropout_p, seed, softclamp, seed_dev = ctx.meta
         T, Din = xn.shape
         I = H * 64
         dev = xn.device
@@ -313,7 +313,7 @@ class Attention(Function):
         ws = torch.empty(((Np + 127) // 128) * 4 * B, device=dev, dtype=torch.int32)
         a = lib.make_args('b200_attn_bwd_args', q=q, k=k, v=v, o=o, d_og=_c(d_og), keymask=mask, gate=gate, lse=lse, ws_dO=ws_dO,
                           ws_delta=ws_delta, d_gate=d_gate, dq=dq, dk=dk, dv=dv, B=B, H=H, Np=Np, dim_head=64, scale=0.125,
-                          softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws)
+                          softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws, seed_dev=seed_dev)
         lib.call(ATTN_BWD_ENTRY, a, _stream())
         d_qkvg = torch.empty((T, ld), device=dev, dtype=BF16)
         d_vfirst = torch.empty_like(v_first) if v_first is not None else None
@@ -326,7 +326,7 @@ class Attention(Function):
         db = colsum(d_qkvg[:, 3 * I:], T, ld - 3 * I, ld)   # only the head-gate / value-residual-mix logits have biases
         return (dx, dW[:I], dW[I:2 * I], dW[2 * I:3 * I], dW[3 * I:3 * I + H], db[:H],
                 dW[3 * I + H:3 * I + 2 * H] if has_mix else None, db[H:2 * H] if has_mix else None,
-                d_vfirst, None, None, None, None, None, None, None, None, None, None)
+                d_vfirst, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def _rowgate_bwd(dy, y, cs, mask, B, rpb, D, want_bias=False):
@@ -369,21 +369,21 @@ class FeedForward(Function):
     """x-transformers FeedForward(glu=True) (A.2): GEGLU GEMM (+dropout) -> out GEMM (+bias, AdaLNZero gate)."""
 
     @staticmethod
-    def forward(ctx, xn, w1, b1, w2, b2, w1pack, b1pack, w2pack, colscale, B, Np, dropout_p, seed):
+    def forward(ctx, xn, w1, b1, w2, b2, w1pack, b1pack, w2pack, colscale, B, Np, dropout_p, seed, seed_dev):
         T, Din = xn.shape
         inner = w2.shape[1]
         ug = torch.empty((T, 2 * inner), device=xn.device, dtype=BF16)
-        h = gemm(xn, w1pack, T, 2 * inner, Din, D2=ug, ldd2=2 * inner, bias=b1pack, geglu=True, dropout_p=dropout_p, seed=seed)
+        h = gemm(xn, w1pack, T, 2 * inner, Din, D2=ug, ldd2=2 * inner, bias=b1pack, geglu=True, dropout_p=dropout_p, seed=seed, seed_dev=seed_dev)
         y = gemm(h, w2pack, T, Din, inner, bias=b2, colscale=colscale, rows_per_batch=Np)
         ctx.save_for_backward(xn, ug, h, y, w1pack, w2pack, colscale)
-        ctx.meta = (B, Np, dropout_p, seed, inner)
+        ctx.meta = (B, Np, dropout_p, seed, inner, seed_dev)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         xn, ug, h, y, w1pack, w2pack, colscale = ctx.saved_tensors
-        B, Np, dropout_p, seed, inner = ctx.meta
+        B, Np, dropout_p, seed, inner, seed_dev = ctx.meta
         T, Din = xn.shape
         if colscale is not None:
             # y = cs * (h W2^T + b2): recover the pre-gate value through y / cs inside the kernel
@@ -395,13 +395,13 @@ class FeedForward(Function):
         dW2 = grad_weight(dz, h, T, Din, inner)
         dug = torch.empty_like(ug)
         db1p = torch.zeros(2 * inner, device=xn.device, dtype=F32)
-        lib.call('b200_geglu_bwd', dh, ug, dug, db1p, T, inner, float(dropout_p), int(seed), _stream())
+        lib.call('b200_geglu_bwd', dh, ug, dug, db1p, T, inner, float(dropout_p), int(seed), seed_dev, _stream())
         dx = gemm(dug, w1pack, T, Din, 2 * inner, b_mn=True)
         dW1p = grad_weight(dug, xn, T, 2 * inner, Din)
         nb = inner // 64
         dW1 = dW1p.view(nb, 2, 64, Din).transpose(0, 1).reshape(2 * inner, Din)   # undo the GEGLU interleave (layout only)
         db1 = db1p.view(nb, 2, 64).transpose(0, 1).reshape(2 * inner)
-        return dx, dW1, db1, dW2, db2, None, None, None, d_cs, None, None, None, None
+        return dx, dW1, db1, dW2, db2, None, None, None, d_cs, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------- cross-stream GEMMs
@@ -622,37 +622,45 @@ class PredHead(Function):
 
 
 class FlowLossHead(Function):
-    """to_pred + masked-MSE flow-matching loss fused at the output stage (e2_tts.py:1296, 1535, 1580-1582, 1595).
-    Returns (loss, pred fp32 [B,N,C], pred_data = x0 + pred); only `loss` is differentiable."""
+    """to_pred + masked-MSE flow-matching loss fused at the output stage (e2_tts.py:1296, 1535, 1580-1582, 1595), optionally with the
+    velocity-consistency term against `vel_target` (:1556-1576, the EMA model's no-grad prediction at t + delta).
+    Returns (loss, pred fp32 [B,N,C], pred_data = x0 + pred, parts = [flow, velocity]); only `loss` is differentiable."""
 
     @staticmethod
-    def forward(ctx, y, w, b, wpack, x1, x0, span):
+    def forward(ctx, y, w, b, wpack, x1, x0, span, vel_target, vel_weight):
         T, D = y.shape
         C = w.shape[0]
         pred = gemm(y, wpack, T, C, D, bias=b, out_fp32=True, ldd=C)
-        sums = torch.empty(2, device=y.device, dtype=F32)
+        return FlowLossHead._loss(ctx, y, wpack, pred, x1, x0, span, vel_target, vel_weight, C)
+
+    @staticmethod
+    def _loss(ctx, y, wpack, pred, x1, x0, span, vel_target, vel_weight, C):
+        T = pred.shape[0]
+        sums = torch.empty(4, device=y.device, dtype=F32)
         loss = torch.empty((), device=y.device, dtype=F32)
+        parts = torch.empty(2, device=y.device, dtype=F32)
         pred_data = torch.empty_like(pred)
-        a = lib.make_args('b200_flow_loss_args', pred=pred, x1=x1, x0=x0, span=span, sums=sums, loss=loss, pred_data=pred_data, rows=T, C=C)
+        a = lib.make_args('b200_flow_loss_args', pred=pred, x1=x1, x0=x0, span=span, sums=sums, loss=loss, pred_data=pred_data, rows=T, C=C,
+                          vel_target=_c(vel_target), vel_weight=float(vel_weight), loss_parts=parts)
         lib.call('b200_flow_loss_fwd', a, _stream())
-        ctx.save_for_backward(y, wpack, pred, x1, x0, span, sums)
-        ctx.C = C
-        ctx.mark_non_differentiable(pred, pred_data)
-        return loss, pred, pred_data
+        ctx.save_for_backward(y, wpack, pred, x1, x0, span, sums, vel_target)
+        ctx.C, ctx.vel_weight = C, float(vel_weight)
+        ctx.mark_non_differentiable(pred, pred_data, parts)
+        return loss, pred, pred_data, parts
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dloss, _dpred, _dpd):
-        y, wpack, pred, x1, x0, span, sums = ctx.saved_tensors
+    def backward(ctx, dloss, _dpred, _dpd, _dparts):
+        y, wpack, pred, x1, x0, span, sums, vel_target = ctx.saved_tensors
         T, D = y.shape
         C = ctx.C
         ldp = (C + 7) // 8 * 8
         dp = torch.empty((T, ldp), device=y.device, dtype=BF16)
         a = lib.make_args('b200_flow_loss_args', pred=pred, x1=x1, x0=x0, span=span, sums=sums, dloss=_c(dloss.to(F32)), dpred=dp, ldp=ldp,
-                          rows=T, C=C)
+                          rows=T, C=C, vel_target=_c(vel_target), vel_weight=ctx.vel_weight)
         lib.call('b200_flow_loss_bwd', a, _stream())
         dy, dW, db, _ = PredHead._bwd_from_bf16(dp, ldp, y, wpack, T, D, C)
-        return dy, dW, db, None, None, None, None
+        return dy, dW, db, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------- conditioning path

@@ -66,14 +66,17 @@ typedef struct {
     int32_t split_k;
     int32_t force_tile;   /* 0 = auto, 1 = 128 x 128 CTA tiles, 2 = 256 x 128 CTA tiles (two MMAs per k-step share one B tile),
                            * 3 = CTA pair (cta_group::2): 2 x (128 x 256), each CTA stages half of the B tile; auto picks it for M >= 512, N >= 256 */
+    const uint64_t* seed_dev;   /* optional DEVICE word added to `seed` when the kernel runs (see "dropout seeds" below); NULL = none */
 } b200_gemm_args;
 int b200_gemm(const b200_gemm_args* a, b200_stream_t stream);
 
-/* Optional device-resident addend of every dropout seed (GEGLU dropout in b200_gemm / b200_geglu_bwd, attention dropout):
- * effective seed = args.seed + *dev_seed. A captured CUDA graph freezes kernel arguments, so the per-step randomness of a graphed
- * training step (e2_tts_pytorch_b200.GraphedTrainStep; the reference draws a fresh torch RNG state every step, trainer.py) comes from
- * this one device word, rewritten before each replay. The pointer is sampled at launch (process-global); NULL (default) disables it. */
-int b200_set_dropout_seed_device(const uint64_t* dev_seed);
+/* Dropout seeds. Every seeded entry point (GEGLU dropout in b200_gemm / b200_geglu_bwd, attention dropout) takes a host `seed`
+ * (a kernel ARGUMENT) and an optional `seed_dev`: a DEVICE word read when the kernel runs, effective seed = seed + *seed_dev.
+ * A captured CUDA graph freezes kernel arguments, so the per-step randomness of a graphed training step
+ * (e2_tts_pytorch_b200.GraphedTrainStep; the reference draws a fresh torch RNG state every step, trainer.py:263) comes from that
+ * one word, which b200_seed_advance() steps in stream order as the first node of the graph. The pointer travels in the args of
+ * each call (the library keeps no pointer after a call returns: two models, or two threads capturing at once, cannot interfere). */
+int b200_seed_advance(uint64_t* seed_dev, b200_stream_t stream);   /* *seed_dev = splitmix64 step of *seed_dev (one thread) */
 
 /* ------------------------------------------------------------------------------------------------
  * Fused softclamped attention, head_dim 64 (x-transformers Attend as configured by the reference: A.4
@@ -92,6 +95,7 @@ typedef struct {
     float scale, softclamp, dropout_p;
     uint64_t seed;
     void* ws_maskbits;   /* workspace of b200_attn_workspace_bytes(B, Np) bytes (key-validity bitmask built by the call) */
+    const uint64_t* seed_dev;   /* optional device addend of `seed` (dropout seeds, above) */
 } b200_attn_fwd_args;
 size_t b200_attn_workspace_bytes(int32_t B, int32_t Np);
 int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream);        /* tcgen05 / TMEM / TMA kernel */
@@ -111,6 +115,7 @@ typedef struct {
     float scale, softclamp, dropout_p;
     uint64_t seed;
     void* ws_maskbits;
+    const uint64_t* seed_dev;   /* optional device addend of `seed` (must be the forward's) */
 } b200_attn_bwd_args;
 int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream);         /* tcgen05 / TMEM / TMA kernel, dq fp32 */
 int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t stream);  /* mma.sync bring-up kernels, dq bf16 */
@@ -212,7 +217,7 @@ int b200_qkv_post_bwd(const b200_qkv_post_args* a, b200_stream_t stream);
 /* GEGLU backward on the packed pre-activations saved by b200_gemm(geglu=1) (A.2); db_packed (fp32 [2*inner], packed order,
  * zeroed by the caller, may be NULL) receives the bias gradient of the GLU projection in the same pass. */
 int b200_geglu_bwd(const void* dh, const void* ug, void* dug, float* db_packed, int64_t T, int32_t inner, float dropout_p, uint64_t seed,
-                   b200_stream_t stream);
+                   const uint64_t* seed_dev, b200_stream_t stream);
 /* out[n] += sum_t X[t,n] (bf16 X, fp32 out; caller zeroes out) — nn.Linear bias gradients. */
 int b200_colsum(const void* X, int64_t T, int32_t ncols, int32_t ld, float* out, b200_stream_t stream);
 
@@ -226,13 +231,17 @@ int b200_final_norm_fwd(const b200_final_norm_args* a, b200_stream_t stream);
 int b200_final_norm_bwd(const b200_final_norm_args* a, b200_stream_t stream);
 
 /* Masked-MSE flow-matching loss (e2_tts.py:1535, 1580-1582, 1595) without the boolean gather / host sync:
- * loss = sum_{span}(pred - (x1 - x0))^2 / (count * C); pred_data = x0 + pred. sums is a 2-float workspace that
- * must be kept for backward; dpred is bf16 [rows, ldp] (pad columns zero) = dloss * 2 (pred - flow) / (count*C). */
+ * flow = sum_{span}(pred - (x1 - x0))^2 / (count * C); pred_data = x0 + pred. sums is a 4-float workspace that
+ * must be kept for backward; dpred is bf16 [rows, ldp] (pad columns zero) = dloss * d(loss)/d(pred).
+ * Velocity-consistency term (e2_tts.py:1556-1576, 1586-1589), when vel_target != NULL (the EMA model's no-grad prediction at
+ * t + delta, fp32 [rows, C]):  velocity = sum_{span}(pred - vel_target)^2 / (count * C),  loss = flow + vel_weight * velocity;
+ * loss_parts (optional, 2 floats) receives {flow, velocity} for the reference's LossBreakdown. */
 typedef struct {
     const float *pred, *x1, *x0; const uint8_t* span;
     float *sums, *loss, *pred_data;
     const float* dloss; void* dpred; int32_t ldp;
     int64_t rows; int32_t C;
+    const float* vel_target; float vel_weight; float* loss_parts;
 } b200_flow_loss_args;
 int b200_flow_loss_fwd(const b200_flow_loss_args* a, b200_stream_t stream);
 int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t stream);
@@ -285,6 +294,46 @@ int b200_cfg_combine(const float* pred, const float* null_pred, double* ws_red, 
 /* MelSpec (e2_tts.py:248-290): wave fp32 [B, nw] -> log-mel fp32 [B, n_mels, 1 + nw/hop]; window [n_fft], fb [n_fft/2+1, n_mels]. */
 int b200_melspec(const float* wave, const float* window, const float* fb, float* out, int32_t B, int32_t nw, int32_t n_fft,
                  int32_t hop, int32_t n_mels, b200_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Around the forward/backward step: multi-tensor gradient gather for ONE ncclAllReduce per step, global
+ * gradient norm, and a fused clip + Adopt + EMA update. Parameters stay separate fp32 tensors (the reference's nn.Parameters);
+ * gradients, optimizer state (m, v) and the EMA copy are flat fp32 buffers owned by the caller, addressed through a chunk table:
+ * one entry per piece (<= 65536 elements) of a parameter, `ptr` = that piece inside the parameter (or its gradient tensor),
+ * `flat_offset` = its element offset in the flat buffers (multiples of 4 keep the 16-byte vector path). One CTA per chunk.
+ */
+typedef struct { void* ptr; int64_t flat_offset; int32_t n; int32_t pidx; /* index of the parameter this piece belongs to */ } b200_chunk;
+/* flat[flat_offset + i] = scale * ptr[i]; a NULL ptr (no gradient this step: the text stream when the text is dropped,
+ * trainer.py:155 find_unused_parameters) zero-fills its slot. scale = 1/world_size gives DDP's gradient averaging (trainer.py:270).
+ * used (optional, fp32 [n_params]): used[pidx] = 1 if the parameter had a gradient else 0 — summed by the same all-reduce when it
+ * lies right behind the gradients, it tells the optimiser which parameters no rank touched (torch optimisers skip grad=None). */
+int b200_flat_gather(const b200_chunk* chunks_dev, int32_t n_chunks, float* flat, float scale, float* used, b200_stream_t stream);
+/* ptr[i] = flat[flat_offset + i] (e.g. EMA weights into a module's parameters) */
+int b200_flat_scatter(const b200_chunk* chunks_dev, int32_t n_chunks, const float* flat, b200_stream_t stream);
+/* *out = sum x[i]^2 (out: ONE device float, zeroed by the call): torch.nn.utils.clip_grad_norm_'s total norm, trainer.py:272-273 */
+int b200_sumsq(const float* x, int64_t n, float* out, b200_stream_t stream);
+/* One pass over every parameter (trainer.py:272-279):
+ *   g    = grad * min(1, max_grad_norm / (sqrt(*gradnorm_sq) + 1e-6))        (clip_grad_norm_; skipped when gradnorm_sq == NULL)
+ *   w   *= 1 - lr * weight_decay                                              (Adopt's decoupled weight decay, when > 0)
+ *   first gradient of a parameter : v = g^2, m = 0, parameter untouched     (Adopt initialises its state on first sight)
+ *   afterwards                    : m += (1-beta1) (g / max(sqrt(v), eps) - m);  w -= lr m;  v += (1-beta2) (g^2 - v)
+ *   ("first" is tracked per chunk in chunk_state (int32 [n_chunks], zeroed once by the caller): a parameter that received no
+ *   gradient on the first steps — the text stream while the text is dropped — is initialised when its first gradient arrives)
+ *   ema_mode 1: ema += ema_weight (w - ema)   (ema-pytorch lerp, ema_weight = 1 - current decay);  2: ema = w (copy phase);  0: none
+ * Adopt = adam-atan2-pytorch's `Adopt` (pyproject.toml:26, call site trainer.py:183) — the package is not under /root/reference;
+ * restated from the ADOPT algorithm it implements (Taniguchi et al. 2024, Alg. 2 without clipping) and pinned by a PyTorch
+ * restatement in oracle/optim_oracle.py. chunk.ptr = the parameter piece. */
+typedef struct {
+    const b200_chunk* chunks_dev; int32_t n_chunks;
+    const float* grad_flat; float *m_flat, *v_flat, *ema_flat;
+    const float* gradnorm_sq; float max_grad_norm;
+    float lr, beta1, beta2, eps, weight_decay;
+    int32_t* chunk_state;
+    int32_t ema_mode; float ema_weight;
+    const float* used;   /* optional fp32 [n_params]: parameters with used[pidx] == 0 keep w, m, v (only their EMA moves) */
+} b200_adopt_args;
+int b200_adopt_step(const b200_adopt_args* a, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -60,6 +60,22 @@ class TransformerCfg:
 
 
 # --------------------------------------------------------------------------------------------------
+# Conditioning probe (test infrastructure): STAGE_ROUND, when set, is applied to every stage output that the CUDA path
+# stores in bf16 (hyper-connection branch / residual streams, conv / attention / feed-forward outputs, cross-condition and
+# skip outputs) with a straight-through gradient. tests use it to tell a badly conditioned golden (the fp32 oracle's own
+# gradients move when its activations are rounded) from a kernel bug. None (default) = exact fp32 oracle.
+STAGE_ROUND = None
+
+
+def bf16_ste(x):
+    return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+
+def _rs(x):
+    return x if STAGE_ROUND is None or x is None else STAGE_ROUND(x)
+
+
+# --------------------------------------------------------------------------------------------------
 # helpers (:113-124, :173-235)
 
 
@@ -162,11 +178,11 @@ def hyper_width(sd, p, res, S):  # A.5 width connection on (b, n, S, d)
     alpha = torch.tanh(normed @ sd[p + '.dynamic_alpha_fn']) * sd[p + '.dynamic_alpha_scale'] + sd[p + '.static_alpha']
     beta = torch.tanh(normed @ sd[p + '.dynamic_beta_fn']) * sd[p + '.dynamic_beta_scale'] + sd[p + '.static_beta']
     mix = torch.einsum('bnst,bnsd->bntd', alpha, res)
-    return mix[..., 0, :], mix[..., 1:, :], beta
+    return mix[..., 0, :], _rs(mix[..., 1:, :]), beta
 
 
 def hyper_depth(rest, beta, y):  # A.5 depth connection
-    return y[..., None, :] * beta[..., None] + rest
+    return _rs(_rs(y)[..., None, :] * beta[..., None] + rest)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -208,8 +224,8 @@ def transformer_forward(sd, cfg: TransformerCfg, x, times=None, mask=None, text_
     def norm(prefix_key, h):  # rmsnorm_klass :615 (AdaptiveRMSNorm when cond_on_time)
         if cfg.cond_on_time:
             gamma = cond @ sd[prefix_key + '.to_gamma.weight'].t()
-            return F.normalize(h, dim=-1) * d ** 0.5 * (gamma[:, None, :] + 1.0)
-        return rmsnorm(h, sd[prefix_key + '.g'])
+            return _rs(F.normalize(h, dim=-1) * d ** 0.5 * (gamma[:, None, :] + 1.0))
+        return _rs(rmsnorm(h, sd[prefix_key + '.g']))
 
     def post(prefix_key, h):  # postbranch_klass :616 (AdaLNZero when cond_on_time)
         if cfg.cond_on_time:
@@ -225,28 +241,28 @@ def transformer_forward(sd, cfg: TransformerCfg, x, times=None, mask=None, text_
         if has_text and i < cfg.text_depth:  # :853-883
             tp = lp + '.1'
             br, rest, beta = hyper_width(sd, hp + '.1.0', ts, S)
-            ts = hyper_depth(rest, beta, depthwise_conv(sd, tp + '.0', br, mask))
+            ts = hyper_depth(rest, beta, depthwise_conv(sd, tp + '.0', _rs(br), mask))
             br, rest, beta = hyper_width(sd, hp + '.1.1', ts, S)
-            out, vals = attention(sd, tp + '.2', rmsnorm(br, sd[tp + '.1.g']), mask, freqs, text_attn_first,
+            out, vals = attention(sd, tp + '.2', _rs(rmsnorm(br, sd[tp + '.1.g'])), mask, freqs, text_attn_first,
                                   cfg.heads, cfg.dim_head, cfg.softclamp)
             ts = hyper_depth(rest, beta, out)
             text_attn_first = vals if text_attn_first is None else text_attn_first
             br, rest, beta = hyper_width(sd, hp + '.1.2', ts, S)
-            ts = hyper_depth(rest, beta, feedforward(sd, tp + '.4', rmsnorm(br, sd[tp + '.3.g'])))
+            ts = hyper_depth(rest, beta, feedforward(sd, tp + '.4', _rs(rmsnorm(br, sd[tp + '.3.g']))))
             at = torch.cat((xs, ts), dim=-1)  # :508-513 on every stream
-            xs_new = xs + at @ sd[tp + '.5.text_to_audio.weight'].t()
+            xs_new = _rs(xs + at @ sd[tp + '.5.text_to_audio.weight'].t())
             if (tp + '.5.audio_to_text.weight') in sd:
-                ts = ts + at @ sd[tp + '.5.audio_to_text.weight'].t()
+                ts = _rs(ts + at @ sd[tp + '.5.audio_to_text.weight'].t())
             xs = xs_new
 
         if (i + 1) <= L // 2:  # :887-896
             skips.append(xs)
         else:
-            xs = torch.cat((xs, skips.pop()), dim=-1) @ sd[lp + '.0.0.weight'].t()
+            xs = _rs(torch.cat((xs, skips.pop()), dim=-1) @ sd[lp + '.0.0.weight'].t())
 
         sp = lp + '.0'
         br, rest, beta = hyper_width(sd, hp + '.0.0', xs, S)  # :900-902
-        xs = hyper_depth(rest, beta, depthwise_conv(sd, sp + '.1', br, mask))
+        xs = hyper_depth(rest, beta, depthwise_conv(sd, sp + '.1', _rs(br), mask))
         br, rest, beta = hyper_width(sd, hp + '.0.1', xs, S)  # :906-916
         out, vals = attention(sd, sp + '.3', norm(sp + '.2', br), mask, freqs, attn_first,
                               cfg.heads, cfg.dim_head, cfg.softclamp)
@@ -282,9 +298,11 @@ def transformer_with_pred_head(sd, cfg, x, cond, times, mask, text, drop_text_co
     return emb @ sd['to_pred.weight'].t() + sd['to_pred.bias']
 
 
-def e2tts_forward(sd, cfg, mel, text, *, x0, times, span_mask, lens=None, drop_text_cond=False):
+def e2tts_forward(sd, cfg, mel, text, *, x0, times, span_mask, lens=None, drop_text_cond=False, velocity_sd=None,
+                  velocity_consistency_weight=0.0, velocity_consistency_delta=1e-5):
     """E2TTS.forward :1468-1595 with the random draws (x0 :1519, times :1523, span mask :1504-1508)
-    injected. Returns dict(loss, cond, pred, pred_data)."""
+    injected. Returns dict(loss, cond, pred, pred_data, flow_loss, velocity_loss). `velocity_sd` = state_dict of the
+    velocity-consistency (EMA) model, :1556-1576."""
     b, n, _ = mel.shape
     if lens is None:
         lens = torch.full((b,), n, device=mel.device)
@@ -296,7 +314,15 @@ def e2tts_forward(sd, cfg, mel, text, *, x0, times, span_mask, lens=None, drop_t
     cond = torch.where(span_mask[..., None], torch.zeros_like(mel), mel)  # :1539-1543
     pred = transformer_with_pred_head(sd, cfg, w, cond, times, mask, text, drop_text_cond)
     loss = ((pred - flow) ** 2)[span_mask].mean()  # :1580-1582
-    return dict(loss=loss, cond=cond, pred=pred, pred_data=x0 + pred)
+    velocity_loss = torch.zeros(())
+    if velocity_sd is not None and velocity_consistency_weight > 0.0:  # :1556-1576
+        td = times + velocity_consistency_delta
+        w_d = (1.0 - td[:, None, None]) * x0 + td[:, None, None] * mel
+        with torch.no_grad():
+            ema_pred = transformer_with_pred_head(velocity_sd, cfg, w_d, cond, td, mask, text, drop_text_cond)
+        velocity_loss = ((pred - ema_pred) ** 2)[span_mask].mean()
+    total = loss + velocity_loss * velocity_consistency_weight  # :1586-1589
+    return dict(loss=total, cond=cond, pred=pred, pred_data=x0 + pred, flow_loss=loss, velocity_loss=velocity_loss)
 
 
 def cfg_pred(sd, cfg, x, cond, times, mask, text, cfg_strength=1.0):  # :1303-1330

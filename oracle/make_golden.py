@@ -11,7 +11,8 @@ Fixtures (fp32, torch.save):
                        cond, parameter grads (full for the text-conditioned case, (norm,sum) per parameter for
                        the text-dropped case)
   sample_d128_L2.pt    E2TTS.sample 4-step midpoint end point (cfg_strength 1 -> cond + null pass + APG)
-  duration_d128_L2.pt  DurationPredictor fwd+bwd loss + per-parameter grad (norm,sum), and return_loss=False prediction
+  duration_d128_L2.pt  DurationPredictor fwd+bwd (B=4, a prefix draw chosen for conditioning, see below): loss, full parameter
+                       grads, and the return_loss=False prediction
   melspec.pt           MelSpec(wave) from torchaudio through the reference module
 """
 import os
@@ -76,22 +77,55 @@ def main():
     torch.save(dict(cond=cond, text_ids=text_ids, duration=64, steps=4, cfg_strength=1.0, y0=holder['y0'], out=smp),
                os.path.join(OUT, 'sample_d128_L2.pt'))
 
-    # DurationPredictor
+    # DurationPredictor. The loss reaches the backbone through a masked mean over a RANDOM PREFIX of every sequence
+    # (e2_tts.py:1081-1086); with a short prefix the gradients of a few first-text-layer parameters are sums of nearly
+    # cancelling terms, and rounding the fp32 oracle's OWN stage outputs to bf16 (O.STAGE_ROUND) flips them (round-1 fixture:
+    # cosine 0.59 / -1.0 against itself). A bf16 path cannot be judged on such a case, so the fixture is minted on the first
+    # torch seed whose prefix draw is well conditioned under that probe (every per-parameter cosine >= 0.997).
     torch.manual_seed(1)
     dp = ref.DurationPredictor(transformer=dict(**REF_TKW))
     dsd = O.randomize_zero_init(dp.state_dict(), seed=13)
     dp.load_state_dict(dsd)
-    torch.manual_seed(5)
-    loss = dp(mel, text=TEXT, lens=lens)
+    torch.manual_seed(21)
+    dmel = torch.randn(4, 96, 100)
+    dlens = torch.tensor([96, 70, 88, 80])
+    dtext = ['Hello', 'Goodbye', 'Good morning', 'Hi']
+    dtext_ids = O.list_str_to_tensor(dtext)
+
+    def conditioning(rand_frac):
+        res = []
+        for rnd in (None, O.bf16_ste):
+            O.STAGE_ROUND = rnd
+            try:
+                sdo = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in dsd.items()}
+                O.duration_forward(sdo, O.TransformerCfg(cond_on_time=False, **TKW), dmel, dtext_ids, lens=dlens, rand_frac=rand_frac).backward()
+            finally:
+                O.STAGE_ROUND = None
+            res.append({k: v.grad.double().flatten() for k, v in sdo.items() if v.grad is not None})
+        total = torch.cat(list(res[0].values())).norm()
+        worst = 1.0
+        for k, a in res[0].items():
+            if a.norm() >= 1e-4 * total:
+                worst = min(worst, float(a @ res[1][k] / (a.norm() * res[1][k].norm() + 1e-30)))
+        return worst
+
+    for dseed in range(5, 200):
+        torch.manual_seed(dseed)
+        rand_frac = dmel.new_zeros(4).uniform_(0, 1)  # e2_tts.py:1082 draws exactly this after the seed
+        if float(rand_frac.min()) >= 0.5 and conditioning(rand_frac) >= 0.997:
+            break
+    else:
+        raise RuntimeError('no well-conditioned prefix draw found')
+    print('duration fixture: seed', dseed, 'rand_frac', rand_frac.tolist())
+    torch.manual_seed(dseed)
+    loss = dp(dmel, text=dtext, lens=dlens)
     loss.backward()
-    torch.manual_seed(5)
-    rand_frac = mel.new_zeros(2).uniform_(0, 1)  # e2_tts.py:1082
-    dgrads = {k: torch.stack((p.grad.norm(), p.grad.sum())) for k, p in dp.named_parameters() if p.grad is not None}
+    dgrads = {k: p.grad.clone() for k, p in dp.named_parameters() if p.grad is not None}
     dp.eval()
     with torch.no_grad():
-        pred = dp(mel, text=TEXT, lens=lens, return_loss=False)
-    torch.save(dict(state_dict={k: v.clone() for k, v in dp.state_dict().items()}, mel=mel, text_ids=text_ids, lens=lens,
-                    rand_frac=rand_frac, loss=loss.detach(), grads=dgrads, pred=pred), os.path.join(OUT, 'duration_d128_L2.pt'))
+        pred = dp(dmel, text=dtext, lens=dlens, return_loss=False)
+    torch.save(dict(state_dict={k: v.clone() for k, v in dp.state_dict().items()}, mel=dmel, text=dtext, text_ids=dtext_ids, lens=dlens,
+                    rand_frac=rand_frac, loss=loss.detach(), grads=dgrads, pred=pred, seed=dseed), os.path.join(OUT, 'duration_d128_L2.pt'))
 
     # MelSpec
     torch.manual_seed(9)

@@ -150,7 +150,7 @@ def test_attention_block(pkg, value_residual, Np):
     gatecs = (torch.rand(B, d, device=dev()) * 0.8 + 0.1).requires_grad_()
     q, k, v, gate = ops.QkvProj.apply(x, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_v_head_gate.weight, attn.to_v_head_gate.bias,
                                       mix[0].weight if value_residual else None, mix[0].bias if value_residual else None, vf, wpack, cs, sn, B, Np, H)
-    og = ops.AttnCore.apply(q, k, v, gate, mu8, 0.0, 0, 50.0)
+    og = ops.AttnCore.apply(q, k, v, gate, mu8, 0.0, 0, 50.0, None)
     y = ops.OutProj.apply(og, attn.to_out.weight, opack, gatecs, mu8, B, Np)
     wo = torch.randn_like(y, dtype=torch.float32)
     params = [p for p in attn.parameters()]
@@ -188,7 +188,7 @@ def test_feedforward_cross_skip(pkg):
     w2p = bf(lin2.weight.detach())
     x = bf(torch.randn(T, d, device=dev())).requires_grad_()
     cs = (torch.rand(B, d, device=dev()) * 0.8 + 0.1).requires_grad_()
-    y = ops.FeedForward.apply(x, lin1.weight, lin1.bias, lin2.weight, lin2.bias, w1p, b1p, w2p, cs, B, Np, 0.0, 0)
+    y = ops.FeedForward.apply(x, lin1.weight, lin1.bias, lin2.weight, lin2.bias, w1p, b1p, w2p, cs, B, Np, 0.0, 0, None)
     wo = torch.randn_like(y, dtype=torch.float32)
     leaves = [x, cs, lin1.weight, lin1.bias, lin2.weight, lin2.bias]
     grads = torch.autograd.grad((y.float() * wo).sum(), leaves)
@@ -247,15 +247,15 @@ def test_attention_dropout_is_consistent(pkg):
     q, k, v = (bf(torch.randn(B, H, Np, 64, device=dev())) for _ in range(3))
     gate = torch.rand(B * Np, H, device=dev())
     v1 = v.clone().requires_grad_()
-    og = ops.AttnCore.apply(q, k, v1, gate, None, 0.3, 1234, 50.0)
+    og = ops.AttnCore.apply(q, k, v1, gate, None, 0.3, 1234, 50.0, None)
     w = torch.randn_like(og, dtype=torch.float32)
     (dv,) = torch.autograd.grad((og.float() * w).sum(), [v1])
     dirn = bf(torch.randn_like(v.float()))
-    og2 = ops.AttnCore.apply(q, k, bf(v.float() + 0.5 * dirn.float()), gate, None, 0.3, 1234, 50.0)
+    og2 = ops.AttnCore.apply(q, k, bf(v.float() + 0.5 * dirn.float()), gate, None, 0.3, 1234, 50.0, None)
     lhs = ((og2.float() - og.float()) * w).sum() / 0.5
     rhs = (dv.float() * dirn.float()).sum()
     assert abs(float(lhs - rhs)) <= 0.05 * abs(float(rhs)) + 0.5, (float(lhs), float(rhs))
-    og3 = ops.AttnCore.apply(q, k, v, gate, None, 0.3, 99, 50.0)
+    og3 = ops.AttnCore.apply(q, k, v, gate, None, 0.3, 99, 50.0, None)
     assert rel_l2(og3.float().cpu(), og.float().cpu()) > 1e-2   # a different seed gives a different mask
 
 
@@ -300,34 +300,33 @@ def test_e2tts_forward_backward_vs_golden(pkg, case):
 
 
 def test_duration_predictor_vs_golden(pkg):
+    """DurationPredictor fwd+bwd against the reference-minted golden (B=4; re-minted in round 2 on a well-conditioned prefix draw,
+    oracle/make_golden.py): loss <= 1e-2, every parameter gradient cosine >= 0.99 and norm within 10 %."""
     g, e = _load('duration_d128_L2.pt'), _load('e2tts_d128_L2.pt')
     dp = pkg.DurationPredictor(transformer=dict(dropout=0., max_seq_len=256, **e['transformer']))
     dp.load_state_dict(g['state_dict'])
     dp.to(dev()).train()
     with pkg.inject_randomness(duration_rand_frac=g['rand_frac'].to(dev())):
-        loss = dp(g['mel'].to(dev()), text=e['text'], lens=g['lens'].to(dev()))
+        loss = dp(g['mel'].to(dev()), text=g['text'], lens=g['lens'].to(dev()))
     loss.backward()
-    assert abs(float(loss) - float(g['loss'])) <= 2e-2 * abs(float(g['loss']))
-    # This synthetic case (|dloss/dpred| ~ 190, randomised dynamic hyper-connection scales) is ill-conditioned for a few
-    # first-text-layer parameters: rounding the oracle's own stage outputs to bf16 moves exactly those gradients by the same
-    # amount ("precision"). So: global gradient direction against the fp32 oracle, per-parameter norms loosely.
-    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g['state_dict'].items()}
-    lo = O.duration_forward(sd, O.TransformerCfg(cond_on_time=False, **e['transformer']), g['mel'], g['text_ids'], lens=g['lens'],
-                            rand_frac=g['rand_frac'])
-    lo.backward()
-    mine, ref, off = [], [], 0
+    assert abs(float(loss) - float(g['loss'])) <= 1e-2 * abs(float(g['loss']))
+    total = float(torch.cat([v.flatten() for v in g['grads'].values()]).norm())
+    worst = (1.0, None)
     for k, p in dp.named_parameters():
-        if sd[k].grad is None:
+        if k not in g['grads']:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, f'{k} should be unused'
             continue
-        mine.append(p.grad.cpu().flatten())
-        ref.append(sd[k].grad.flatten())
-        r = float(p.grad.norm()) / (float(sd[k].grad.norm()) + 1e-30)
-        off += int(not (0.8 <= r <= 1.25))
-    assert cos(torch.cat(mine), torch.cat(ref)) >= 0.99
-    assert off <= 0.05 * len(mine), f'{off} of {len(mine)} parameter-gradient norms are off by more than 25%'
+        gr = g['grads'][k]
+        if float(gr.norm()) < 1e-4 * total:
+            continue
+        cs_ = cos(p.grad.cpu(), gr)
+        worst = min(worst, (cs_, k))
+        assert cs_ >= 0.99, (k, cs_)
+        assert 0.9 <= float(p.grad.norm()) / float(gr.norm()) <= 1.1, (k, float(p.grad.norm()), float(gr.norm()))
+    print('duration: worst grad cosine', worst)
     dp.eval()
     with torch.no_grad():
-        pred = dp(g['mel'].to(dev()), text=e['text'], lens=g['lens'].to(dev()), return_loss=False)
+        pred = dp(g['mel'].to(dev()), text=g['text'], lens=g['lens'].to(dev()), return_loss=False)
     assert rel_l2(pred.cpu(), g['pred']) < 2e-2
 
 
@@ -414,7 +413,7 @@ def test_attention_tcgen05_forward_matches_mma_sync_forward(pkg, Np, masked, dro
         ops.ATTN_FWD_ENTRY = entry
         try:
             qq = q.clone().requires_grad_()
-            og = ops.AttnCore.apply(qq, k, v, gate, mask, dropout, 4242, 50.0)
+            og = ops.AttnCore.apply(qq, k, v, gate, mask, dropout, 4242, 50.0, None)
             ctx = og.grad_fn
             outs[entry] = (og.float().cpu(), ctx.saved_tensors[5].float().cpu(), ctx.saved_tensors[6].cpu())
         finally:
@@ -445,7 +444,7 @@ def test_attention_tcgen05_backward_matches_mma_sync_backward(pkg, Np, masked, d
         ops.ATTN_BWD_ENTRY = entry
         try:
             leaves = [t.clone().requires_grad_() for t in (q, k, v)] + [gate.clone().requires_grad_()]
-            og = ops.AttnCore.apply(*leaves, mask, dropout, 99, 50.0)
+            og = ops.AttnCore.apply(*leaves, mask, dropout, 99, 50.0, None)
             res[entry] = [g.float().cpu() for g in torch.autograd.grad(og, leaves, w)]
         finally:
             ops.ATTN_BWD_ENTRY = 'b200_attn_bwd'
@@ -467,7 +466,7 @@ def test_feedforward_dropout_mask_is_consistent_between_forward_and_backward(pkg
     b1p = lin1.bias.detach().view(2, nb, 64).transpose(0, 1).reshape(2 * inner).contiguous()
     w2p = bf(lin2.weight.detach())
     x = bf(torch.randn(T, d, device=dev()))
-    run = lambda xx, seed: ops.FeedForward.apply(xx, lin1.weight, lin1.bias, lin2.weight, lin2.bias, w1p, b1p, w2p, None, B, Np, 0.3, seed)
+    run = lambda xx, seed: ops.FeedForward.apply(xx, lin1.weight, lin1.bias, lin2.weight, lin2.bias, w1p, b1p, w2p, None, B, Np, 0.3, seed, None)
     x1 = x.clone().requires_grad_()
     y1 = run(x1, 77)
     w = torch.randn_like(y1, dtype=torch.float32)

@@ -57,9 +57,9 @@ def test_duration_matches_golden():
     loss = O.duration_forward(sd, cfg, g['mel'], g['text_ids'], lens=g['lens'], rand_frac=g['rand_frac'])
     assert abs(loss.item() - g['loss'].item()) < 1e-4 * abs(g['loss'].item())
     loss.backward()
-    for k, gref in g['grads'].items():
-        got = torch.stack((sd[k].grad.norm(), sd[k].grad.sum()))
-        assert (got - gref).abs().max() <= 5e-4 * gref.abs().max() + 1e-6, k
+    total = torch.cat([v.flatten() for v in g['grads'].values()]).norm()
+    for k, gref in g['grads'].items():   # full per-parameter gradients of the reference (fixture re-minted in round 2, oracle/make_golden.py)
+        assert (sd[k].grad - gref).norm() <= 5e-4 * gref.norm() + 1e-6 * total, k
     with torch.no_grad():
         pred = O.duration_forward(g['state_dict'], cfg, g['mel'], g['text_ids'], lens=g['lens'], return_loss=False)
     assert rel_l2(pred, g['pred']) < 1e-5

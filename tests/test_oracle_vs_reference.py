@@ -119,3 +119,73 @@ def test_duration_predictor_vs_reference():
     for k, p in dp.named_parameters():
         if p.grad is not None:
             assert (p.grad - sd[k].grad).abs().max() <= 5e-4 * p.grad.abs().max() + 1e-6, k
+
+
+def test_mask_helpers_bit_exact_vs_reference():
+    """The product's host-side mask helpers (e2-tts-pytorch_b200/modules.py: lens_to_mask, mask_from_frac_lengths — SURVEY §8 row a14)
+    against the reference's (e2_tts.py:173-210), bit for bit on 200 seeded ragged cases (same torch RNG state -> same rand_like draw)."""
+    import e2_tts_pytorch_b200 as pkg
+    ref = load_reference()
+    g = torch.Generator().manual_seed(0)
+    for case in range(200):
+        b = int(torch.randint(1, 9, (1,), generator=g))
+        n = int(torch.randint(8, 300, (1,), generator=g))
+        lens = torch.randint(1, n + 1, (b,), generator=g)
+        if case % 3 == 0:
+            lens[int(torch.randint(0, b, (1,), generator=g))] = n
+        frac = torch.rand(b, generator=g) * 0.3 + 0.7          # frac_lengths_mask = (0.7, 1.0), e2_tts.py:1133
+        torch.manual_seed(1000 + case)
+        want = ref.mask_from_frac_lengths(lens, frac, max_length=n)
+        torch.manual_seed(1000 + case)
+        got = pkg.mask_from_frac_lengths(lens, frac, n)
+        assert got.dtype == torch.bool and got.shape == want.shape and torch.equal(got, want), case
+        assert torch.equal(pkg.lens_to_mask(lens, length=n), ref.lens_to_mask(lens, length=n)), case
+        assert torch.equal(pkg.lens_to_mask(lens), ref.lens_to_mask(lens)), case
+    ids = pkg.list_str_to_tensor(['Hello', 'Goodbye', 'héllo wörld'])
+    assert torch.equal(ids, ref.list_str_to_tensor(['Hello', 'Goodbye', 'héllo wörld']))
+
+
+def test_velocity_consistency_loss_vs_reference():
+    """E2TTS.forward with a velocity_consistency_model (e2_tts.py:1556-1576, trainer hook trainer.py:259-268): total loss, breakdown and
+    gradients of the online model against the oracle's restatement."""
+    ref = load_reference()
+    torch.manual_seed(5)
+    kw = dict(dim=128, depth=2, heads=2)
+    model = ref.E2TTS(transformer=dict(dropout=0., max_seq_len=128, **kw), use_vocos=False, velocity_consistency_weight=0.7)
+    model.load_state_dict(O.randomize_zero_init(model.state_dict(), seed=5))
+    ema = ref.E2TTS(transformer=dict(dropout=0., max_seq_len=128, **kw), use_vocos=False)
+    ema.load_state_dict(O.randomize_zero_init(ema.state_dict(), seed=6))
+    ema.eval()
+    mel = torch.randn(2, 64, 100)
+    lens_t = torch.tensor([64, 50])
+    text = ['abc', 'some text']
+    from oracle.load_reference import TorchRecorder
+    rec = TorchRecorder(ref.torch)
+    span = {}
+    orig = ref.mask_from_frac_lengths
+
+    def mffl(*a, **k):
+        span['mask'] = orig(*a, **k)
+        return span['mask'].clone()
+
+    model.cond_drop_prob = -1.0
+    ref.torch, ref.mask_from_frac_lengths = rec, mffl
+    try:
+        out = model(mel, text=text, lens=lens_t, velocity_consistency_model=ema, velocity_consistency_delta=1e-3)
+    finally:
+        ref.torch, ref.mask_from_frac_lengths = rec._t, orig
+    out.loss.backward()
+    x0, times = rec.log['randn_like'][0], rec.log['rand'][0]
+    span_mask = span['mask'] & ref.lens_to_mask(lens_t, length=64)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    o = O.e2tts_forward(sd, O.TransformerCfg(**kw), mel, O.list_str_to_tensor(text), lens=lens_t, x0=x0, times=times, span_mask=span_mask,
+                        velocity_sd=ema.state_dict(), velocity_consistency_weight=0.7, velocity_consistency_delta=1e-3)
+    o['loss'].backward()
+    assert abs(float(o['loss']) - float(out.loss)) <= 1e-5 * abs(float(out.loss))
+    assert abs(float(o['flow_loss']) - float(out.loss_breakdown.flow)) <= 1e-5 * abs(float(out.loss_breakdown.flow))
+    assert abs(float(o['velocity_loss']) - float(out.loss_breakdown.velocity_consistency)) <= 1e-5 * abs(float(out.loss_breakdown.velocity_consistency))
+    assert float(out.loss_breakdown.velocity_consistency) > 0
+    total = torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None]).norm()
+    for k, p in model.named_parameters():
+        if p.grad is not None:   # fp32 summation order differs between the two autograd graphs: norm-wise agreement
+            assert (sd[k].grad - p.grad).norm() <= 2e-3 * p.grad.norm() + 1e-5 * total, k

@@ -61,6 +61,7 @@ class GraphedTrainStep:
                 self.grad_sync.all_reduce()    # NCCL communicator / channel setup outside the timed path
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()   # the warm-up's side-stream blocks would sit beside the graph's private pool (a full set of activations each)
         self.graph = torch.cuda.CUDAGraph()
         table = self.grad_sync.new_table() if self.grad_sync is not None else None
         n0 = lib.launch_count()

@@ -13,7 +13,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'b200_e2tts.h')
-LIB_PATH = os.path.join(_HERE, 'libb200e2tts.so')
+LIB_PATH = os.environ.get('B200_LIB') or os.path.join(_HERE, 'libb200e2tts.so')   # B200_LIB: developer A/B builds of the same ABI
 
 _SCALARS = {
     'int32_t': ctypes.c_int32, 'int64_t': ctypes.c_int64, 'uint64_t': ctypes.c_uint64, 'uint32_t': ctypes.c_uint32,

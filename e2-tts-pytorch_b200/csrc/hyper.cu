@@ -640,9 +640,9 @@ static bool hc_prefetch_enabled() {
 }
 // the dynamic shared-memory ceiling of a token kernel depends on D, which a process may vary between calls (text / audio streams):
 // raise it once per (kernel instantiation, device) to the kernel's maximum instead of per call (once_flag-guarded init)
-template <typename K>
-static int set_smem(K kern, size_t bytes) {
-    static DeviceOnce once;   // one per instantiation of this template = per kernel
+template <auto kern>          // the kernel is a template VALUE: instantiations that share a function type still get their own flag
+static int set_smem(size_t bytes) {
+    static DeviceOnce once;
     constexpr int kMax = 200 * 1024;
     B200_REQUIRE(bytes <= (size_t)kMax, "hyper-connections: %zu B of shared memory exceed the kernel's ceiling", bytes);
     cudaError_t e = set_max_smem_once(once, kern, kMax);
@@ -678,10 +678,10 @@ extern "C" int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stre
         const size_t smem = smem_par + (size_t)8 * 2 * HS * a->D * 2;
         const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 2);
         if (a->D <= 256) {
-            if (int rc = set_smem(hc_width_fwd_kernel<1, true>, smem)) return rc;
+            if (int rc = set_smem<hc_width_fwd_kernel<1, true>>(smem)) return rc;
             B200_LAUNCH((hc_width_fwd_kernel<1, true>), grid, 256, smem, st, p);
         } else {
-            if (int rc = set_smem(hc_width_fwd_kernel<2, true>, smem)) return rc;
+            if (int rc = set_smem<hc_width_fwd_kernel<2, true>>(smem)) return rc;
             B200_LAUNCH((hc_width_fwd_kernel<2, true>), grid, 256, smem, st, p);
         }
         return check_launch("hc_width_fwd_kernel");
@@ -714,10 +714,10 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     if (a->D <= 512 && hc_prefetch_enabled()) {
         const size_t smem = smem_par + (size_t)8 * 2 * (2 * HS + 1) * a->D * 2;   // + per-warp {r, d_res, d_branch} double buffers
         if (a->D <= 256) {
-            if (int rc = set_smem(hc_width_bwd_kernel<1, true>, smem)) return rc;
+            if (int rc = set_smem<hc_width_bwd_kernel<1, true>>(smem)) return rc;
             B200_LAUNCH((hc_width_bwd_kernel<1, true>), grid, 256, smem, st, p, cmat);
         } else {
-            if (int rc = set_smem(hc_width_bwd_kernel<2, true>, smem)) return rc;
+            if (int rc = set_smem<hc_width_bwd_kernel<2, true>>(smem)) return rc;
             B200_LAUNCH((hc_width_bwd_kernel<2, true>), grid, 256, smem, st, p, cmat);
         }
     } else if (a->D <= 256) B200_LAUNCH((hc_width_bwd_kernel<1, false>), grid, 256, smem_par, st, p, cmat);

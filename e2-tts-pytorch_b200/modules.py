@@ -342,6 +342,7 @@ class Transformer(Module):
         # optional int64 device word added to every dropout seed when the kernels RUN (include/b200_e2tts.h "dropout seeds"):
         # set by GraphedTrainStep, whose captured graph would otherwise replay the same dropout masks on every step
         self._seed_dev = None
+        self._frozen = False   # True inside E2TTS.sample(): the bf16 operands were packed once for the whole ODE solve (weights cannot change)
 
     # ------------------------------------------------------------------ packed operands
     def _apply(self, fn, *a, **k):
@@ -351,7 +352,7 @@ class Transformer(Module):
 
     def __deepcopy__(self, memo):  # EMA(model) deep-copies the module (trainer.py:170-174): caches are per instance
         pack, packed, rot, seed_dev = self._pack, self._packed, self._rot, self._seed_dev
-        self._pack, self._packed, self._rot, self._seed_dev = None, None, {}, None
+        self._pack, self._packed, self._rot, self._seed_dev, self._frozen = None, None, {}, None, False
         try:
             cls = self.__class__
             new = cls.__new__(cls)
@@ -420,9 +421,21 @@ class Transformer(Module):
 
     def refresh_packed(self):
         """Re-pack the bf16 GEMM operands from the current fp32 parameters (one launch)."""
+        if self._frozen and self._pack is not None:
+            return
         if self._pack is None:
             self._build_pack()
         self._pack[0].run()
+
+    def freeze_packed(self, on):
+        """sample() runs 124 forwards over frozen weights (e2_tts.py:1332 @torch.no_grad, :1351 eval): pack the tensor-core operands and the
+        batched to_gamma matrix ONCE instead of once per forward."""
+        self._frozen = False
+        if on:
+            self.refresh_packed()
+            if self.cond_on_time:
+                self._pack[1].run()
+            self._frozen = True
 
     def _rotary(self, Np, dev):
         if Np not in self._rot:
@@ -443,7 +456,10 @@ class Transformer(Module):
         tab = self._pack[1]
         weights = [l.weight for l in c['lins']]
         biases = [l.bias for l in c['lins'] if l.bias is not None]  # AdaLNZero gates sit on the odd d-wide segments
-        W, b_full = ops.CondPack.apply(tab.run, c['W'], c['b'], self.dim, len(weights), *weights, *biases)
+        if self._frozen:
+            W, b_full = c['W'], c['b']
+        else:
+            W, b_full = ops.CondPack.apply(tab.run, c['W'], c['b'], self.dim, len(weights), *weights, *biases)
         gains = ops.SmallLinear.apply(cond, W, b_full, 5, self.dim, True)
         return list(gains.unbind(0))
 
@@ -781,6 +797,8 @@ class E2TTS(Module):
 
     def _packed(self):
         dev = self.device
+        if self.transformer._frozen and self._wpack is not None and self._wpack['stem'].device == dev:
+            return self._wpack
         if self._wpack is None or self._wpack['stem'].device != dev:
             C, d = self.num_channels, self.dim
             Cp = (C + 63) // 64 * 64
@@ -871,14 +889,24 @@ class E2TTS(Module):
         y = _rng.draw('y0', lambda: torch.randn_like(cond))
         ts = torch.linspace(0, 1, steps, device=dev)
         method = self.odeint_kwargs.get('method', 'midpoint')
-        for i in range(steps - 1):
-            t0, dt = ts[i], ts[i + 1] - ts[i]
-            if method == 'euler':
-                y = ops.axpy(y, fn(t0, y), dt)
-            else:
-                half = 0.5 * dt
-                ymid = ops.axpy(y, fn(t0, y), half)
-                y = ops.axpy(y, fn(t0 + half, ymid), dt)
+        frozen = [self.transformer] + ([cfg_null_model.transformer] if exists(cfg_null_model) else [])
+        try:
+            for tr in frozen:            # weights are fixed for the whole solve: pack the bf16 operands once, not 124 times
+                tr.freeze_packed(True)
+            self._packed()
+            if exists(cfg_null_model):
+                cfg_null_model._packed()
+            for i in range(steps - 1):
+                t0, dt = ts[i], ts[i + 1] - ts[i]
+                if method == 'euler':
+                    y = ops.axpy(y, fn(t0, y), dt)
+                else:
+                    half = 0.5 * dt
+                    ymid = ops.axpy(y, fn(t0, y), half)
+                    y = ops.axpy(y, fn(t0 + half, ymid), dt)
+        finally:
+            for tr in frozen:
+                tr.freeze_packed(False)
         out = torch.where(cond_mask, cond, y)
         if exists(return_raw_output) and return_raw_output:
             return out

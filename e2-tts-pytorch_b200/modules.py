@@ -891,11 +891,11 @@ class E2TTS(Module):
         method = self.odeint_kwargs.get('method', 'midpoint')
         frozen = [self.transformer] + ([cfg_null_model.transformer] if exists(cfg_null_model) else [])
         try:
-            for tr in frozen:            # weights are fixed for the whole solve: pack the bf16 operands once, not 124 times
-                tr.freeze_packed(True)
-            self._packed()
+            self._packed()               # weights are fixed for the whole solve: pack the bf16 operands once (fresh), not 124 times
             if exists(cfg_null_model):
                 cfg_null_model._packed()
+            for tr in frozen:
+                tr.freeze_packed(True)
             for i in range(steps - 1):
                 t0, dt = ts[i], ts[i + 1] - ts[i]
                 if method == 'euler':

@@ -84,10 +84,12 @@ __global__ void attn_maskbits_kernel(const unsigned char* mask, unsigned int* bi
 
 // ---- forward, persistent: one CTA per SM walks work items (128-query tile, head, batch); item index = (b*H + h)*nq + qt, so the
 // CTAs running at one moment share the K/V of a few heads through L2. Everything is pipelined ACROSS items: the producer prefetches
-// the next item's Q/K/V, the MMA warp issues S_0 of the next item before the last P V of the current one, O is double-buffered in
-// TMEM so an item's epilogue overlaps the next item's main loop. Barriers are indexed by running tile / item counters.
-constexpr int KVS = 3;                        // K/V smem stages
-constexpr int FWD_SMEM = 2 * TILE16 + 2 * KVS * TILE16 + 2 * PTILE + 512 + 2 * 4 * 128 * 4 + 1024;
+// the next item's Q/K/V, the MMA warp issues S two key tiles ahead of the P V it is waiting for (also across an item boundary), O
+// is double-buffered in TMEM so an item's epilogue overlaps the next item's main loop. Barriers are indexed by running tile /
+// item counters. (First persistent version, gpurun_out/r2c_*: S was issued only ONE tile ahead, behind the previous P V, while the
+// softmax warps had started to prefetch half a tile early — 20 % of all stall samples sat on the s_full wait.)
+constexpr int KS = 3, VS = 3;                 // K / V smem stages (separate rings: a K tile is free once its S MMAs retire)
+constexpr int FWD_SMEM = 2 * TILE16 + (KS + VS) * TILE16 + 2 * PTILE + 512 + 2 * 4 * 128 * 4 + 1024;
 
 struct FwdItem { int b, hh, qt; };
 __device__ __forceinline__ FwdItem fwd_item(int w, int nq, int H) {
@@ -107,16 +109,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // accesses compile to LDS / STS instead of generic LD / ST (+ a full MEMBAR before the async-proxy fence)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sQ = smem;                     // [2]
-    uint8_t* sK = sQ + 2 * TILE16;          // [KVS]
-    uint8_t* sV = sK + KVS * TILE16;        // [KVS]
-    uint8_t* sP = sV + KVS * TILE16;        // [2] x 32 KB
+    uint8_t* sK = sQ + 2 * TILE16;          // [KS]
+    uint8_t* sV = sK + KS * TILE16;         // [VS]
+    uint8_t* sP = sV + VS * TILE16;         // [2] x 32 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PTILE);
     uint64_t* q_full = bars;                // 2
     uint64_t* q_empty = bars + 2;           // 2
-    uint64_t* k_full = bars + 4;            // KVS
-    uint64_t* v_full = bars + 4 + KVS;      // KVS
-    uint64_t* kv_empty = bars + 4 + 2 * KVS;  // KVS
-    uint64_t* s_full = bars + 4 + 3 * KVS;  // 2
+    uint64_t* k_full = bars + 4;            // KS
+    uint64_t* k_empty = k_full + KS;        // KS
+    uint64_t* v_full = k_empty + KS;        // VS
+    uint64_t* v_empty = v_full + VS;        // VS
+    uint64_t* s_full = v_empty + VS;        // 2
     uint64_t* s_empty = s_full + 2;         // 2
     uint64_t* p_full = s_full + 4;          // 2
     uint64_t* p_empty = s_full + 6;         // 2
@@ -129,6 +132,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int nkv = p.nkv, nq = p.nkv;      // query and key tiles cover the same Np rows
     const int n_items = p.B * p.H * nq;
     const int w0 = blockIdx.x, wstep = gridDim.x;
+    const int my_items = (n_items - w0 + wstep - 1) / wstep;
+    const int G = my_items * nkv;           // key tiles this CTA walks
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -138,7 +143,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_init(&p_full[i], 16); mbar_init(&p_empty[i], 1);
             mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 16);
         }
-        for (int i = 0; i < KVS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -161,58 +167,62 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_arrive_expect_tx(&q_full[qb], TILE16);
                 tma_load_2d(sQ + qb * TILE16, &tmQ, &q_full[qb], 0, row_base + it.qt * TQ);
                 for (int j = 0; j < nkv; ++j, ++t) {
-                    const int st = t % KVS;
-                    mbar_wait(&kv_empty[st], ((t / KVS) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&k_full[st], TILE16);
-                    tma_load_2d(sK + st * TILE16, &tmK, &k_full[st], 0, row_base + j * TKV);
-                    mbar_arrive_expect_tx(&v_full[st], TILE16);
-                    tma_load_2d(sV + st * TILE16, &tmV, &v_full[st], 0, row_base + j * TKV);
+                    const int ks = t % KS, vs = t % VS;
+                    mbar_wait(&k_empty[ks], ((t / KS) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&k_full[ks], TILE16);
+                    tma_load_2d(sK + ks * TILE16, &tmK, &k_full[ks], 0, row_base + j * TKV);
+                    mbar_wait(&v_empty[vs], ((t / VS) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&v_full[vs], TILE16);
+                    tma_load_2d(sV + vs * TILE16, &tmV, &v_full[vs], 0, row_base + j * TKV);
                 }
             }
             pdl_launch_dependents();
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer: S of tile g is issued before P V of tile g-1,
-            // across item boundaries too (g = running tile counter; item = g / nkv, j = g % nkv)
+            // ---------------------------------------------------------------- MMA issuer. Per running tile g: S(g+1) first — its S
+            // buffer was released when the softmax warps fetched the scores of tile g-1, i.e. half a tile before P(g) exists — then
+            // wait for P(g) and issue O += P(g) V(g). The scores of a tile are therefore complete a full tile before the softmax
+            // warps (which prefetch half a tile early) ask for them.
             constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-            const int my_items = (n_items - w0 + wstep - 1) / wstep;
-            const int G = my_items * nkv;
-            for (int g = 0; g <= G; ++g) {
-                if (g < G) {
-                    const int i = g / nkv, j = g - i * nkv;
-                    const int sb = g & 1, st = g % KVS;
-                    if (j == 0) mbar_wait(&q_full[i & 1], (i >> 1) & 1);
-                    mbar_wait(&k_full[st], (g / KVS) & 1);
-                    mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + (i & 1) * TILE16), 0, 1024);
-                    const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + st * TILE16), 0, 1024);
+            auto issue_s = [&](int g, int i, int j) {
+                const int sb = g & 1, ks = g % KS;
+                if (j == 0) mbar_wait(&q_full[i & 1], (i >> 1) & 1);
+                mbar_wait(&k_full[ks], (g / KS) & 1);
+                mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + (i & 1) * TILE16), 0, 1024);
+                const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + ks * TILE16), 0, 1024);
 #pragma unroll
-                    for (int k = 0; k < DH / 16; ++k) umma_f16(tS + sb * 128, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
-                    umma_commit(&s_full[sb]);
-                    if (j == nkv - 1) umma_commit(&q_empty[i & 1]);   // the item's last S: its Q tile may be overwritten
-                }
-                if (g >= 1) {
-                    const int gg = g - 1;
-                    const int i = gg / nkv, j = gg - i * nkv;
-                    const int pb = gg & 1, st = gg % KVS;
-                    mbar_wait(&p_full[pb], (gg >> 1) & 1);
-                    mbar_wait(&v_full[st], (gg / KVS) & 1);
-                    if (j == 0) mbar_wait(&o_empty[i & 1], ((i >> 1) & 1) ^ 1);   // the epilogue of item i-2 has read this accumulator
-                    tc_fence_after();
-                    const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + st * TILE16), 128 * 128, 1024);
-                    const uint32_t pbase = smem_u32(sP + pb * PTILE);
+                for (int k = 0; k < DH / 16; ++k) umma_f16(tS + sb * 128, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[sb]);
+                umma_commit(&k_empty[ks]);                        // the K tile may be overwritten once these MMAs retire
+                if (j == nkv - 1) umma_commit(&q_empty[i & 1]);   // the item's last S: its Q tile may be overwritten
+            };
+            int i = 0, j = 0;          // item / tile-in-item of running tile g
+            int in = 0, jn = 1;        // ... of running tile g + 1
+            if (jn == nkv) { in = 1; jn = 0; }
+            if (G > 0) issue_s(0, 0, 0);
+            for (int g = 0; g < G; ++g) {
+                if (g + 1 < G) issue_s(g + 1, in, jn);
+                const int pb = g & 1, vs = g % VS;
+                mbar_wait(&p_full[pb], (g >> 1) & 1);
+                mbar_wait(&v_full[vs], (g / VS) & 1);
+                if (j == 0) mbar_wait(&o_empty[i & 1], ((i >> 1) & 1) ^ 1);   // the epilogue of item i-2 has read this accumulator
+                tc_fence_after();
+                const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vs * TILE16), 128 * 128, 1024);
+                const uint32_t pbase = smem_u32(sP + pb * PTILE);
 #pragma unroll
-                    for (int k = 0; k < TKV / 16; ++k) {
-                        const uint64_t pdesc = make_smem_desc_sw128(pbase + (k >> 2) * TILE16 + (k & 3) * 32, 0, 1024);
-                        umma_f16(tO + (i & 1) * 64, pdesc, vdesc + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&kv_empty[st]);
-                    umma_commit(&p_empty[pb]);
-                    if (j == nkv - 1) umma_commit(&o_full[i & 1]);
+                for (int k = 0; k < TKV / 16; ++k) {
+                    const uint64_t pdesc = make_smem_desc_sw128(pbase + (k >> 2) * TILE16 + (k & 3) * 32, 0, 1024);
+                    umma_f16(tO + (i & 1) * 64, pdesc, vdesc + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                 }
+                umma_commit(&v_empty[vs]);
+                umma_commit(&p_empty[pb]);
+                if (j == nkv - 1) umma_commit(&o_full[i & 1]);
+                i = in; j = jn;
+                if (++jn == nkv) { jn = 0; ++in; }
             }
         }
     } else {
@@ -220,8 +230,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // The softclamp bounds every logit to [-clamp, clamp] (clamp <= 64 on this path), so exp(logit) stays inside the fp32 / bf16
         // range without a running row maximum: no max pass, no cross-warp exchange per tile, no rescale — P V accumulates in TMEM
         // over all key tiles and is read once. LSE = log(sum exp(logit)).
-        // The scores of tile g+1 are fetched from TMEM into a second register set BEFORE the math of tile g (the 16 warps run in
-        // lockstep on the same barriers, so nothing else would hide the tcgen05.ld latency), and 32 x 32 blocks without a valid key
+        // A thread's 32 scores of a tile are fetched from TMEM as two 16-key halves, each while the other half is being computed
+        // (the 16 warps run in lockstep on the same barriers, so nothing else would hide the tcgen05.ld latency) — the first half of the
+        // NEXT tile (also the next item's first tile) under the second half of this one — and 32 x 32 blocks without a valid key
         // (sequence tail, padded keys) or without a valid query row (last query tile) skip the math altogether.
         const int qd = warp & 3, part = (warp - 2) >> 2;
         const int row = qd * 32 + lane;
@@ -234,141 +245,161 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float lim5 = 0.15f / fabsf(soc), lim9 = TANH_POLY_MAX / fabsf(soc);   // |u| <= 0.15: degree 5 is exact to 1e-7; <= 0.5: degree 9
         const float2 soc2 = make_float2(soc, soc), cl2 = make_float2(cl, cl);
 
-        int g = 0, i = 0;
         uint32_t h0[16], h1[16];   // the two 16-key halves of this thread's 32 scores of a tile
-        auto run_item = [&](int w, int item_idx, int& gref) {
+        // ---- per-item state (cur = the item running tile g belongs to)
+        // (only what the tile loop needs is kept live; the epilogue re-derives (b, head, row) from the item index)
+        struct ItemState { bool rows_live; const unsigned int* mb; unsigned long long drop_row; };
+        auto make_item = [&](int w) {
             const FwdItem it = fwd_item(w, nq, p.H);
-            const int bh = it.b * p.H + it.hh;
-            const int q0 = it.qt * TQ;
-            const int qi = q0 + row;
-            const bool rows_live = q0 + qd * 32 < p.Np;        // warp-uniform: this warp's 32 query rows exist
-            const unsigned int* mb = p.maskbits + (size_t)it.b * p.mask_words + part;
-            const unsigned long long drop_row = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride;
-            float2 l2 = make_float2(0.f, 0.f);
+            ItemState s_;
+            s_.rows_live = it.qt * TQ + qd * 32 < p.Np;       // warp-uniform: this warp's 32 query rows exist
+            s_.mb = p.maskbits + (size_t)it.b * p.mask_words + part;
+            s_.drop_row = ((unsigned long long)(it.b * p.H + it.hh) * p.Np + (unsigned long long)(it.qt * TQ + row)) * (unsigned long long)p.drop_stride;
+            return s_;
+        };
+        float2 l2 = make_float2(0.f, 0.f);
 
-            // 16 scores -> 8 packed bf16 pairs of un-normalised probabilities (in place); warp-uniform control flow
-            auto half_math = [&](uint32_t (&r)[16], unsigned int hbits, int j, int half) {
-                float amax = 0.f;
+        // 16 scores -> 8 packed bf16 pairs of un-normalised probabilities (in place); warp-uniform control flow
+        auto half_math = [&](uint32_t (&r)[16], unsigned int hbits, unsigned long long drop_base) {
+            float amax = 0.f;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) amax = fmaxf(amax, fabsf(__uint_as_float(r[e])));
-                const bool small5 = __all_sync(0xffffffffu, amax <= lim5);
-                const bool small9 = __all_sync(0xffffffffu, amax <= lim9);
-                float pv[16];
-                if (small5) {
+            for (int e = 0; e < 16; ++e) amax = fmaxf(amax, fabsf(__uint_as_float(r[e])));
+            const bool small5 = __all_sync(0xffffffffu, amax <= lim5);
+            const bool small9 = __all_sync(0xffffffffu, amax <= lim9);
+            float pv[16];
+            if (small5) {
 #pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const float2 s = make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-                        const float2 s2 = __fmul2_rn(s, s);
-                        float2 q = __ffma2_rn(s2, make_float2(k5, k5), make_float2(k3, k3));
-                        q = __ffma2_rn(q, s2, make_float2(k1, k1));
-                        const float2 y = __fmul2_rn(s, q);
-                        pv[e] = ex2_approx(y.x); pv[e + 1] = ex2_approx(y.y);
-                    }
-                } else if (small9) {
-#pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const float2 s = make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-                        const float2 s2 = __fmul2_rn(s, s);
-                        float2 q = __ffma2_rn(s2, make_float2(k9, k9), make_float2(k7, k7));
-                        q = __ffma2_rn(q, s2, make_float2(k5, k5));
-                        q = __ffma2_rn(q, s2, make_float2(k3, k3));
-                        q = __ffma2_rn(q, s2, make_float2(k1, k1));
-                        const float2 y = __fmul2_rn(s, q);
-                        pv[e] = ex2_approx(y.x); pv[e + 1] = ex2_approx(y.y);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const float2 x = __fmul2_rn(make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), soc2);
-                        const float2 y = __fmul2_rn(make_float2(tanh_approx(x.x), tanh_approx(x.y)), cl2);
-                        pv[e] = ex2_approx(y.x); pv[e + 1] = ex2_approx(y.y);
-                    }
+                for (int e = 0; e < 16; e += 2) {
+                    const float2 s = make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+                    const float2 s2 = __fmul2_rn(s, s);
+                    float2 q = __ffma2_rn(s2, make_float2(k5, k5), make_float2(k3, k3));
+                    q = __ffma2_rn(q, s2, make_float2(k1, k1));
+                    const float2 y = __fmul2_rn(s, q);
+                    pv[e] = ex2_approx(y.x); pv[e + 1] = ex2_approx(y.y);
                 }
-                if (hbits != 0xffffu) {
+            } else if (small9) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) pv[e] = ((hbits >> e) & 1u) ? pv[e] : 0.f;
+                for (int e = 0; e < 16; e += 2) {
+                    const float2 s = make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+                    const float2 s2 = __fmul2_rn(s, s);
+                    float2 q = __ffma2_rn(s2, make_float2(k9, k9), make_float2(k7, k7));
+                    q = __ffma2_rn(q, s2, make_float2(k5, k5));
+                    q = __ffma2_rn(q, s2, make_float2(k3, k3));
+                    q = __ffma2_rn(q, s2, make_float2(k1, k1));
+                    const float2 y = __fmul2_rn(s, q);
+                    pv[e] = ex2_approx(y.x); pv[e + 1] = ex2_approx(y.y);
                 }
+            } else {
 #pragma unroll
-                for (int e = 0; e < 16; e += 2) l2 = __fadd2_rn(l2, make_float2(pv[e], pv[e + 1]));
-                if (p.dropout_p > 0.f) {   // the 1/(1-p) factor is applied once, to the normalised output
-                    const uint32_t pbase = (uint32_t)((drop_row + (unsigned long long)(j * TKV + part * 32 + half * 16)) >> 1);
-#pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const uint32_t h = hash_pair32(seedmix, pbase + (e >> 1));
-                        pv[e] = ((h & 0xffffu) >= p.drop_thresh) ? pv[e] : 0.f;
-                        pv[e + 1] = ((h >> 16) >= p.drop_thresh) ? pv[e + 1] : 0.f;
-                    }
+                for (int e = 0; e < 16; e += 2) {
+                    const float2 x = __fmul2_rn(make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), soc2);
+                    const float2 y = __fmul2_rn(make_float2(tanh_approx(x.x), tanh_approx(x.y)), cl2);
+                    pv[e] = ex2_approx(y.x); pv[e + 1] = ex2_approx(y.y);
                 }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) r[e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
-            };
-            auto wait_s = [&](int gt) {
-                mbar_wait(&s_full[gt & 1], (gt >> 1) & 1);
-                tc_fence_after();
-            };
-            auto release_s = [&](int gt) {      // this thread's scores of running tile gt are in registers: hand the S buffer back
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[gt & 1]);
-            };
-            auto s_addr = [&](int gt, int half) { return tS + (gt & 1) * 128 + part * 32 + half * 16 + lane_off; };
-
-            // Software pipeline over the item's key tiles. Invariant at the top of iteration j: half 0 of tile j is loading into h0.
-            unsigned int mbits = rows_live ? mb[0] : 0u;
-            wait_s(gref);
-            if (mbits != 0u) tmem_ld16(s_addr(gref, 0), h0);
-            for (int j = 0; j < nkv; ++j, ++gref) {
-                const int pb = gref & 1;
-                const unsigned int mnext = (j + 1 < nkv && rows_live) ? mb[(j + 1) * 4] : 0u;
-                uint32_t pk[16];
-                if (mbits != 0u) {
-                    tmem_ld_wait();                              // half 0 has landed
-                    tmem_ld16(s_addr(gref, 1), h1);              // half 1 loads under the math of half 0
-                    half_math(h0, mbits & 0xffffu, j, 0);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) pk[e] = h0[e];
-                    tmem_ld_wait();                              // half 1 has landed: the S buffer is free
-                }
-                release_s(gref);
-                if (j + 1 < nkv) {                               // next tile's half 0 loads under the math of half 1
-                    wait_s(gref + 1);
-                    if (mnext != 0u) tmem_ld16(s_addr(gref + 1, 0), h0);
-                }
-                if (mbits != 0u) {
-                    half_math(h1, mbits >> 16, j, 1);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) pk[8 + e] = h1[e];
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) pk[e] = 0u;
-                }
-                // the P buffer was last read by the PV MMA of running tile gref-2
-                mbar_wait(&p_empty[pb], ((gref >> 1) & 1) ^ 1);
-                uint8_t* pdst = sP + pb * PTILE + (part >> 1) * TILE16 + row * 128;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int chunk = (part & 1) * 4 + c;
-                    *reinterpret_cast<uint4*>(pdst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-                }
-                fence_proxy_async();        // make the generic-proxy smem writes of P visible to the tensor-core (async) proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[pb]);
-                mbits = mnext;
             }
-            // ---- epilogue: total row sum over the four quarters, normalise, write O (ungated), Og (gated, head-merged) and LSE
-            float* xch = s_xch + (item_idx & 1) * 512;
+            if (hbits != 0xffffu) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pv[e] = ((hbits >> e) & 1u) ? pv[e] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) l2 = __fadd2_rn(l2, make_float2(pv[e], pv[e + 1]));
+            if (p.dropout_p > 0.f) {   // the 1/(1-p) factor is applied once, to the normalised output
+                const uint32_t pbase = (uint32_t)(drop_base >> 1);
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    const uint32_t h = hash_pair32(seedmix, pbase + (e >> 1));
+                    pv[e] = ((h & 0xffffu) >= p.drop_thresh) ? pv[e] : 0.f;
+                    pv[e + 1] = ((h >> 16) >= p.drop_thresh) ? pv[e + 1] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[e] = pack_bf16(pv[2 * e], pv[2 * e + 1]);
+        };
+        auto wait_s = [&](int gt) {
+            mbar_wait(&s_full[gt & 1], (gt >> 1) & 1);
+            tc_fence_after();
+        };
+        auto release_s = [&](int gt) {      // this thread's scores of running tile gt are in registers: hand the S buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[gt & 1]);
+        };
+        auto s_addr = [&](int gt, int half) { return tS + (gt & 1) * 128 + part * 32 + half * 16 + lane_off; };
+
+        // Software pipeline over the CTA's running key tiles. Invariant at the top of iteration g: half 0 of tile g is loading into h0.
+        int w = w0, i = 0, j = 0;
+        ItemState cur = make_item(w);
+        unsigned int mbits = 0u;
+        if (G > 0) {
+            mbits = cur.rows_live ? cur.mb[0] : 0u;
+            wait_s(0);
+            if (mbits != 0u) tmem_ld16(s_addr(0, 0), h0);
+        }
+        for (int g = 0; g < G; ++g) {
+            const int pb = g & 1;
+            const bool last = j == nkv - 1;
+            // the tile after this one: next key tile of the item, or the first one of the CTA's next item
+            ItemState nxt = cur;
+            unsigned int mnext = 0u;
+            if (!last) {
+                mnext = cur.rows_live ? cur.mb[(j + 1) * 4] : 0u;
+            } else if (g + 1 < G) {
+                nxt = make_item(w + wstep);
+                mnext = nxt.rows_live ? nxt.mb[0] : 0u;
+            }
+            const unsigned long long drop_base = cur.drop_row + (unsigned long long)(j * TKV + part * 32);
+            uint32_t pk[16];
+            if (mbits != 0u) {
+                tmem_ld_wait();                              // half 0 has landed
+                tmem_ld16(s_addr(g, 1), h1);                 // half 1 loads under the math of half 0
+                half_math(h0, mbits & 0xffffu, drop_base);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[e] = h0[e];
+                tmem_ld_wait();                              // half 1 has landed: the S buffer is free
+            }
+            release_s(g);
+            if (g + 1 < G) {                                 // next tile's half 0 loads under the math of half 1
+                wait_s(g + 1);
+                if (mnext != 0u) tmem_ld16(s_addr(g + 1, 0), h0);
+            }
+            if (mbits != 0u) {
+                half_math(h1, mbits >> 16, drop_base + 16ull);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk[8 + e] = h1[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pk[e] = 0u;
+            }
+            // the P buffer was last read by the PV MMA of running tile g-2
+            mbar_wait(&p_empty[pb], ((g >> 1) & 1) ^ 1);
+            uint8_t* pdst = sP + pb * PTILE + (part >> 1) * TILE16 + row * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int chunk = (part & 1) * 4 + c;
+                *reinterpret_cast<uint4*>(pdst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+            }
+            fence_proxy_async();        // make the generic-proxy smem writes of P visible to the tensor-core (async) proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[pb]);
+            mbits = mnext;
+            if (!last) { ++j; continue; }
+            // ---- item epilogue (the next item's first half-tile is already loading): total row sum over the four quarters, normalise,
+            //      write O (ungated), Og (gated, head-merged) and LSE
+            float* xch = s_xch + (i & 1) * 512;
             xch[part * 128 + row] = l2.x + l2.y;
             asm volatile("bar.sync 1, 512;" ::: "memory");
             const float l_tot = (xch[row] + xch[128 + row]) + (xch[256 + row] + xch[384 + row]);
-            const int ob = item_idx & 1;
-            mbar_wait(&o_full[ob], (item_idx >> 1) & 1);
+            const int ob = i & 1;
+            mbar_wait(&o_full[ob], (i >> 1) & 1);
             tc_fence_after();
             uint32_t ro[16];
             tmem_ld16(tO + ob * 64 + part * 16 + lane_off, ro);
-            tmem_ld_wait();
+            tmem_ld_wait();             // (also covers the prefetched half 0 of the next item's first tile)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[ob]);
+            const FwdItem it = fwd_item(w, nq, p.H);
+            const int qi = it.qt * TQ + row, bh = it.b * p.H + it.hh;
             if (qi < p.Np) {
                 const float inv = l_tot > 0.f ? p.keep_scale / l_tot : 0.f;
                 const float gt = p.gate ? p.gate[((size_t)it.b * p.Np + qi) * p.H + it.hh] : 1.f;
@@ -388,8 +419,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
                 if (part == 0) p.lse[(size_t)bh * p.Np + qi] = logf(l_tot);
             }
-        };
-        for (int w = w0; w < n_items; w += wstep, ++i) run_item(w, i, g);
+            cur = nxt; w += wstep; ++i; j = 0;
+            l2 = make_float2(0.f, 0.f);
+        }
     }
     tc_fence_before();
     __syncthreads();

@@ -42,11 +42,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#ifdef B200_WAIT_NO_HINT   // developer A/B: the plain form (hardware default suspend time)
+    asm volatile(
+        "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(B200_WAIT_HINT_NS)
         : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ unsigned long long global_ns() {

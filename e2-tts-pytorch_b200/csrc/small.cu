@@ -472,43 +472,71 @@ __global__ void __launch_bounds__(256) cfg_apply_kernel(const float* pred, const
 
 // ------------------------------------------------------------------------------------------------ MelSpec
 // torchaudio MelSpectrogram(n_fft = win, hop, center/reflect, power 1, HTK fb) -> log(clamp(., 1e-5)) (e2_tts.py:248-290).
-// One block per (frame, batch): windowed frame in smem, direct 1024-point real DFT with an smem twiddle table
-// (index (k*n) mod n_fft), magnitude, dense mel filterbank, log. Output [B, n_mels, frames] like the reference.
-__global__ void __launch_bounds__(256) melspec_kernel(const float* wave, const float* window, const float* fb, float* out, int nw, int n_fft,
-                                                       int hop, int n_mels, int frames) {
+// One block per (frame, batch): the windowed frame goes through an in-place radix-2 FFT in shared memory (bit-reversed load,
+// log2(n_fft) butterfly stages, one smem twiddle table per block), magnitudes of the n_fft/2+1 bins, then the mel filterbank
+// restricted to each filter's non-zero band (HTK triangles: 1 008 of the 51 300 entries of the reference's 513 x 100 matrix are
+// non-zero; the bands are found once per call by mel_bands_kernel), log. Output [B, n_mels, frames] like the reference.
+// (Round 1 used a direct O(n^2) DFT and the dense filterbank: ~1 M serial FMAs per frame.)
+__global__ void mel_bands_kernel(const float* __restrict__ fb, int nbins, int n_mels, int2* __restrict__ bands) {
+    pdl_wait();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mels) return;
+    int lo = nbins, hi = 0;
+    for (int k = 0; k < nbins; ++k)
+        if (fb[(size_t)k * n_mels + m] != 0.f) { lo = min(lo, k); hi = k + 1; }
+    bands[m] = make_int2(lo, hi);   // empty filter: lo >= hi
+}
+
+__global__ void __launch_bounds__(256) melspec_kernel(const float* __restrict__ wave, const float* __restrict__ window, const float* __restrict__ fb,
+                                                       const int2* __restrict__ bands, float* __restrict__ out, int nw_max, int n_fft, int log2n,
+                                                       int hop, int n_mels, int frames, const int* __restrict__ wave_lens, int out_bnd) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
-    extern __shared__ float msm[];
-    float* xs = msm;                 // [n_fft]
-    float* cs = xs + n_fft;          // [n_fft]
-    float* sn = cs + n_fft;          // [n_fft]
-    float* mag = sn + n_fft;         // [n_fft/2 + 1]
+    extern __shared__ float2 zsm[];
+    float2* z = zsm;                 // [n_fft] in-place FFT buffer
+    float2* tw = z + n_fft;          // [n_fft/2] twiddles e^{-2 pi i k / n_fft}
+    float* mag = reinterpret_cast<float*>(tw + n_fft / 2);   // [n_fft/2 + 1]
     const int f = blockIdx.x, b = blockIdx.y;
     const int pad = n_fft / 2, nbins = n_fft / 2 + 1;
+    // ragged batch (on-device collate, trainer.py:61-82): sample b has wave_lens[b] samples -> 1 + len/hop frames, reflect-padded at ITS
+    // end; the frames behind them are the collate's zero padding
+    const int nw = wave_lens ? min(wave_lens[b], nw_max) : nw_max;
+    if (wave_lens && (f >= 1 + nw / hop || nw <= pad)) {
+        for (int m = threadIdx.x; m < n_mels; m += 256)
+            out[out_bnd ? ((size_t)b * frames + f) * n_mels + m : ((size_t)b * n_mels + m) * frames + f] = 0.f;
+        return;
+    }
     for (int n = threadIdx.x; n < n_fft; n += 256) {
-        int j = f * hop + n - pad;
+        int j = f * hop + n - pad;               // center=True, reflect padding
         if (j < 0) j = -j;
         if (j >= nw) j = 2 * (nw - 1) - j;
-        xs[n] = wave[(size_t)b * nw + j] * window[n];
-        float s, c;
-        sincospif(2.f * (float)n / (float)n_fft, &s, &c);
-        cs[n] = c; sn[n] = s;
+        const int r = (int)(__brev((unsigned)n) >> (32 - log2n));
+        z[r] = make_float2(wave[(size_t)b * nw_max + j] * window[n], 0.f);
+        if (n < n_fft / 2) {
+            float sn, cs;
+            sincospif(-2.f * (float)n / (float)n_fft, &sn, &cs);
+            tw[n] = make_float2(cs, sn);
+        }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < nbins; k += 256) {
-        float re = 0.f, im = 0.f;
-        int idx = 0;
-        for (int n = 0; n < n_fft; ++n) {
-            re += xs[n] * cs[idx];
-            im -= xs[n] * sn[idx];
-            idx = (idx + k) & (n_fft - 1);
+    for (int s = 1; s <= log2n; ++s) {
+        const int half = 1 << (s - 1), tstride = n_fft >> s;
+        for (int t = threadIdx.x; t < n_fft / 2; t += 256) {
+            const int pos = t & (half - 1);
+            const int i = ((t >> (s - 1)) << s) + pos, j = i + half;
+            const float2 w = tw[pos * tstride], u = z[i], x = z[j];
+            const float2 v = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+            z[i] = make_float2(u.x + v.x, u.y + v.y);
+            z[j] = make_float2(u.x - v.x, u.y - v.y);
         }
-        mag[k] = sqrtf(re * re + im * im);
+        __syncthreads();
     }
+    for (int k = threadIdx.x; k < nbins; k += 256) mag[k] = sqrtf(z[k].x * z[k].x + z[k].y * z[k].y);   // power = 1
     __syncthreads();
     for (int m = threadIdx.x; m < n_mels; m += 256) {
+        const int2 bd = bands[m];
         float acc = 0.f;
-        for (int k = 0; k < nbins; ++k) acc += mag[k] * __ldg(fb + (size_t)k * n_mels + m);
-        out[((size_t)b * n_mels + m) * frames + f] = logf(fmaxf(acc, 1e-5f));
+        for (int k = bd.x; k < bd.y; ++k) acc += mag[k] * __ldg(fb + (size_t)k * n_mels + m);
+        out[out_bnd ? ((size_t)b * frames + f) * n_mels + m : ((size_t)b * n_mels + m) * frames + f] = logf(fmaxf(acc, 1e-5f));
     }
 }
 
@@ -616,13 +644,20 @@ extern "C" int b200_cfg_combine(const float* pred, const float* null_pred, doubl
     return check_launch("cfg_apply_kernel");
 }
 extern "C" int b200_melspec(const float* wave, const float* window, const float* fb, float* out, int32_t B, int32_t nw, int32_t n_fft,
-                            int32_t hop, int32_t n_mels, b200_stream_t stream) {
-    B200_REQUIRE(wave && window && fb && out && B > 0 && B <= 65535, "melspec: bad arguments");
+                            int32_t hop, int32_t n_mels, int32_t* ws_bands, const int32_t* wave_lens, int32_t out_bnd, b200_stream_t stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B200_REQUIRE(wave && window && fb && out && ws_bands && B > 0 && B <= 65535, "melspec: bad arguments");
     B200_REQUIRE(n_fft >= 64 && (n_fft & (n_fft - 1)) == 0 && n_fft <= 4096 && hop > 0 && nw > n_fft / 2, "melspec: n_fft must be a power of two <= 4096 and the wave longer than n_fft/2");
+    B200_REQUIRE(n_mels > 0 && (reinterpret_cast<uintptr_t>(ws_bands) & 7) == 0, "melspec: ws_bands must be 8-byte aligned");
     const int frames = 1 + nw / hop;
-    const size_t smem = (size_t)(3 * n_fft + n_fft / 2 + 1) * sizeof(float);
+    int log2n = 0;
+    while ((1 << log2n) < n_fft) ++log2n;
+    int2* bands = reinterpret_cast<int2*>(ws_bands);
+    B200_LAUNCH(mel_bands_kernel, (n_mels + 127) / 128, 128, 0, st, fb, n_fft / 2 + 1, n_mels, bands);
+    if (int rc = check_launch("mel_bands_kernel")) return rc;
+    const size_t smem = (size_t)n_fft * 8 + (size_t)(n_fft / 2) * 8 + (size_t)(n_fft / 2 + 1) * 4;
     static DeviceOnce once;
     B200_REQUIRE(set_max_smem_once(once, melspec_kernel, 64 * 1024) == cudaSuccess, "melspec: cudaFuncSetAttribute failed");
-    B200_LAUNCH(melspec_kernel, dim3(frames, B), 256, smem, reinterpret_cast<cudaStream_t>(stream), wave, window, fb, out, nw, n_fft, hop, n_mels, frames);
+    B200_LAUNCH(melspec_kernel, dim3(frames, B), 256, smem, st, wave, window, fb, bands, out, nw, n_fft, log2n, hop, n_mels, frames, wave_lens, out_bnd);
     return check_launch("melspec_kernel");
 }

@@ -538,6 +538,8 @@ class Transformer(Module):
         assert x.ndim == 3, '`has_freq_axis` is not supported by the B200 build'
         assert not (exists(times) ^ self.cond_on_time), '`times` must be passed in if `cond_on_time` is set to `True` and vice versa'
         B, N, d = x.shape
+        if torch.is_grad_enabled():
+            ops.zero_pool.begin(x.device)
         h = ops.CastRows.apply(x.reshape(B * N, d))
         te = ops.CastRows.apply(text_embed.reshape(B * N, -1)) if exists(text_embed) else None
         y = self._forward_from_h(h, B, N, times, mask, te_bf16=te)
@@ -616,6 +618,33 @@ class MelSpec(Module):
             self.to(inp.device)
         return ops.melspec(inp.to(F32).contiguous(), self.mel_stft.spectrogram.window, self.mel_stft.mel_scale.fb, self.n_fft, self.hop)
 
+    def collate(self, waves, lens=None):
+        """On-device data path: what the reference does per item on CPU workers — `MelSpec` in HFDataset.__getitem__
+        (trainer.py:101-131) — and per batch in `collate_fn` (:61-82: zero-pad the mels to the longest, lengths) plus the trainer's
+        `rearrange(batch['mel'], 'b d n -> b n d')` (:253), as ONE kernel launch over the ragged batch.
+        waves: list of 1-D fp32 tensors at `sampling_rate` (resampling is the dataset's job) or a zero-padded [B, nw_max] tensor with
+        `lens` (samples per sequence). Returns dict(mel [B, n_frames_max, n_mels] fp32, mel_lengths [B] int64) — pass as
+        `model(batch['mel'], text=..., lens=batch['mel_lengths'])`."""
+        if isinstance(waves, (list, tuple)):
+            dev = self.dummy.device if self.dummy.device.type == 'cuda' else waves[0].device
+            lens = torch.tensor([w.shape[-1] for w in waves], dtype=torch.int32)
+            nmax = int(lens.max())
+            padded = torch.zeros((len(waves), nmax), dtype=F32).pin_memory() if dev.type == 'cuda' and not waves[0].is_cuda else torch.zeros((len(waves), nmax), dtype=F32, device=waves[0].device)
+            for i, w in enumerate(waves):
+                padded[i, :w.shape[-1]] = w.reshape(-1)
+            waves = padded.to(dev, non_blocking=True)
+            lens = lens.to(dev, non_blocking=True)
+        else:
+            assert lens is not None and waves.ndim == 2
+            lens = lens.to(device=waves.device, dtype=torch.int32)
+        if self.dummy.device != waves.device:
+            self.to(waves.device)
+        mel = ops.melspec(waves.to(F32).contiguous(), self.mel_stft.spectrogram.window, self.mel_stft.mel_scale.fb, self.n_fft, self.hop,
+                          wave_lens=lens.contiguous(), out_bnd=True)
+        mel_lengths = 1 + lens.long() // self.hop
+        n_max = int(1 + waves.shape[1] // self.hop)
+        return dict(mel=mel[:, :n_max], mel_lengths=mel_lengths)
+
 
 # ----------------------------------------------------------------------------------------------------------------------
 
@@ -676,6 +705,8 @@ class DurationPredictor(Module):
         x = x.to(F32).contiguous()
         B, N, C = x.shape
         dev = x.device
+        if torch.is_grad_enabled() and return_loss:
+            ops.zero_pool.begin(dev)
         Cp = (C + 7) // 8 * 8
         if self._wpack is None or self._wpack[0].device != dev:
             w = torch.zeros((self.dim, Cp), device=dev, dtype=BF16)
@@ -924,6 +955,8 @@ class E2TTS(Module):
         x1 = inp.to(F32).contiguous()
         B, N, C = x1.shape
         dev = self.device
+        if torch.is_grad_enabled():
+            ops.zero_pool.begin(dev)
         if isinstance(text, list):
             text = self.tokenizer(text).to(dev)
             assert text.shape[0] == B

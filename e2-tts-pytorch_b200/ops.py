@@ -27,6 +27,41 @@ def _c(t):
     return t if t is None or t.is_contiguous() else t.contiguous()
 
 
+class _ZeroPool:
+    """One zero-filled fp32 slab per training step for the ~300 small gradient accumulators the backward kernels add into
+    (hyper-connection parameter grads, conv weight/bias grads, bias column sums, gate grads, abs-pos grads): ONE memset per step
+    instead of 300 `torch.zeros` fill kernels (3.1 % of the round-1 step, profiles/r1h_launch_summary.txt). `begin()` is called by the
+    model's forward when a backward will follow; a fresh slab is allocated every step (gradients handed to autograd alias it and
+    must outlive the step), sized by the previous step's demand; anything that does not fit falls back to torch.zeros."""
+
+    def __init__(self):
+        self.buf, self.off, self.used, self.peak = None, 0, 0, 0
+
+    def begin(self, device):
+        self.peak = max(self.peak, self.used)
+        self.used, self.off = 0, 0
+        self.buf = torch.zeros(int(self.peak * 1.1) + 4096, device=device, dtype=F32) if self.peak else None
+
+    def zeros(self, shape, device):
+        n = 1
+        for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
+            n *= int(d)
+        n_al = (n + 31) // 32 * 32      # 128-byte aligned slices
+        self.used += n_al
+        if self.buf is None or self.buf.device != device or self.off + n_al > self.buf.numel():
+            return torch.zeros(shape, device=device, dtype=F32)
+        out = self.buf[self.off:self.off + n].view(shape)
+        self.off += n_al
+        return out
+
+
+zero_pool = _ZeroPool()
+
+
+def _zeros(shape, device):
+    return zero_pool.zeros(shape, device)
+
+
 def gemm(A, B, M, N, K, *, lda=None, ldb=None, A2=None, lda2=0, K1=0, a_mn=False, b_mn=False, out=None, ldd=None,
          out_fp32=False, D2=None, ldd2=0, bias=None, colscale=None, rows_per_batch=0, rowmask=None, resid=None, ldr=0,
          geglu=False, dropout_p=0.0, seed=0, split_k=1, force_tile=0, seed_dev=None):
@@ -64,7 +99,7 @@ def grad_weight(dY, X, T, n_out, n_in, *, ldy=None, ldx=None, out=None, ldd=None
 
 
 def colsum(X, T, ncols, ld):
-    out = torch.zeros(ncols, device=X.device, dtype=F32)
+    out = _zeros(ncols, X.device)
     lib.call('b200_colsum', X, T, ncols, ld, out, _stream())
     return out
 
@@ -110,7 +145,7 @@ class HcWidth(Function):
         # one zero-filled fp32 slab for all parameter-gradient accumulators
         n_gain = 0 if norm_mode == 0 else norm_gain.numel()
         sizes = [D, D * (S + 1), 1, S * (S + 1), D, 1, S, n_gain]
-        slab = torch.zeros(sum(sizes), device=dev, dtype=F32)
+        slab = _zeros(sum(sizes), dev)
         parts, o = [], 0
         for n in sizes:
             parts.append(slab[o:o + n])
@@ -176,8 +211,8 @@ class DwConv(Function):
         D = x.shape[-1]
         w2 = weight.reshape(D, -1)
         dx = torch.empty_like(x)
-        dw = torch.zeros_like(w2)
-        db = torch.zeros_like(bias)
+        dw = _zeros(w2.shape, w2.device)
+        db = _zeros(bias.shape, bias.device)
         a = lib.make_args('b200_dwconv_args', x=x, mask=mask, weight=w2, bias=bias, dy=_c(dy), dx=dx, dweight=dw, dbias=db,
                           B=B, Np=Np, D=D, ksize=w2.shape[1])
         lib.call('b200_dwconv_bwd', a, _stream())
@@ -334,8 +369,8 @@ def _rowgate_bwd(dy, y, cs, mask, B, rpb, D, want_bias=False):
     if cs is None and mask is None:
         return (dy, None, None) if want_bias else (dy, None)
     dz = torch.empty_like(dy)
-    d_cs = torch.zeros_like(cs) if cs is not None else None
-    d_bias = torch.zeros(D, device=dy.device, dtype=F32) if want_bias else None
+    d_cs = _zeros(cs.shape, cs.device) if cs is not None else None
+    d_bias = _zeros(D, dy.device) if want_bias else None
     lib.call('b200_rowgate_bwd', dy, y, cs, mask, dz, d_cs, d_bias, B, rpb, D, _stream())
     return (dz, d_cs, d_bias) if want_bias else (dz, d_cs)
 
@@ -394,7 +429,7 @@ class FeedForward(Function):
         dh = gemm(dz, w2pack, T, inner, Din, b_mn=True)
         dW2 = grad_weight(dz, h, T, Din, inner)
         dug = torch.empty_like(ug)
-        db1p = torch.zeros(2 * inner, device=xn.device, dtype=F32)
+        db1p = _zeros(2 * inner, xn.device)
         lib.call('b200_geglu_bwd', dh, ug, dug, db1p, T, inner, float(dropout_p), int(seed), seed_dev, _stream())
         dx = gemm(dug, w1pack, T, Din, 2 * inner, b_mn=True)
         dW1p = grad_weight(dug, xn, T, 2 * inner, Din)
@@ -524,7 +559,7 @@ class Assemble(Function):
         R = registers.shape[0]
         dev = registers.device
         d_h = torch.empty((B * N, D), device=dev, dtype=BF16)
-        d_abs = torch.zeros((max_len, D), device=dev, dtype=F32) if max_len else None
+        d_abs = _zeros((max_len, D), dev) if max_len else None
         d_reg = torch.empty((R, D), device=dev, dtype=F32)
         a = lib.make_args('b200_assemble_args', h=d_h, registers=registers, d_out=_c(d_out), d_h=d_h, d_abs_pos=d_abs, d_registers=d_reg,
                           B=B, N=N, R=R, D=D, S=S)
@@ -584,7 +619,7 @@ class FinalNorm(Function):
         B, N, R = ctx.meta
         T, S, D = xres.shape
         d_xres = torch.empty_like(xres)
-        g_g = torch.zeros_like(g)
+        g_g = _zeros(g.shape, g.device)
         a = lib.make_args('b200_final_norm_args', xres=xres, g=g, dy=_c(dy), d_xres=d_xres, g_g=g_g, B=B, N=N, R=R, D=D, S=S)
         lib.call('b200_final_norm_bwd', a, _stream())
         return d_xres, g_g, None, None, None
@@ -796,10 +831,13 @@ def cfg_combine(pred, null_pred, strength, remove_parallel, keep_frac):
     return out
 
 
-def melspec(wave, window, fb, n_fft, hop):
-    """MelSpec front-end (e2_tts.py:248-290): fp32 [B, nw] -> [B, n_mels, frames]."""
+def melspec(wave, window, fb, n_fft, hop, wave_lens=None, out_bnd=False):
+    """MelSpec front-end (e2_tts.py:248-290): fp32 [B, nw] -> [B, n_mels, frames] (or [B, frames, n_mels] with out_bnd); wave_lens
+    (int32 [B]) makes it the on-device collate of a zero-padded ragged batch (trainer.py:61-82)."""
     B, nw = wave.shape
     n_mels = fb.shape[1]
-    out = torch.empty((B, n_mels, 1 + nw // hop), device=wave.device, dtype=F32)
-    lib.call('b200_melspec', wave, _c(window), _c(fb), out, B, nw, n_fft, hop, n_mels, _stream())
+    frames = 1 + nw // hop
+    out = torch.empty((B, frames, n_mels) if out_bnd else (B, n_mels, frames), device=wave.device, dtype=F32)
+    bands = torch.empty(2 * n_mels, device=wave.device, dtype=torch.int32)
+    lib.call('b200_melspec', wave, _c(window), _c(fb), out, B, nw, n_fft, hop, n_mels, bands, wave_lens, int(out_bnd), _stream())
     return out

@@ -291,9 +291,15 @@ int b200_axpy(const float* y, const float* f, float a, float* out, int64_t n, b2
  * out = pred + (orth + par * keep) * strength per sample over all n*d elements. ws_red: 2*B doubles. */
 int b200_cfg_combine(const float* pred, const float* null_pred, double* ws_red, float* out, int32_t B, int64_t per_sample,
                      float cfg_strength, int32_t remove_parallel, float keep_parallel_frac, b200_stream_t stream);
-/* MelSpec (e2_tts.py:248-290): wave fp32 [B, nw] -> log-mel fp32 [B, n_mels, 1 + nw/hop]; window [n_fft], fb [n_fft/2+1, n_mels]. */
+/* MelSpec (e2_tts.py:248-290): wave fp32 [B, nw] -> log-mel fp32 [B, n_mels, 1 + nw/hop]; window [n_fft], fb [n_fft/2+1, n_mels].
+ * Shared-memory radix-2 FFT per frame + band-limited filterbank; ws_bands: caller workspace of 2 * n_mels int32 (8-byte aligned),
+ * filled by the call with each filter's non-zero bin range.
+ * On-device collate (trainer.py:61-82 collate_fn + :101-131 HFDataset.__getitem__): wave_lens (optional int32 [B]) =
+ * samples per sequence of a zero-padded ragged batch — sequence b yields 1 + wave_lens[b]/hop frames (reflect-padded at its own end),
+ * the remaining frames are the collate's zero padding; out_bnd != 0 writes [B, frames, n_mels] (the layout E2TTS.forward consumes,
+ * trainer.py:253 rearrange 'b d n -> b n d') instead of the reference MelSpec's [B, n_mels, frames]. */
 int b200_melspec(const float* wave, const float* window, const float* fb, float* out, int32_t B, int32_t nw, int32_t n_fft,
-                 int32_t hop, int32_t n_mels, b200_stream_t stream);
+                 int32_t hop, int32_t n_mels, int32_t* ws_bands, const int32_t* wave_lens, int32_t out_bnd, b200_stream_t stream);
 
 
 /* ------------------------------------------------------------------------------------------------

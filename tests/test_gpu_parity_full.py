@@ -173,7 +173,11 @@ def test_attention_core_vs_fp32_softmax(pkg, Np, H, big_logits):
 def _whole_model(pkg, tkw, B, N, lens, seed, tol_pred=3e-2):
     torch.manual_seed(seed)
     model = pkg.E2TTS(transformer=dict(dropout=0., max_seq_len=N, **tkw), use_vocos=False)
-    sd = O.randomize_zero_init({k: v.clone() for k, v in model.state_dict().items()}, seed=seed + 1)
+    # dyn_scale 0.05 (5x the reference's init of the hyper-connections' dynamic scales): with the 0.5 of the 2-layer fixtures a depth-8
+    # stack amplifies bf16 rounding of the residual streams ~10x — the fp32 oracle with its OWN stage outputs rounded to bf16
+    # (O.STAGE_ROUND) then moves its prediction by 12.6 %, exactly what the kernels showed (gpurun_out/r2b_pytest.log). The probe below
+    # keeps this test honest: the case must be well conditioned for a bf16 path before the kernels are held to 3e-2.
+    sd = O.randomize_zero_init({k: v.clone() for k, v in model.state_dict().items()}, seed=seed + 1, dyn_scale=0.05)
     model.load_state_dict(sd)
     model.to(dev()).train()
     mel = torch.randn(B, N, 100)
@@ -191,9 +195,18 @@ def _whole_model(pkg, tkw, B, N, lens, seed, tol_pred=3e-2):
     osd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     ref = O.e2tts_forward(osd, O.TransformerCfg(**tkw), mel, O.list_str_to_tensor(text), x0=x0, times=times, span_mask=span, lens=lens_t)
     ref['loss'].backward()
+    O.STAGE_ROUND = O.bf16_ste
+    try:
+        with torch.no_grad():
+            probe = O.e2tts_forward(sd, O.TransformerCfg(**tkw), mel, O.list_str_to_tensor(text), x0=x0, times=times, span_mask=span, lens=lens_t)
+    finally:
+        O.STAGE_ROUND = None
+    e_probe = rel_l2(probe['pred'], ref['pred'].detach())
+    assert e_probe < 1.5e-2, f'test case is ill-conditioned for bf16 activations (oracle vs bf16-stage oracle: {e_probe:.3g})'
     loss, rloss = float(out.loss), float(ref['loss'])
     assert abs(loss - rloss) <= 1e-2 * abs(rloss), (loss, rloss)
     check('pred', out.pred_flow, ref['pred'].detach(), tol_pred)
+    print(f'pred rel-L2 {rel_l2(out.pred_flow.float().cpu(), ref["pred"].detach()):.4g} (bf16-stage oracle probe {e_probe:.4g})')
     total = float(torch.cat([v.grad.flatten() for v in osd.values() if v.grad is not None]).norm())
     worst = (1.0, None)
     for k, p in model.named_parameters():
@@ -318,3 +331,28 @@ def test_velocity_consistency_loss_vs_oracle(pkg):
         out2 = model(mel.to(dev()), text=text, lens=lens.to(dev()))
     assert float(out2.loss_breakdown.velocity_consistency) == 0.0
     assert abs(float(out2.loss) - float(ref['flow_loss'])) <= 1e-2 * abs(float(ref['flow_loss']))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# on-device data path — MelSpec per item (trainer.py:101-131) + collate_fn (:61-82) + 'b d n -> b n d' (:253) as one launch
+def test_melspec_collate_ragged_batch_vs_per_item_reference(pkg):
+    torch.manual_seed(100)
+    ms = pkg.MelSpec().to(dev())
+    lens = [256 * 24, 256 * 17 + 100, 5000, 256 * 24 - 1]
+    waves = [torch.randn(n) * 0.3 for n in lens]
+    batch = ms.collate(waves)
+    per_item = [O.melspec(w[None])[0] for w in waves]                 # [n_mels, frames_i] each (torchaudio semantics, pinned by test_oracle_*)
+    n_max = max(m.shape[-1] for m in per_item)
+    want = torch.stack([F.pad(m, (0, n_max - m.shape[-1])) for m in per_item]).transpose(1, 2)   # collate_fn zero-pads, trainer transposes
+    assert batch['mel'].shape == want.shape, (batch['mel'].shape, want.shape)
+    assert batch['mel_lengths'].tolist() == [m.shape[-1] for m in per_item]
+    assert float((batch['mel'].cpu() - want).abs().max()) < 1e-3
+    # the batched output feeds the model directly
+    model = pkg.E2TTS(transformer=dict(dim=128, depth=2, heads=2), use_vocos=False).to(dev())
+    out = model(batch['mel'], text=['a', 'b', 'c', 'd'], lens=batch['mel_lengths'])
+    assert torch.isfinite(out.loss)
+    # a long wave at the benchmark's frame count (1024 frames) against the oracle
+    wave = torch.randn(2, 256 * 1023) * 0.2
+    got = ms(wave.to(dev()))
+    assert got.shape == (2, 100, 1024)
+    assert float((got.cpu() - O.melspec(wave)).abs().max()) < 1e-3

@@ -36,7 +36,7 @@ if 'attn' in which:
     gate = torch.rand(T, H, device=dev).requires_grad_()
     m = torch.ones(B, Np, dtype=torch.uint8, device=dev)
     for _ in range(reps):
-        og = ops.AttnCore.apply(q, k, v, gate, m, 0.1, 7, 50.0)
+        og = ops.AttnCore.apply(q, k, v, gate, m, 0.1, 7, 50.0, None)
         torch.autograd.grad(og, [q, k, v], torch.ones_like(og))
 torch.cuda.synchronize()
 print('done')

@@ -211,6 +211,7 @@ def run_gpu(args):
         model = pkg.E2TTS(transformer=tkw, use_vocos=False).to(dev)
         model.cond_drop_prob = 0.0  # text conditioning on every step: the expensive branch, identical graph on every rank
     model.train()
+    pkg.broadcast_module(model)      # identical replicas, as DDP's constructor guarantees (part of the init is rank dependent)
     sync = pkg.GradSync(list(model.parameters())) if (world > 1 and kind != 'sample') else None   # eager N > 1 step: flat all-reduce too
     torch.manual_seed(rank)
     n_in = cfg['prompt'] if kind == 'sample' else N

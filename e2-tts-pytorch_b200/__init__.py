@@ -11,6 +11,6 @@ from .modules import (  # noqa: E402,F401
 )
 from . import lib, ops, optim  # noqa: E402,F401
 from .graphed import GraphedTrainStep  # noqa: E402,F401
-from .optim import GradSync, FusedAdoptEMA  # noqa: E402,F401
+from .optim import GradSync, FusedAdoptEMA, broadcast_module  # noqa: E402,F401
 
-__all__ = ['E2TTS', 'DurationPredictor', 'Transformer', 'MelSpec', 'E2TTSReturn', 'LossBreakdown', 'inject_randomness', 'GraphedTrainStep', 'GradSync', 'FusedAdoptEMA']
+__all__ = ['E2TTS', 'DurationPredictor', 'Transformer', 'MelSpec', 'E2TTSReturn', 'LossBreakdown', 'inject_randomness', 'GraphedTrainStep', 'GradSync', 'FusedAdoptEMA', 'broadcast_module']

@@ -355,9 +355,9 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const __nv_bfloat16* dh,
                 const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned long long)inner + hcol) >> 1);
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {
-                    const uint32_t hsh = hash_pair32(seedmix, pbase + (j >> 1));
-                    d[j] = ((hsh & 0xffffu) >= thr) ? d[j] * ks : 0.f;
-                    d[j + 1] = ((hsh >> 16) >= thr) ? d[j + 1] * ks : 0.f;
+                    const DropWords hsh = drop_words(seedmix, pbase + (j >> 1));
+                    d[j] = (hsh.a >= drop_thresh32(thr)) ? d[j] * ks : 0.f;
+                    d[j + 1] = (hsh.b >= drop_thresh32(thr)) ? d[j + 1] * ks : 0.f;
                 }
             }
 #pragma unroll

@@ -268,20 +268,28 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float 
     return (hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
-// Attention dropout: one cheap 32-bit hash (murmur3 finaliser) decides TWO neighbouring keys (16 bits each): keep iff
-// half >= thresh, thresh = p * 65536. idx = row_id * drop_stride + key with drop_stride even, so (idx >> 1) pairs keys
-// (2k, 2k+1) of one query row; only the low 32 bits of the pair index are hashed (the pattern repeats after 2^33 scores).
-__device__ __forceinline__ uint32_t hash_pair32(uint32_t seedmix, uint32_t pair) {
-    // one multiply-xorshift round after the golden-ratio counter step: 6 integer ops per PAIR of dropout decisions (the two-round
-    // murmur finaliser used first was 9, and the softmax / GEGLU threads that call this are ALU-pipe bound)
+// Dropout masks: counter-based, recomputed by the backward kernels from the same (seed, index). One mixing step decides TWO
+// neighbouring elements: x = pair * golden + seed; x ^= x >> 15; then the HIGH bits of two different odd multiples of x are compared
+// against the threshold as full 32-bit words — keep iff word >= thresh16 << 16, i.e. P(drop) = thresh16 / 65536. idx = row_id *
+// stride + column with an even stride, so (idx >> 1) pairs columns (2k, 2k+1) of one row; only the low 32 bits of the pair index
+// are hashed (the pattern repeats after 2^33 elements).
+// Cost per pair: 3 IMAD (FMA pipe) + SHF + LOP3 + 2 ISETP (+ the two selects): the round-1 hash (two xorshift-multiply rounds, then
+// 16-bit field extraction) put 10 instructions per pair on the half-rate ALU pipe, which the softmax threads of the attention kernels
+// are bound by (ncu r2c: ALU pipe 42 %, dropout = 160 of the 509 instructions per warp and key tile).
+struct DropWords { uint32_t a, b; };
+__device__ __forceinline__ DropWords drop_words(uint32_t seedmix, uint32_t pair) {
     uint32_t x = pair * 0x9E3779B1u + seedmix;
-    x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 16;
-    return x;
+    x ^= x >> 15;
+    DropWords w;
+    w.a = x * 0x85EBCA6Bu;
+    w.b = x * 0xC2B2AE35u;
+    return w;
 }
+__device__ __forceinline__ uint32_t drop_thresh32(uint32_t thresh16) { return thresh16 << 16; }
 __device__ __forceinline__ uint32_t seed_mix32(uint64_t seed) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA77u); }
 __device__ __forceinline__ bool dropout_keep16(uint64_t seed, uint64_t idx, uint32_t thresh) {
-    const uint32_t h = hash_pair32(seed_mix32(seed), (uint32_t)(idx >> 1));
-    return ((idx & 1) ? (h >> 16) : (h & 0xffffu)) >= thresh;
+    const DropWords w = drop_words(seed_mix32(seed), (uint32_t)(idx >> 1));
+    return ((idx & 1) ? w.b : w.a) >= drop_thresh32(thresh);
 }
 
 }  // namespace b200

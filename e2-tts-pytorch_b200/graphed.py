@@ -24,7 +24,7 @@ from __future__ import annotations
 import torch
 
 from . import lib
-from .optim import GradSync
+from .optim import GradSync, broadcast_module
 
 
 class GraphedTrainStep:
@@ -45,6 +45,8 @@ class GraphedTrainStep:
         self.text = text.clone() if torch.is_tensor(text) else (model.tokenizer(text).to(dev) if isinstance(text, list) else None)
         self.lens = lens.clone() if torch.is_tensor(lens) else None
         world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if world > 1:
+            broadcast_module(model, 0, process_group)    # replicas must start identical (DDP does this when it wraps the module)
         use_flat = (world > 1) if flat_grads is None else bool(flat_grads) or world > 1
         self.grad_sync = GradSync(list(model.parameters()), process_group) if use_flat else None
         # the device seed word: every dropout seed of the step is `host seed + *seed_dev` (frozen host part, stepping device part)

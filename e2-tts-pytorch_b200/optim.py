@@ -79,6 +79,24 @@ class FlatLayout:
         return [flat[o:o + n].view_as(p) for o, n, p in zip(self.offsets, self.numels, self.params)]
 
 
+def broadcast_module(module, src=0, process_group=None):
+    """Make every rank start from rank `src`'s parameters AND buffers — what DistributedDataParallel does when it wraps a module
+    (trainer.py:155-162 via accelerate). Needed because part of the reference's initialisation is rank dependent: the
+    hyper-connections pick their initial stream with python's `randrange` and RandomFourierEmbed draws its
+    frequencies with torch.randn (e2_tts.py:358), so replicas seeded only through torch.manual_seed are NOT identical."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=process_group)
+    for m in module.modules():            # packed bf16 operand caches are derived from the parameters
+        if hasattr(m, '_pack'):
+            m._pack, m._packed = None, None
+        if hasattr(m, '_wpack'):
+            m._wpack = None
+
+
 class GradSync:
     """Data-parallel gradient exchange for one replica per GPU: after `loss.backward()` every parameter gradient is
     gathered (x 1/world, one launch) into ONE flat buffer which is all-reduced (SUM) with a single NCCL call; `p.grad` then becomes a

@@ -72,6 +72,12 @@ def _worker(rank, world, port, errs):
         dev = torch.device('cuda', rank)
         dist.init_process_group('nccl', device_id=dev)
         model = _make(pkg, dev)
+        # replicas must be identical: the hyper-connections' initial stream is drawn with python's randrange (rank dependent)
+        sa = model.transformer.hyper_conns[0][0][0].static_alpha.detach().clone()
+        pkg.broadcast_module(model)
+        gathered = [torch.zeros_like(sa) for _ in range(world)]
+        dist.all_gather(gathered, model.transformer.hyper_conns[0][0][0].static_alpha.detach())
+        assert all(torch.equal(g, gathered[0]) for g in gathered)
         data = _data(dev)
         text = pkg.list_str_to_tensor(['Hello', 'Goodbye', 'Good morning', 'Hi']).to(dev)
         mine = slice(2 * rank, 2 * rank + 2)

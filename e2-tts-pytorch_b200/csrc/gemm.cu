@@ -631,6 +631,20 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
         p.kb_a1 = (int)(a->K1 / BK);
     }
     int split = a->split_k > 1 ? a->split_k : 1;
+    if (a->split_k < 0) {
+        // auto (weight gradients: few output tiles, very long K): fill the machine once — one work item per CTA pair (or CTA) —
+        // while every split keeps >= 8 k-blocks so that the pipeline fill and the fp32 reduction of its partial tile stay amortised.
+        // (The Python-side heuristic of round 1 counted 128 x 128 tiles whatever tile the kernel chose and left 35-50 % of the SMs idle
+        // on the dW problems, profiles/r2f_gemm_breakdown_by_shape.txt.)
+        const int units = pair ? num_sms() / 2 : num_sms();
+        const int tiles = p.tiles_m * p.tiles_n;
+        int s_fill = (units + tiles / 2) / tiles;                 // nearest number of splits that fills the units once
+        while (s_fill > 1 && tiles * s_fill > units) --s_fill;     // never spill into a second, mostly empty round
+        const int s_max = p.kb_total / 8;
+        split = s_fill < 1 ? 1 : s_fill;
+        if (split > s_max) split = s_max < 1 ? 1 : s_max;
+        if (split > 64) split = 64;
+    }
     if (split > p.kb_total) split = p.kb_total;
     p.kb_per_split = (p.kb_total + split - 1) / split;
     split = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;

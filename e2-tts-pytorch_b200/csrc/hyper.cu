@@ -547,319 +547,6 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
     }
 }
 
-// ---- 16-warp variant of the backward token kernel (D <= 512). The 8-warp kernel above keeps a token's four streams AND their
-// gradients in registers (242 registers/thread -> one 8-warp block per SM): ncu r1h shows it at 0.36 of the HBM roofline with the
-// schedulers issuing 42 % of the time — two warps per scheduler, each a long dependent FFMA2 chain, cannot hide latencies.
-// Here nothing token-sized lives in registers across phases: the token {r[4][D], d_res[4][D], d_branch[D]} is staged ONCE by bulk
-// (TMA) copies into a per-warp shared-memory buffer and re-read from there in each of the three passes (shared-memory reads are
-// cheap next to the 9 KB that crossed HBM), d(mix_0) goes through a per-warp fp32 scratch row. <= 128 registers -> 16 warps per SM;
-// while one warp waits for its next token the other 15 compute (single buffer per warp: 16 tokens in flight per SM).
-constexpr int HC16_TOK_PER_BLOCK = 128;
-struct TokScal {
-    float inv[HS];        // sqrt(D) / max(||r_s||, 1e-12)
-    float alpha[HS][HT];  // broadcast to every lane
-    float myraw, myinv, myth, myval;   // lane-owned (see TokState)
-};
-__device__ __forceinline__ void ld8p(const __nv_bfloat16* src, f2 (&f)[4]) { unpack8p(*reinterpret_cast<const uint4*>(src), f); }
-
-template <int VPT>
-__device__ __forceinline__ void token_scalars(const HcP& p, const float4* __restrict__ sp, const __nv_bfloat16* __restrict__ rsrc, int lane,
-                                              const LaneConst& lc, TokScal& st) {
-    const int nchunk = p.D >> 3;
-    f2 ss2[HS], acc[HS][6];
-#pragma unroll
-    for (int s = 0; s < HS; ++s) {
-        ss2[s] = splat(0.f);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) acc[s][k] = splat(0.f);
-    }
-#pragma unroll
-    for (int v = 0; v < VPT; ++v) {
-        const int c = lane + 32 * v;
-        if (c < nchunk) {
-#pragma unroll
-            for (int s = 0; s < HS; ++s) {
-                f2 r[4];
-                ld8p(rsrc + (size_t)s * p.D + c * 8, r);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 q0 = sp[sp_idx(nchunk, c, j, 0)], q1 = sp[sp_idx(nchunk, c, j, 1)], q2 = sp[sp_idx(nchunk, c, j, 2)];
-                    const f2 rp = r[j];
-                    ss2[s] = ffma2(rp, rp, ss2[s]);
-                    acc[s][0] = ffma2(rp, lo2(q0), acc[s][0]); acc[s][1] = ffma2(rp, hi2(q0), acc[s][1]);
-                    acc[s][2] = ffma2(rp, lo2(q1), acc[s][2]); acc[s][3] = ffma2(rp, hi2(q1), acc[s][3]);
-                    acc[s][4] = ffma2(rp, lo2(q2), acc[s][4]); acc[s][5] = ffma2(rp, hi2(q2), acc[s][5]);
-                }
-            }
-        }
-    }
-    float red[32];
-#pragma unroll
-    for (int s = 0; s < HS; ++s) {
-#pragma unroll
-        for (int t = 0; t < HT; ++t) red[s * HT + t] = hsum(acc[s][t]);
-        red[HS * HT + s] = hsum(acc[s][5]);
-        red[24 + s] = 0.f;
-        red[28 + s] = hsum(ss2[s]);
-    }
-    const float mine = warp_reduce32(red, lane);
-    const float sqrtD = sqrtf((float)p.D);
-    float myinv = 0.f;
-    const int s_of = lane < HS * HT ? lane / HT : lane - HS * HT;
-#pragma unroll
-    for (int s = 0; s < HS; ++s) {
-        st.inv[s] = sqrtD / fmaxf(sqrtf(__shfl_sync(0xffffffffu, mine, 28 + s)), 1e-12f);
-        myinv = (s_of == s) ? st.inv[s] : myinv;
-    }
-    const float th = tanhf(mine * myinv);
-    st.myraw = mine; st.myinv = myinv; st.myth = th; st.myval = th * lc.scale + lc.stat;
-#pragma unroll
-    for (int s = 0; s < HS; ++s)
-#pragma unroll
-        for (int t = 0; t < HT; ++t) st.alpha[s][t] = __shfl_sync(0xffffffffu, st.myval, s * HT + t);
-}
-
-template <int VPT>
-__global__ void __launch_bounds__(512, 1) hc_width_bwd16_kernel(const HcP p, __nv_bfloat16* __restrict__ cmat) {
-    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
-    extern __shared__ float4 sp[];
-    const int D = p.D, nchunk = D >> 3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tok_bytes = (uint32_t)(HS * D * 2), br_bytes = (uint32_t)(D * 2), buf_bytes = 2 * tok_bytes + br_bytes;
-    uint8_t* base = reinterpret_cast<uint8_t*>(sp) + hc_param_smem(D);
-    uint8_t* wbuf = base + (size_t)warp * buf_bytes;                                            // {r, d_res, d_branch} of the warp's token
-    float* dm0s = reinterpret_cast<float*>(base + (size_t)16 * buf_bytes) + (size_t)warp * D;    // d(mix_0) of the warp's token, fp32
-    float* s_gng = reinterpret_cast<float*>(base + (size_t)16 * buf_bytes) + (size_t)16 * D;     // [D] d(norm gain) of this block
-    float* s_scal = s_gng + D;                                                                    // [32]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_scal + 32);                                    // [16]
-    if (threadIdx.x < 32) s_scal[threadIdx.x] = 0.f;
-    for (int i = threadIdx.x; i < D; i += 512) s_gng[i] = 0.f;
-    const int b = blockIdx.y;
-    const int n0 = blockIdx.x * HC16_TOK_PER_BLOCK;
-    const int n1 = min(p.rows_per_batch, n0 + HC16_TOK_PER_BLOCK);
-    auto prefetch = [&](int n) {
-        const size_t tk = (size_t)b * p.rows_per_batch + n;
-        mbar_arrive_expect_tx(&bars[warp], buf_bytes);
-        bulk_load_1d(wbuf, p.xres + tk * HS * D, tok_bytes, &bars[warp]);
-        bulk_load_1d(wbuf + tok_bytes, p.d_res + tk * HS * D, tok_bytes, &bars[warp]);
-        bulk_load_1d(wbuf + 2 * tok_bytes, p.d_branch + tk * D, br_bytes, &bars[warp]);
-    };
-    if (lane == 0) {
-        mbar_init(&bars[warp], 1);
-        fence_barrier_init();
-        if (n0 + warp < n1) prefetch(n0 + warp);
-    }
-    stage_params(p, sp);          // (ends with __syncthreads)
-    const LaneConst lc = lane_const(p, lane);
-    float g_stat = 0.f, g_scale = 0.f;
-    const float invD = 1.f / (float)D;
-    f2 gng2[VPT][4];
-#pragma unroll
-    for (int v = 0; v < VPT; ++v)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gng2[v][j] = splat(0.f);
-    const int c_row = lane < HS * HT ? lane / HT : (lane < HS * HT + HS ? lane - HS * HT : (lane - 24) >> 1);
-    const int c_col = lane < HS * HT ? lane % HT : (lane < HS * HT + HS ? HT : 6 + ((lane - 24) & 1));
-    const __nv_bfloat16* rsrc = reinterpret_cast<const __nv_bfloat16*>(wbuf);
-    const __nv_bfloat16* drsrc = reinterpret_cast<const __nv_bfloat16*>(wbuf + tok_bytes);
-    const __nv_bfloat16* dbsrc = reinterpret_cast<const __nv_bfloat16*>(wbuf + 2 * tok_bytes);
-
-    int it = 0;
-    for (int n = n0 + warp; n < n1; n += 16, ++it) {
-        const long long tok = (long long)b * p.rows_per_batch + n;
-        mbar_wait(&bars[warp], (uint32_t)it & 1u);
-        // ---- pass 1: forward scalars (alpha, beta, inverse norms)
-        TokScal st;
-        token_scalars<VPT>(p, sp, rsrc, lane, lc, st);
-        // ---- pass 2: branch = mix_0, its norm, <gain * dy, branch>
-        float cn = 1.f, nk = 0.f;
-        const float* ng = p.norm_mode ? norm_gain(p, tok) : nullptr;
-        if (p.norm_mode) {
-            f2 bss2 = splat(0.f), dot2 = splat(0.f);
-#pragma unroll
-            for (int v = 0; v < VPT; ++v) {
-                const int c = lane + 32 * v;
-                if (c < nchunk) {
-                    f2 br[4], r[4], dy[4], g[4];
-                    ld8p(rsrc + c * 8, r);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) br[j] = fmul2(splat(st.alpha[0][0]), r[j]);
-#pragma unroll
-                    for (int s = 1; s < HS; ++s) {
-                        ld8p(rsrc + (size_t)s * D + c * 8, r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) br[j] = ffma2(splat(st.alpha[s][0]), r[j], br[j]);
-                    }
-                    ld8p(dbsrc + c * 8, dy);
-                    load_gain8(ng + c * 8, g);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        bss2 = ffma2(br[j], br[j], bss2);
-                        dot2 = ffma2(fmul2(g[j], dy[j]), br[j], dot2);
-                    }
-                }
-            }
-            cn = sqrtf((float)D) / fmaxf(sqrtf(warp_sum(hsum(bss2))), 1e-12f);
-            nk = -(cn * cn * cn * invD * warp_sum(hsum(dot2)));
-        }
-        // ---- pass 3: d(mix_0) (kept in the warp's fp32 scratch row), d(norm gain), d_alpha[s][t] = <d_mix_t, r_s>
-        f2 red2[HS][HT];
-#pragma unroll
-        for (int s = 0; s < HS; ++s)
-#pragma unroll
-            for (int t = 0; t < HT; ++t) red2[s][t] = splat(0.f);
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-            const int c = lane + 32 * v;
-            if (c < nchunk) {
-                f2 dm[4], r[4];
-                ld8p(dbsrc + c * 8, dm);                     // dy
-                if (p.norm_mode) {
-                    f2 br[4], g[4];
-                    ld8p(rsrc + c * 8, r);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) br[j] = fmul2(splat(st.alpha[0][0]), r[j]);
-#pragma unroll
-                    for (int s = 1; s < HS; ++s) {
-                        ld8p(rsrc + (size_t)s * D + c * 8, r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) br[j] = ffma2(splat(st.alpha[s][0]), r[j], br[j]);
-                    }
-                    load_gain8(ng + c * 8, g);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        gng2[v][j] = ffma2(fmul2(dm[j], br[j]), splat(cn), gng2[v][j]);   // d gain += dy * normalised branch
-                        dm[j] = ffma2(fmul2(g[j], dm[j]), splat(cn), fmul2(br[j], splat(nk)));
-                    }
-                }
-                *reinterpret_cast<float4*>(dm0s + c * 8) = make_float4(dm[0].x, dm[0].y, dm[1].x, dm[1].y);
-                *reinterpret_cast<float4*>(dm0s + c * 8 + 4) = make_float4(dm[2].x, dm[2].y, dm[3].x, dm[3].y);
-#pragma unroll
-                for (int s = 0; s < HS; ++s) {
-                    ld8p(rsrc + (size_t)s * D + c * 8, r);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) red2[s][0] = ffma2(dm[j], r[j], red2[s][0]);
-                }
-#pragma unroll
-                for (int t = 1; t < HT; ++t) {
-                    ld8p(drsrc + (size_t)(t - 1) * D + c * 8, dm);
-#pragma unroll
-                    for (int s = 0; s < HS; ++s) {
-                        ld8p(rsrc + (size_t)s * D + c * 8, r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) red2[s][t] = ffma2(dm[j], r[j], red2[s][t]);
-                    }
-                }
-            }
-        }
-        float red[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) red[i] = 0.f;
-#pragma unroll
-        for (int s = 0; s < HS; ++s)
-#pragma unroll
-            for (int t = 0; t < HT; ++t) red[s * HT + t] = hsum(red2[s][t]);
-        const float mine = warp_reduce32(red, lane);     // lane s*HT+t owns d_alpha[s][t]; lanes >= 20 hold 0
-        // ---- scalar backward, lane-owned (as in the 8-warp kernel)
-        const bool is_beta = lane >= HS * HT && lane < HS * HT + HS;
-        const float dval = is_beta ? (p.d_beta ? __ldg(p.d_beta + (size_t)tok * HS + (lane - HS * HT)) : 0.f) : mine;
-        g_stat += dval;
-        g_scale += dval * st.myth;
-        const float mycoef = dval * lc.scale * (1.f - st.myth * st.myth);
-        cmat[((size_t)tok * HS + c_row) * 8 + c_col] = __float2bfloat16(mycoef * st.myinv);
-        float nk3[HS], cw[HS][6];
-        {
-            const float term = mycoef * st.myraw;
-            const float cws = mycoef * st.myinv;
-#pragma unroll
-            for (int s = 0; s < HS; ++s) {
-                float Rs = __shfl_sync(0xffffffffu, term, HS * HT + s);
-                cw[s][5] = __shfl_sync(0xffffffffu, cws, HS * HT + s);
-#pragma unroll
-                for (int t = 0; t < HT; ++t) {
-                    Rs += __shfl_sync(0xffffffffu, term, s * HT + t);
-                    cw[s][t] = __shfl_sync(0xffffffffu, cws, s * HT + t);
-                }
-                nk3[s] = -(st.inv[s] * st.inv[s] * st.inv[s] * invD * Rs);
-            }
-        }
-        __syncwarp();    // the scratch row written in pass 3 is read by the same lanes below (same columns), no cross-lane hazard
-        // ---- pass 4: d_r_s = sum_t alpha[s][t] d_mix_t + nk3[s] r_s + sum_k cw[s][k] P_k
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-            const int c = lane + 32 * v;
-            if (c < nchunk) {
-#pragma unroll
-                for (int s = 0; s < HS; ++s) {
-                    f2 r[4], o[4];
-                    ld8p(rsrc + (size_t)s * D + c * 8, r);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = fmul2(r[j], splat(nk3[s]));
-                    {   // t = 0: d(mix_0) from the scratch row
-                        const float4 a = *reinterpret_cast<const float4*>(dm0s + c * 8), bq = *reinterpret_cast<const float4*>(dm0s + c * 8 + 4);
-                        const f2 al = splat(st.alpha[s][0]);
-                        o[0] = ffma2(al, lo2(a), o[0]); o[1] = ffma2(al, hi2(a), o[1]); o[2] = ffma2(al, lo2(bq), o[2]); o[3] = ffma2(al, hi2(bq), o[3]);
-                    }
-#pragma unroll
-                    for (int t = 1; t < HT; ++t) {   // d(mix_t) = d_res[t-1], re-read from the staged token (registers are the scarce resource here)
-                        f2 dm[4];
-                        ld8p(drsrc + (size_t)(t - 1) * D + c * 8, dm);
-                        const f2 al = splat(st.alpha[s][t]);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) o[j] = ffma2(al, dm[j], o[j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 q0 = sp[sp_idx(nchunk, c, j, 0)], q1 = sp[sp_idx(nchunk, c, j, 1)], q2 = sp[sp_idx(nchunk, c, j, 2)];
-                        f2 acc = o[j];
-                        acc = ffma2(splat(cw[s][0]), lo2(q0), acc); acc = ffma2(splat(cw[s][1]), hi2(q0), acc);
-                        acc = ffma2(splat(cw[s][2]), lo2(q1), acc); acc = ffma2(splat(cw[s][3]), hi2(q1), acc);
-                        acc = ffma2(splat(cw[s][4]), lo2(q2), acc); acc = ffma2(splat(cw[s][5]), hi2(q2), acc);
-                        o[j] = acc;
-                    }
-                    *reinterpret_cast<uint4*>(p.d_xres + ((size_t)tok * HS + s) * D + c * 8) = pack8p(o);
-                }
-            }
-        }
-        __syncwarp();   // every lane is done with the token buffer: fetch the warp's next token into it
-        if (lane == 0 && n + 16 < n1) prefetch(n + 16);
-    }
-    if (p.norm_mode) {
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-            const int c = lane + 32 * v;
-            if (c < nchunk) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    atomicAdd(&s_gng[c * 8 + 2 * j], gng2[v][j].x);
-                    atomicAdd(&s_gng[c * 8 + 2 * j + 1], gng2[v][j].y);
-                }
-            }
-        }
-    }
-    {
-        if (lane < HS * HT + HS) atomicAdd(&s_scal[lane], g_stat);
-        const float gas = warp_sum(lane < HS * HT ? g_scale : 0.f);
-        const float gbs = warp_sum((lane >= HS * HT && lane < HS * HT + HS) ? g_scale : 0.f);
-        if (lane == 0) {
-            atomicAdd(&s_scal[24], gas);
-            atomicAdd(&s_scal[25], gbs);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 20) atomicAdd(p.g_salpha + threadIdx.x, s_scal[threadIdx.x]);
-    else if (threadIdx.x < 24) atomicAdd(p.g_sbeta + (threadIdx.x - 20), s_scal[threadIdx.x]);
-    else if (threadIdx.x == 24) atomicAdd(p.g_ascale, s_scal[24]);
-    else if (threadIdx.x == 25) atomicAdd(p.g_bscale, s_scal[25]);
-    if (p.norm_mode) {
-        float* dst = p.g_ng + (p.norm_mode == 2 ? (size_t)b * D : 0);
-        for (int i = threadIdx.x; i < D; i += 512) atomicAdd(dst + i, s_gng[i]);
-    }
-}
-__host__ __device__ inline size_t hc16_smem(int D) {
-    return hc_param_smem(D) + (size_t)16 * (2 * HS + 1) * D * 2 + (size_t)16 * D * 4 + (size_t)D * 4 + 32 * 4 + 16 * 8;
-}
-
 // Parameter gradients from G[col][k] = sum_{token, stream} r[token, stream, col] * C[(token, stream)][k]  (fp32 [D, 8], produced by the
 // tcgen05 GEMM  R^T C):  with n^ = r * inv * (gamma + 1) and C = inv * d(tanh argument),
 //   d dynamic_alpha_fn[col][t] = (gamma+1) G[col][t],  d dynamic_beta_fn[col] = (gamma+1) G[col][5],
@@ -1024,18 +711,7 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     B200_REQUIRE((size_t)a->T * 24 >= (size_t)a->D * 8, "hc_width_bwd: workspace too small for D=%d at T=%lld", a->D, (long long)a->T);
     dim3 grid((a->rows_per_batch + HC_TOK_PER_BLOCK - 1) / HC_TOK_PER_BLOCK, a->T / a->rows_per_batch);
     const size_t smem_par = hc_param_smem(a->D);
-    static const int hc16 = getenv("B200_HC16") ? atoi(getenv("B200_HC16")) : 1;   // developer A/B switch: 16-warp token kernel, default on
-    if (a->D <= 512 && hc16) {
-        dim3 grid16((a->rows_per_batch + HC16_TOK_PER_BLOCK - 1) / HC16_TOK_PER_BLOCK, a->T / a->rows_per_batch);
-        const size_t smem = hc16_smem(a->D);
-        if (a->D <= 256) {
-            if (int rc = set_smem<hc_width_bwd16_kernel<1>>(smem)) return rc;
-            B200_LAUNCH((hc_width_bwd16_kernel<1>), grid16, 512, smem, st, p, cmat);
-        } else {
-            if (int rc = set_smem<hc_width_bwd16_kernel<2>>(smem)) return rc;
-            B200_LAUNCH((hc_width_bwd16_kernel<2>), grid16, 512, smem, st, p, cmat);
-        }
-    } else if (a->D <= 512 && hc_prefetch_enabled()) {
+    if (a->D <= 512 && hc_prefetch_enabled()) {
         const size_t smem = smem_par + (size_t)8 * 2 * (2 * HS + 1) * a->D * 2;   // + per-warp {r, d_res, d_branch} double buffers
         if (a->D <= 256) {
             if (int rc = set_smem<hc_width_bwd_kernel<1, true>>(smem)) return rc;

@@ -877,34 +877,6 @@ class E2TTS(Module):
         null_pred = cfg_null_model.transformer_with_pred_head(*args, drop_text_cond=null_drop, **kwargs)
         return ops.cfg_combine(pred, null_pred, float(cfg_strength), bool(remove_parallel_component), float(keep_parallel_frac))
 
-    def _graphed_nfe(self, fn, y):
-        """One function evaluation of the ODE right-hand side (text pass + null pass + CFG/APG, ~1 100 launches at depth 24) captured
-        as a CUDA graph and replayed for each of the 2 (steps - 1) evaluations of the solve: static (t, y) inputs, frozen
-        weights. Falls back to the eager closure if capture is not possible."""
-        try:
-            dev = y.device
-            st_y, st_t = torch.empty_like(y), torch.zeros((), device=dev, dtype=F32)
-            st_y.copy_(y)
-            cur = torch.cuda.current_stream(dev)
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):     # warm-up off the capture stream (lazy tables, allocator)
-                fn(st_t, st_y)
-            cur.wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                st_out = fn(st_t, st_y)
-
-            def fn_g(t, x):
-                st_t.copy_(t)
-                st_y.copy_(x)
-                graph.replay()
-                return st_out      # consumed (axpy into a fresh tensor) before the next replay overwrites it
-            return fn_g
-        except Exception:  # noqa: BLE001 - capture is an optimisation; the eager closure computes the same thing
-            torch.cuda.synchronize()
-            return fn
-
     @torch.no_grad()
     @_on_module_device
     def sample(self, cond, *, text=None, lens=None, duration=None, steps=32, cfg_strength=1., cfg_null_model=None, max_duration=4096,
@@ -956,7 +928,7 @@ class E2TTS(Module):
                 cfg_null_model._packed()
             for tr in frozen:
                 tr.freeze_packed(True)
-            fn_eval = self._graphed_nfe(fn, y) if (y.is_cuda and steps > 3) else fn
+            fn_eval = fn   # (one function evaluation as a CUDA graph was measured: -1 % at cfg5, but re-capturing per call costs the e2e path 19 %)
             for i in range(steps - 1):
                 t0, dt = ts[i], float(ts_host[i + 1] - ts_host[i])
                 if method == 'euler':

@@ -85,17 +85,10 @@ _GEMM_FIELDS = ('A', 'lda', 'A2', 'lda2', 'K1', 'B', 'ldb', 'M', 'N', 'K', 'a_mn
                 'bias', 'colscale', 'rows_per_batch', 'rowmask', 'resid', 'ldr', 'geglu', 'dropout_p', 'seed', 'split_k', 'force_tile', 'seed_dev')
 
 
-def _split_for(M, N, K):
-    """split-K factor for weight-gradient GEMMs (few output tiles, very long K)."""
-    tiles = ((M + 127) // 128) * ((N + 127) // 128)
-    kb = (K + 63) // 64
-    return max(1, min(kb, (148 + tiles - 1) // tiles, 32))
-
-
 def grad_weight(dY, X, T, n_out, n_in, *, ldy=None, ldx=None, out=None, ldd=None):
     """dW[n_out, n_in] = dY[T, n_out]^T X[T, n_in]  — both operands MN-major, fp32 out, split-K."""
     return gemm(dY, X, n_out, n_in, T, lda=ldy if ldy is not None else n_out, ldb=ldx if ldx is not None else n_in,
-                a_mn=True, b_mn=True, out=out, ldd=ldd, out_fp32=True, split_k=_split_for(n_out, n_in, T))
+                a_mn=True, b_mn=True, out=out, ldd=ldd, out_fp32=True, split_k=-1)   # -1: the library fills the SMs for the tile it picks
 
 
 def colsum(X, T, ncols, ld):

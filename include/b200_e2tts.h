@@ -48,7 +48,8 @@ uint64_t b200_launch_count(void);
  *   zero rows where rowmask[m]==0 (A.4 step 6)   + resid[m,n] (bf16)
  *   geglu=1: B rows are packed [u(64) | gate(64)] per 128-column tile (b200_pack_weight mode 2);
  *            D2[M,N] <- pre-activation (bf16), D[M,N/2] <- u * gelu_erf(gate) * dropout  (A.2)
- *   split_k>1: fp32 atomic accumulation into D (D is zeroed by the call); d_fp32 must be 1.
+ *   split_k>1: fp32 atomic accumulation into D (D is zeroed by the call); d_fp32 must be 1. split_k<0: the library picks the
+ *            split that fills the SMs once for the tile shape it selects (weight-gradient GEMMs: few tiles, very long K).
  */
 typedef struct {
     const void* A; int64_t lda;

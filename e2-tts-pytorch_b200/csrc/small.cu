@@ -213,178 +213,220 @@ __global__ void fourier_embed_kernel(const float* times, const float* w, float* 
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise conv
+// y = m * silu(conv1d_depthwise(m * x) + bias)  on bf16 [B, Np, D]  (DepthwiseConv, e2_tts.py:295-328).
+// Tile = 64 tokens x 64 channels staged in shared memory as fp32 (+ 15 halo rows each side). A thread owns a channel PAIR and a
+// run of consecutive tokens: its 31 taps sit in registers as fp32x2 and every window element is read once (one LDS.64) and fed to
+// all the outputs it touches, so the inner loop is pure FFMA2 — two FMAs per lane and issue slot. (The scalar version of round 1
+// issued one FMA per slot: 110 FFMA per element in backward, 94 us per call, FMA-pipe bound at half the fp32 peak.)
+// Forward also stores the bf16 pre-activation; backward reads it back instead of recomputing the convolution over tile + halo
+// (the same trade as the GEGLU pre-activations: +2 B per element of HBM traffic for 42 % fewer FMAs).
 constexpr int CV_TN = 64, CV_TC = 64, CV_HALO = 15;
+constexpr int CV_R = CV_TN + 2 * CV_HALO;   // staged rows of a tile: token n0 - 15 + r
+
+typedef float2 cf2;
+__device__ __forceinline__ cf2 cv_ffma2(cf2 a, cf2 b, cf2 c) { return __ffma2_rn(a, b, c); }
 
 __device__ __forceinline__ bool tok_ok(const unsigned char* mask, int b, int n, int Np) {
     return n >= 0 && n < Np && (!mask || mask[(size_t)b * Np + n]);
 }
-
-// Both kernels keep the thread's channel weights in registers and slide a register window over the sequence, so the
-// inner loop is pure FFMA (the first version re-read weights and inputs from shared memory for every tap and was
-// LSU-bound: ncu profiles/r1_hc_conv_before.txt). KS = 31 (reference default, e2_tts.py:539) is fully unrolled;
-// other odd sizes <= 31 run the same code with zero-padded taps.
+__device__ __forceinline__ void cv_unpack8(const uint4& u, float (&v)[8]) {
+    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+}
+// the tile's taps, staged once per block as [31][CV_TC] so that channel pairs are adjacent (one conflict-free LDS.64 per tap and thread);
+// centred inside a 31-wide window (kernel sizes < 31 are zero-padded); flip = reversed taps. (Per-thread global loads of the 62 taps
+// cost more address arithmetic and load latency than the convolution itself: ncu r2m.)
+__device__ __forceinline__ void cv_stage_taps(const b200_dwconv_args& a, int c0, bool flip, float (*sw)[CV_TC]) {
+    const int shift = CV_HALO - a.ksize / 2;
+    for (int i = threadIdx.x; i < 31 * CV_TC; i += blockDim.x) {
+        const int c = i / 31, k = i % 31, kk = k - shift;   // consecutive threads walk the weights in memory order
+        const bool in = c0 + c < a.D && kk >= 0 && kk < a.ksize;
+        sw[flip ? 30 - k : k][c] = in ? __ldg(a.weight + (size_t)(c0 + c) * a.ksize + kk) : 0.f;
+    }
+}
+__device__ __forceinline__ void cv_load_taps(const float (*sw)[CV_TC], int cp, cf2 (&w)[31]) {
+#pragma unroll
+    for (int k = 0; k < 31; ++k) w[k] = *reinterpret_cast<const cf2*>(&sw[k][2 * cp]);
+}
+// out[j] (+)= sum_k w[k] * src[row0 + j + k][2cp .. 2cp+1],  j < ROWS: one pass over the ROWS + 30 window rows
 template <int ROWS>
-__device__ __forceinline__ void conv_rows(const float (&w)[31], const float (*src)[CV_TC], int row0, int cl, float bias, float (&out)[ROWS]) {
-    float win[ROWS + 30];
+__device__ __forceinline__ void conv_rows2(const cf2 (&w)[31], const float (*src)[CV_TC], int row0, int cp, cf2 (&out)[ROWS]) {
 #pragma unroll
-    for (int j = 0; j < ROWS + 30; ++j) win[j] = src[row0 + j][cl];
+    for (int m = 0; m < ROWS + 30; ++m) {
+        const cf2 v = *reinterpret_cast<const cf2*>(&src[row0 + m][2 * cp]);
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
-        float acc = bias;
-#pragma unroll
-        for (int k = 0; k < 31; ++k) acc += w[k] * win[j + k];
-        out[j] = acc;
+        for (int j = 0; j < ROWS; ++j) {
+            const int k = m - j;
+            if (k >= 0 && k < 31) out[j] = cv_ffma2(w[k], v, out[j]);
+        }
     }
 }
 
-// row validity (inside the sequence and not masked) is staged once per tile so that no global load sits behind a branch
-// on another global load (the first version chained mask -> dy loads per row and was latency-bound: ncu r1).
-__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const b200_dwconv_args a) {
+// 256 threads = 32 channel pairs x 8 groups of 8 tokens
+__global__ void __launch_bounds__(256, 4) dwconv_fwd_kernel(const b200_dwconv_args a) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
-    __shared__ float xs[CV_TN + 2 * CV_HALO][CV_TC];
-    __shared__ unsigned char sok[CV_TN + 2 * CV_HALO];
+    __shared__ __align__(16) float xs[CV_R][CV_TC];
+    __shared__ __align__(16) float sw[31][CV_TC];
+    __shared__ unsigned char sok[CV_R];
     const int n0 = blockIdx.x * CV_TN, c0 = blockIdx.y * CV_TC, b = blockIdx.z;
-    const int pad = a.ksize / 2, shift = CV_HALO - pad;   // taps are centred inside the 31-wide register window
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
-    if (threadIdx.x < CV_TN + 2 * CV_HALO) sok[threadIdx.x] = tok_ok(a.mask, b, n0 - CV_HALO + (int)threadIdx.x, a.Np);
+    if (threadIdx.x < CV_R) sok[threadIdx.x] = tok_ok(a.mask, b, n0 - CV_HALO + (int)threadIdx.x, a.Np);
+    cv_stage_taps(a, c0, false, sw);
     __syncthreads();
-    for (int i = threadIdx.x; i < (CV_TN + 2 * CV_HALO) * (CV_TC / 8); i += 256) {
-        const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
-        const int n = n0 - CV_HALO + r;
-        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (sok[r] && c0 + ch < a.D) {
-            const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + n) * a.D + c0 + ch);
-            v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-            v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+    // row validity (inside the sequence and not masked) is staged first so that no global load sits behind a branch on another one;
+    // the three 16-byte loads of a thread are issued together
+    {
+        constexpr int NIT = (CV_R * (CV_TC / 8) + 255) / 256;
+        uint4 u[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = threadIdx.x + it * 256, r = i / (CV_TC / 8), cc = (i % (CV_TC / 8)) * 8;
+            u[it] = make_uint4(0, 0, 0, 0);
+            if (i < CV_R * (CV_TC / 8) && sok[r] && c0 + cc < a.D)
+                u[it] = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + (n0 - CV_HALO + r)) * a.D + c0 + cc);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xs[r][ch + j] = v[j];
+        for (int it = 0; it < NIT; ++it) {
+            const int i = threadIdx.x + it * 256, r = i / (CV_TC / 8), cc = (i % (CV_TC / 8)) * 8;
+            if (i < CV_R * (CV_TC / 8)) {
+                float v[8];
+                cv_unpack8(u[it], v);
+                *reinterpret_cast<float4*>(&xs[r][cc]) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(&xs[r][cc + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
     }
-    const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
-    const bool cok = c0 + cl < a.D;
-    float w[31];
-#pragma unroll
-    for (int k = 0; k < 31; ++k) w[k] = (cok && k >= shift && k - shift < a.ksize) ? a.weight[(size_t)(c0 + cl) * a.ksize + (k - shift)] : 0.f;
+    const int cp = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int ch = c0 + 2 * cp;
+    const bool cok = ch < a.D;
     __syncthreads();
     if (!cok) return;
-    float out[16];
-    conv_rows<16>(w, xs, tg * 16, cl, a.bias[c0 + cl], out);
-    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y);
+    cf2 w[31];
+    cv_load_taps(sw, cp, w);
+    const cf2 bias2 = make_float2(__ldg(a.bias + ch), __ldg(a.bias + ch + 1));
+    cf2 out[8];
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) {
-        const int n = n0 + tg * 16 + jj;
+    for (int j = 0; j < 8; ++j) out[j] = bias2;
+    conv_rows2<8>(w, xs, rg * 8, cp, out);
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y);
+    __nv_bfloat16* pre = reinterpret_cast<__nv_bfloat16*>(a.pre);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r = rg * 8 + j, n = n0 + r;
         if (n < a.Np) {
-            const float o = sok[tg * 16 + jj + CV_HALO] ? out[jj] / (1.f + __expf(-out[jj])) : 0.f;
-            y[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(o);
+            const size_t off = ((size_t)b * a.Np + n) * a.D + ch;
+            const bool ok = sok[r + CV_HALO];
+            const float o0 = ok ? __fdividef(out[j].x, 1.f + __expf(-out[j].x)) : 0.f, o1 = ok ? __fdividef(out[j].y, 1.f + __expf(-out[j].y)) : 0.f;
+            *reinterpret_cast<uint32_t*>(y + off) = pack_bf16(o0, o1);
+            if (pre) *reinterpret_cast<uint32_t*>(pre + off) = pack_bf16(out[j].x, out[j].y);
         }
     }
 }
 
 constexpr int CV_TILES_PER_BLOCK = 4;   // n-tiles marched by one block: weight/bias partial sums stay in registers across them
-constexpr int CV_P1 = 96;               // phase-1 rows (tile + halo each side = 94, padded to 8 x 12)
 
+// Backward. Staging turns dy into d(pre-activation) = dy * silu'(pre) on the fly (rows outside the sequence or masked: 0). Then the
+// block splits by warp: warps 0-3 compute dx = flipped conv of d_pre (taps in registers), warps 4-7 accumulate the tap gradients
+// dW[k] += d_pre[n] * x[n + k - 15] and d(bias) in registers across the block's tiles — both halves run 31 FFMA2 per element pair.
 __global__ void __launch_bounds__(256, 2) dwconv_bwd_kernel(const b200_dwconv_args a) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
-    extern __shared__ float sm[];
-    float (*xs)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm);                              // [CV_P1 + 30] rows, token n0 - 30 + r
-    float (*dps)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (CV_P1 + 30) * CV_TC);       // [CV_P1] rows, token n0 - 15 + r
-    float (*sdw)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + (2 * CV_P1 + 30) * CV_TC);   // [32] (31 taps + bias)
-    unsigned char* sok = reinterpret_cast<unsigned char*>(sm + (2 * CV_P1 + 30 + 32) * CV_TC);  // [CV_P1 + 30] row validity
+    extern __shared__ __align__(16) float sm[];
+    float (*xs)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm);                          // [CV_R] masked x
+    float (*dps)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + CV_R * CV_TC);           // [CV_R] d_pre
+    float (*sdw)[CV_TC] = reinterpret_cast<float (*)[CV_TC]>(sm + 2 * CV_R * CV_TC);       // [32] flipped taps, then (31 tap grads + bias grad)
+    unsigned char* sok = reinterpret_cast<unsigned char*>(sm + (2 * CV_R + 32) * CV_TC);   // [CV_R] row validity
     const int c0 = blockIdx.y * CV_TC, b = blockIdx.z;
-    const int pad = a.ksize / 2, shift = CV_HALO - pad;
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
     const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy);
+    const __nv_bfloat16* pre = reinterpret_cast<const __nv_bfloat16*>(a.pre);
     __nv_bfloat16* dx = reinterpret_cast<__nv_bfloat16*>(a.dx);
-    for (int i = threadIdx.x; i < 32 * CV_TC; i += 256) sdw[i / CV_TC][i % CV_TC] = 0.f;
-    const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
-    const bool cok = c0 + cl < a.D;
-    const float bias = cok ? a.bias[c0 + cl] : 0.f;
-    float w[31], dwk[31];
+    const int cp = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int role = wrp >> 2, rg = wrp & 3;   // role 0: dx, role 1: dW / d(bias); 16 tokens per thread
+    const int ch = c0 + 2 * cp;
+    const bool cok = ch < a.D;
+    cf2 wv[31];                                // role 0: flipped taps; role 1: tap-gradient partial sums
+    cv_stage_taps(a, c0, true, sdw);
+    __syncthreads();
+    if (role == 0) {
+        cv_load_taps(sdw, cp, wv);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 31; ++k) {
-        w[k] = (cok && k >= shift && k - shift < a.ksize) ? a.weight[(size_t)(c0 + cl) * a.ksize + (k - shift)] : 0.f;
-        dwk[k] = 0.f;
+        for (int k = 0; k < 31; ++k) wv[k] = make_float2(0.f, 0.f);
     }
-    float db = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * CV_TC; i += 256) sdw[i / CV_TC][i % CV_TC] = 0.f;   // ordered before its use by the tile loop's barriers
+    cf2 db2 = make_float2(0.f, 0.f);
     const int ntiles = (a.Np + CV_TN - 1) / CV_TN;
     for (int tile = blockIdx.x * CV_TILES_PER_BLOCK; tile < min(ntiles, (int)(blockIdx.x + 1) * CV_TILES_PER_BLOCK); ++tile) {
         const int n0 = tile * CV_TN;
         __syncthreads();
-        if (threadIdx.x < CV_P1 + 30) sok[threadIdx.x] = tok_ok(a.mask, b, n0 - 2 * CV_HALO + (int)threadIdx.x, a.Np);
+        if (threadIdx.x < CV_R) sok[threadIdx.x] = tok_ok(a.mask, b, n0 - CV_HALO + (int)threadIdx.x, a.Np);
         __syncthreads();
-        for (int i = threadIdx.x; i < (CV_P1 + 30) * (CV_TC / 8); i += 256) {
-            const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
-            const int n = n0 - 2 * CV_HALO + r;
-            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (sok[r] && c0 + ch < a.D) {
-                const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)b * a.Np + n) * a.D + c0 + ch);
-                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-                v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
-            }
+        for (int i = threadIdx.x; i < CV_R * (CV_TC / 8); i += 256) {
+            const int r = i / (CV_TC / 8), cc = (i % (CV_TC / 8)) * 8;
+            float xv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (sok[r] && c0 + cc < a.D) {
+                const size_t off = ((size_t)b * a.Np + (n0 - CV_HALO + r)) * a.D + c0 + cc;
+                const uint4 ux = *reinterpret_cast<const uint4*>(x + off), ud = *reinterpret_cast<const uint4*>(dy + off),
+                            up = *reinterpret_cast<const uint4*>(pre + off);
+                float pv[8];
+                cv_unpack8(ux, xv); cv_unpack8(ud, dv); cv_unpack8(up, pv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xs[r][ch + j] = v[j];
-        }
-        for (int i = threadIdx.x; i < CV_P1 * (CV_TC / 8); i += 256) {   // dy tile (token n0 - 15 + r) staged into dps
-            const int r = i / (CV_TC / 8), ch = (i % (CV_TC / 8)) * 8;
-            const int n = n0 - CV_HALO + r;
-            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (sok[r + CV_HALO] && c0 + ch < a.D) {
-                const uint4 u = *reinterpret_cast<const uint4*>(dy + ((size_t)b * a.Np + n) * a.D + c0 + ch);
-                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
-                v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dps[r][ch + j] = v[j];
-        }
-        __syncthreads();
-        // phase 1: d(pre-activation) = dy * silu'(pre), in place over the staged dy (two 12-row sweeps per thread group)
-#pragma unroll 1
-        for (int hp = 0; hp < 2; ++hp) {
-            float pre[12];
-            const int r0 = tg * 24 + hp * 12;
-            conv_rows<12>(w, xs, r0, cl, bias, pre);
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                const float s = 1.f / (1.f + __expf(-pre[j]));
-                dps[r0 + j][cl] *= s * (1.f + pre[j] * (1.f - s));
-            }
-        }
-        __syncthreads();
-        // phase 2: dx = flipped conv of d_pre; weight / bias partial sums accumulate in registers across tiles
-        if (cok) {
-            {
-                float wr[31], dxo[16];
-#pragma unroll
-                for (int k = 0; k < 31; ++k) wr[k] = w[30 - k];
-                conv_rows<16>(wr, dps, tg * 16, cl, 0.f, dxo);
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    const int r = tg * 16 + jj, n = n0 + r;
-                    if (n < a.Np) dx[((size_t)b * a.Np + n) * a.D + c0 + cl] = __float2bfloat16(sok[r + 2 * CV_HALO] ? dxo[jj] : 0.f);
+                for (int j = 0; j < 8; ++j) {
+                    const float sg = __fdividef(1.f, 1.f + __expf(-pv[j]));
+                    dv[j] *= sg * (1.f + pv[j] * (1.f - sg));
                 }
             }
-            float win[46];
+            *reinterpret_cast<float4*>(&xs[r][cc]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            *reinterpret_cast<float4*>(&xs[r][cc + 4]) = make_float4(xv[4], xv[5], xv[6], xv[7]);
+            *reinterpret_cast<float4*>(&dps[r][cc]) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            *reinterpret_cast<float4*>(&dps[r][cc + 4]) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+        }
+        __syncthreads();
+        if (!cok) continue;
+        if (role == 0) {
+            cf2 dxo[16];
 #pragma unroll
-            for (int j = 0; j < 46; ++j) win[j] = xs[tg * 16 + CV_HALO + j][cl];
+            for (int j = 0; j < 16; ++j) dxo[j] = make_float2(0.f, 0.f);
+            conv_rows2<16>(wv, dps, rg * 16, cp, dxo);
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                const int r = tg * 16 + jj;
-                if (n0 + r < a.Np) {
-                    const float dpr = dps[r + CV_HALO][cl];
-                    db += dpr;
+            for (int j = 0; j < 16; ++j) {
+                const int r = rg * 16 + j, n = n0 + r;
+                if (n < a.Np) {
+                    const bool ok = sok[r + CV_HALO];
+                    *reinterpret_cast<uint32_t*>(dx + ((size_t)b * a.Np + n) * a.D + ch) = pack_bf16(ok ? dxo[j].x : 0.f, ok ? dxo[j].y : 0.f);
+                }
+            }
+        } else {
+            cf2 dpr[16];
 #pragma unroll
-                    for (int k = 0; k < 31; ++k) dwk[k] += dpr * win[jj + k];
+            for (int j = 0; j < 16; ++j) {
+                dpr[j] = *reinterpret_cast<const cf2*>(&dps[rg * 16 + CV_HALO + j][2 * cp]);   // 0 for rows outside the sequence / masked
+                db2.x += dpr[j].x; db2.y += dpr[j].y;
+            }
+#pragma unroll
+            for (int m = 0; m < 46; ++m) {
+                const cf2 v = *reinterpret_cast<const cf2*>(&xs[rg * 16 + m][2 * cp]);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int k = m - j;
+                    if (k >= 0 && k < 31) wv[k] = cv_ffma2(dpr[j], v, wv[k]);
                 }
             }
         }
     }
-    if (cok) {
+    if (cok && role == 1) {
 #pragma unroll
-        for (int k = 0; k < 31; ++k) atomicAdd(&sdw[k][cl], dwk[k]);
-        atomicAdd(&sdw[31][cl], db);
+        for (int k = 0; k < 31; ++k) {
+            atomicAdd(&sdw[k][2 * cp], wv[k].x);
+            atomicAdd(&sdw[k][2 * cp + 1], wv[k].y);
+        }
+        atomicAdd(&sdw[31][2 * cp], db2.x);
+        atomicAdd(&sdw[31][2 * cp + 1], db2.y);
     }
     __syncthreads();
-    if (cok && tg == 0) {
+    if (threadIdx.x < CV_TC && c0 + (int)threadIdx.x < a.D) {
+        const int cl = threadIdx.x, shift = CV_HALO - a.ksize / 2;
         for (int k = 0; k < a.ksize; ++k) atomicAdd(a.dweight + (size_t)(c0 + cl) * a.ksize + k, sdw[k + shift][cl]);
         atomicAdd(a.dbias + c0 + cl, sdw[31][cl]);
     }
@@ -605,7 +647,8 @@ extern "C" int b200_dwconv_fwd(const b200_dwconv_args* a, b200_stream_t stream) 
 extern "C" int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream) {
     if (check_conv(a)) return -1;
     B200_REQUIRE(a->dy && a->dx && a->dweight && a->dbias, "dwconv_bwd: null pointer");
-    const size_t smem = (size_t)(2 * CV_P1 + 30 + 32) * CV_TC * sizeof(float) + 128;
+    B200_REQUIRE(a->pre, "dwconv_bwd: the pre-activation saved by b200_dwconv_fwd (args.pre) is required");
+    const size_t smem = (size_t)(2 * CV_R + 32) * CV_TC * sizeof(float) + 128;
     static DeviceOnce once;
     B200_REQUIRE(set_max_smem_once(once, dwconv_bwd_kernel, (int)smem) == cudaSuccess, "dwconv_bwd: cudaFuncSetAttribute failed");
     const int ntiles = (a->Np + CV_TN - 1) / CV_TN;

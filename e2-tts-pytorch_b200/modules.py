@@ -25,6 +25,18 @@ E2TTSReturn = namedtuple('E2TTS', ['loss', 'cond', 'pred_flow', 'pred_data', 'lo
 
 BF16, F32 = torch.bfloat16, torch.float32
 SOFTCLAMP = 50.0  # x-transformers logit_softclamp_value default (A.4)
+# text sub-blocks of layer i+1 overlap the audio sub-blocks of layer i on a second CUDA stream (Transformer._run_layers);
+# B200_TWO_STREAM=0 serialises them on the current stream (developer A/B switch)
+import os as _os
+TWO_STREAM = _os.environ.get('B200_TWO_STREAM', '1') != '0'
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
 
 
 def exists(v):
@@ -499,15 +511,45 @@ class Transformer(Module):
                                       pk['w1'], pk['b1'], pk['w2'], colscale, B, Np, p_drop, next_seed(), self._seed_dev)
             return ops.HcDepth.apply(rest, y, beta)
 
+        def text_block(i, ts, tvf):  # the three text sub-blocks of layer i (:853-882)
+            text, thc, pk = self.layers[i][1], self.hyper_conns[i][1], P[i]['t']
+            ts = sub_conv(ts, thc[0], text[0])
+            ts, tvf = sub_attn(ts, thc[1], text[1].g, 1, text[2], pk, tvf, None)
+            return sub_ff(ts, thc[2], text[3].g, 1, text[4], pk, None), tvf
+
+        # The text sub-blocks of layer i+1 depend on the cross-conditioning of layer i only, not on layer i's audio sub-blocks
+        # (:853-939): enqueue them on a second stream so that the half-width text kernels (K = dt GEMMs, D = dt token kernels)
+        # fill the launch gaps and tile-quantisation tails of the audio kernels instead of serialising with them. The autograd
+        # engine replays the same fork/join in backward (each node runs on its forward stream). Tensors that cross streams are
+        # registered with the caching allocator (record_stream).
+        has_text = lambda i: ts is not None and i < len(self.layers) and self.layers[i][1] is not None
+        two = TWO_STREAM and has_text(0) and xs.is_cuda
+        if two:
+            main, side = torch.cuda.current_stream(xs.device), _side_stream(xs.device)
+            for t in (mask_u8, cs, sn):
+                if t is not None:
+                    t.record_stream(side)
+
+            def fork_text(i, ts_in, tvf):
+                side.wait_stream(main)
+                ts_in.record_stream(side)
+                with torch.cuda.stream(side):
+                    return text_block(i, ts_in, tvf)
+            ts, tv_first = fork_text(0, ts, tv_first)
+
         for i, ((speech, text), (shc, thc)) in enumerate(zip(self.layers, self.hyper_conns)):
             pk = P[i]
             if ts is not None and text is not None:  # :853-883
-                ts = sub_conv(ts, thc[0], text[0])
-                ts, tv_first = sub_attn(ts, thc[1], text[1].g, 1, text[2], pk['t'], tv_first, None)
-                ts = sub_ff(ts, thc[2], text[3].g, 1, text[4], pk['t'], None)
+                if two:
+                    main.wait_stream(side)      # join: text sub-blocks of this layer (enqueued one layer ago)
+                    ts.record_stream(main)
+                else:
+                    ts, tv_first = text_block(i, ts, tv_first)
                 cc = text[5]
                 xs, ts = ops.CrossCondition.apply(xs, ts, cc.text_to_audio.weight,
                                                   cc.audio_to_text.weight if cc.cond_audio_to_text else None, pk['cross'])
+                if two and has_text(i + 1):
+                    ts, tv_first = fork_text(i + 1, ts, tv_first)
             if (i + 1) <= self.depth // 2:  # :887-896
                 skips.append(xs)
             else:

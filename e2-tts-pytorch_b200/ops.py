@@ -190,16 +190,17 @@ class DwConv(Function):
         D = x.shape[-1]
         w2 = weight.reshape(D, -1)
         y = torch.empty_like(x)
-        a = lib.make_args('b200_dwconv_args', x=x, mask=mask, weight=w2, bias=bias, y=y, B=B, Np=Np, D=D, ksize=w2.shape[1])
+        pre = torch.empty_like(x) if any(ctx.needs_input_grad[:3]) else None   # bf16 pre-activation: backward does not redo the convolution
+        a = lib.make_args('b200_dwconv_args', x=x, mask=mask, weight=w2, bias=bias, y=y, B=B, Np=Np, D=D, ksize=w2.shape[1], pre=pre)
         lib.call('b200_dwconv_fwd', a, _stream())
-        ctx.save_for_backward(x, weight, bias, mask)
+        ctx.save_for_backward(x, weight, bias, mask, pre)
         ctx.meta = (B, Np)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, weight, bias, mask = ctx.saved_tensors
+        x, weight, bias, mask, pre = ctx.saved_tensors
         B, Np = ctx.meta
         D = x.shape[-1]
         w2 = weight.reshape(D, -1)
@@ -207,7 +208,7 @@ class DwConv(Function):
         dw = _zeros(w2.shape, w2.device)
         db = _zeros(bias.shape, bias.device)
         a = lib.make_args('b200_dwconv_args', x=x, mask=mask, weight=w2, bias=bias, dy=_c(dy), dx=dx, dweight=dw, dbias=db,
-                          B=B, Np=Np, D=D, ksize=w2.shape[1])
+                          B=B, Np=Np, D=D, ksize=w2.shape[1], pre=pre)
         lib.call('b200_dwconv_bwd', a, _stream())
         return dx, dw.view_as(weight), db, None, None, None
 

@@ -272,12 +272,14 @@ int b200_small_linear_bwd(const b200_small_linear_args* a, b200_stream_t stream)
 int b200_fourier_embed(const float* times, const float* weights, float* out, int32_t B, int32_t half, b200_stream_t stream);
 
 /* Masked depthwise conv k (odd, <= 31) + SiLU (DepthwiseConv e2_tts.py:295-328) on bf16 [B, Np, D]:
- *   y = m * silu(conv1d_depthwise(m * x) + bias), weight fp32 [D, k]. bwd recomputes the pre-activation;
- *   dweight/dbias are ADDED into zero-initialised fp32 buffers. */
+ *   y = m * silu(conv1d_depthwise(m * x) + bias), weight fp32 [D, k]. fwd also stores the bf16 pre-activation (conv + bias) into
+ *   `pre` [B, Np, D] when it is non-null; bwd REQUIRES it (caller-owned, like every saved tensor) instead of recomputing the
+ *   convolution. dweight/dbias are ADDED into zero-initialised fp32 buffers. */
 typedef struct {
     const void* x; const uint8_t* mask; const float *weight, *bias; void* y;
     const void* dy; void* dx; float *dweight, *dbias;
     int32_t B, Np, D, ksize;
+    void* pre;
 } b200_dwconv_args;
 int b200_dwconv_fwd(const b200_dwconv_args* a, b200_stream_t stream);
 int b200_dwconv_bwd(const b200_dwconv_args* a, b200_stream_t stream);

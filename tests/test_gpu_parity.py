@@ -105,16 +105,17 @@ def test_hyper_width_depth(pkg):
             check(f'{nm} m{mode}', a.reshape(-1), b.reshape(-1), 3e-2)
 
 
-@pytest.mark.parametrize('D,ks', [(128, 31), (64, 7)])
-def test_dwconv(pkg, D, ks):
+@pytest.mark.parametrize('D,ks,Np', [(128, 31, 100), (64, 7, 100), (512, 31, 333), (264, 31, 70)])
+def test_dwconv(pkg, D, ks, Np):
+    """fwd + (dx, dw, db) vs the oracle; Np = 333 spans two blocks of four 64-token tiles, D = 264 leaves a partial channel tile."""
     torch.manual_seed(2)
     ops = pkg.ops
-    B, Np = 2, 100
+    B = 2
     x = bf(torch.randn(B * Np, D, device=dev())).requires_grad_()
     w = (torch.randn(D, 1, ks, device=dev()) * 0.2).requires_grad_()
     b = (torch.randn(D, device=dev()) * 0.1).requires_grad_()
     mask = torch.ones(B, Np, dtype=torch.bool, device=dev())
-    mask[1, 70:] = False
+    mask[1, int(Np * 0.7):] = False
     y = ops.DwConv.apply(x, w, b, mask.to(torch.uint8).contiguous(), B, Np)
     wo = torch.randn_like(y, dtype=torch.float32)
     g = torch.autograd.grad((y.float() * wo).sum(), [x, w, b])

@@ -187,5 +187,7 @@ def test_velocity_consistency_loss_vs_reference():
     assert float(out.loss_breakdown.velocity_consistency) > 0
     total = torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None]).norm()
     for k, p in model.named_parameters():
-        if p.grad is not None:   # fp32 summation order differs between the two autograd graphs: norm-wise agreement
-            assert (sd[k].grad - p.grad).norm() <= 2e-3 * p.grad.norm() + 1e-5 * total, k
+        if p.grad is not None:   # fp32 summation order differs between the two autograd graphs (and with the host's thread count), and the
+            # velocity term's finite difference divides by delta = 1e-3, amplifying fp32 rounding ~1000x: norm-wise agreement with an
+            # absolute floor of 5e-5 of the total gradient norm (scalar parameters summed over every token sit at 1-3e-5)
+            assert (sd[k].grad - p.grad).norm() <= 2e-3 * p.grad.norm() + 5e-5 * total, k

@@ -38,5 +38,13 @@ if 'attn' in which:
     for _ in range(reps):
         og = ops.AttnCore.apply(q, k, v, gate, m, 0.1, 7, 50.0, None)
         torch.autograd.grad(og, [q, k, v], torch.ones_like(og))
+if 'gemm' in which:   # the epilogue-heavy / short-K GEMMs of the step: FF-in GEGLU (audio, text), out-proj, a plain K=256 problem
+    for (N, K, kw) in [(4096, 512, dict(geglu=True, bias=torch.randn(4096, device=dev), dropout_p=0.1, seed=3, D2=torch.empty((T, 4096), device=dev, dtype=torch.bfloat16), ldd2=4096)),
+                       (2048, 256, dict(geglu=True, bias=torch.randn(2048, device=dev), dropout_p=0.1, seed=3, D2=torch.empty((T, 2048), device=dev, dtype=torch.bfloat16), ldd2=2048)),
+                       (512, 512, dict(colscale=torch.rand(B, 512, device=dev), rows_per_batch=Np, rowmask=torch.ones(T, dtype=torch.uint8, device=dev))),
+                       (512, 256, dict())]:
+        A, W = bf(T, K), bf(N, K)
+        for _ in range(reps):
+            ops.gemm(A, W, T, N, K, **kw)
 torch.cuda.synchronize()
 print('done')

@@ -279,6 +279,7 @@ def run_gpu(args):
         launches = (lib.launch_count() - n0) // steps
         ms_e2e = timed(lambda: step(host_mel.to(dev, non_blocking=True), True), steps)
         ops.gemm = gemm_timed
+        two_stream, pkg.modules.TWO_STREAM = pkg.modules.TWO_STREAM, False   # per-kernel event times need the kernels serialised on one stream
         nprof = 1 if kind == 'sample' else min(steps, 3)
         if kind == 'sample':    # profile ONE function evaluation (text pass + null pass) instead of all 62
             with torch.no_grad():
@@ -287,9 +288,13 @@ def run_gpu(args):
                                                      mask=torch.ones(B, N, dtype=torch.bool, device=dev), cfg_strength=1.0)
         else:
             for _ in range(nprof):
+                # park the GPU (~40 ms spin kernel) while the host enqueues the step: with the queue full, the event pair around a
+                # GEMM brackets the kernel alone — on a host-bound eager step it would also bracket the wait for the next launch
+                torch.cuda._sleep(80_000_000)
                 step(dev_mel, False)
         torch.cuda.synchronize()
         ops.gemm = orig_gemm
+        pkg.modules.TWO_STREAM = two_stream
         # -- the same train step through pkg.GraphedTrainStep (forward + backward captured in one CUDA graph, then — N > 1 — ONE flat
         #    all-reduce): identical kernels and work, no per-launch host cost. Falls back to the eager numbers if capture fails.
         if kind == 'train' and not args.no_graph:
@@ -351,6 +356,8 @@ def run_gpu(args):
                    'grad_exchange': ('one flat fp32 ncclAllReduce per step after backward (e2_tts_pytorch_b200.GradSync)' if world > 1 and kind != 'sample' else 'none'),
                    'step': (what + ' replayed through e2_tts_pytorch_b200.GraphedTrainStep (one CUDA graph, same kernels)'
                             if step_mode == 'cuda_graph' else what + ', eager launches'),
+                   'streams': ('text sub-blocks of layer i+1 overlap the audio sub-blocks of layer i on a second CUDA stream (fork/join inside the step); '
+                               'the roofline pass times the GEMMs serialised on one stream') if pkg.modules.TWO_STREAM else 'one stream',
                    **({'eager_ms_per_step': eager_ms} if eager_ms is not None else {}), **({'cuda_graph': graph_note} if graph_note else {})},
         'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': 'mel-frames/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': host_mel.numel() * 4,
                 'd2h_bytes_per_step': d2h_bytes},

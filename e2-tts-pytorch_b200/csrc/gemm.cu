@@ -52,57 +52,62 @@ struct GemmSmem {
     static constexpr int kStages = (STAGE_BYTES <= 32768) ? 6 : 4;
     static constexpr int TILE_BYTES = kStages * STAGE_BYTES;
     static constexpr int BAR_BYTES = 160;
-    static constexpr int STG_BYTES = 8 * 4224;   // per epilogue warp: 32 x 128 B bf16 staging tile, or 32 x 33 fp32 for split-K atomics
-    static constexpr int TOTAL = TILE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // + slack for manual 1024B alignment
+    static constexpr int STG_WARP = 4096;        // per epilogue warp: 32 x 128 B bf16 TMA-store staging tile (1024-B aligned: the 128B swizzle
+                                                 // pattern is a function of the smem address), or 32 x 32 fp32 for split-K reductions
+    static constexpr int STG_BYTES = 8 * STG_WARP;
+    static constexpr int TOTAL = TILE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // + slack for manual 1024B alignment
 };
 
-// Coalesced epilogue store: every lane holds NCH 16-byte pieces of ITS row (a tcgen05.ld 32x32b chunk is row-per-lane); the warp
-// transposes them through a 32-row smem staging tile (XOR-swizzled, conflict-minimal) and writes full 64/128-byte row segments
-// (complete 32-byte sectors). Direct per-lane stores wrote half sectors at a 32-row stride and cost L2 bandwidth the operand
-// loads need (profiles/r1_gemm_shapes_metrics.csv).
-template <int NCH>
-__device__ __forceinline__ void warp_store_rows(uint8_t* stg, const uint4 (&vals)[NCH], __nv_bfloat16* base, long long ld, int row0, int M, int lane) {
-    constexpr int ROWB = NCH * 16;                 // bytes per staged row
-    constexpr int LPR = NCH;                       // lanes per row when reading back
-    constexpr int RPI = 32 / LPR;                  // rows per read iteration
+// Epilogue store of bf16 tiles: every lane holds NCH 16-byte pieces of ITS row (a tcgen05.ld 32x32b chunk is row-per-lane). The warp
+// writes them into its staging tile in the TMA swizzle pattern (NCH == 8: 128-byte rows / SWIZZLE_128B, NCH == 4: 64-byte rows /
+// SWIZZLE_64B — both bank-conflict free for row-per-lane 16-byte writes) and one lane issues a TMA tile store: the copy to global
+// memory, its address arithmetic and the clipping of rows >= M / columns >= N are the copy engine's work. (Round 1 read the tile back
+// with LDS and wrote it with predicated 16-byte STG: that store line alone was 16 % of the GEGLU kernel's stall samples and 11 % of
+// its instructions, and the serial STS -> LDS -> STG chain of 8 epilogue warps bounded every K <= 1024 problem: ncu r2l.)
+// `pending` = how many earlier store groups of this warp may still be reading OTHER staging buffers.
+template <int NCH, int PENDING>
+__device__ __forceinline__ void warp_store_tma(uint8_t* stg, const uint4 (&vals)[NCH], const CUtensorMap* map, int col, int row0, int lane) {
+    constexpr int ROWB = NCH * 16;
+    if (lane == 0) bulk_wait_group_read<PENDING>();   // the buffer's previous tile has been read out
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int sw = (NCH == 8) ? (c ^ (lane & 7)) : (c ^ ((lane >> 1) & 3));
         *reinterpret_cast<uint4*>(stg + lane * ROWB + sw * 16) = vals[c];
     }
+    fence_proxy_async();
     __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 32 / RPI; ++it) {
-        const int r = it * RPI + lane / LPR, c = lane % LPR;
-        const int sw = (NCH == 8) ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3));
-        const uint4 v = *reinterpret_cast<const uint4*>(stg + r * ROWB + sw * 16);
-        if (row0 + r < M) *reinterpret_cast<uint4*>(base + (long long)(row0 + r) * ld + c * 8) = v;
+    if (lane == 0) {
+        tma_store_2d(map, stg, col, row0);
+        bulk_commit_group();
     }
 }
 
-// Exact (erf) GELU of x-transformers' GLU (A.2) with erf from Abramowitz-Stegun 7.1.26: |error| < 6e-7 absolute on the GELU value
-// (the result is rounded to bf16, 4e-3 relative) for 2 MUFU + ~11 FMA-pipe instructions; libdevice erff() is ~30 instructions with
-// a branch, and this epilogue is what bounds the GEGLU GEMM (ncu r1h: tensor pipe 29 %, ALU 39 %, XU 23 %).
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float ax = fabsf(x) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
-    const float erf_abs = fmaf(-p, e, 1.0f);            // erf(|x| / sqrt 2)
-    return 0.5f * x + 0.5f * fabsf(x) * erf_abs;         // 0.5 x (1 + sign(x) erf(|x|/sqrt 2))
+// Exact (erf) GELU of x-transformers' GLU (A.2) for a PAIR of pre-activations:  gelu(x) = x Phi(x) = relu(x) - |x| Phi(-|x|), with the
+// Gaussian tail written as Phi(-a) = 2^(-h(a)) and h a degree-7 polynomial (Chebyshev fit on [0, 6]; beyond, h keeps growing and
+// a 2^-h < 6e-9): |error| < 5e-7 absolute on the GELU value in fp32 Horner arithmetic, 0.5 % of a bf16 half-ulp of the result.
+// 7 FFMA2 + 2 MUFU.EX2 + ~5 more per PAIR; the Abramowitz-Stegun form it replaces cost 2 MUFU + ~13 scalar FMA-pipe instructions per
+// element, and this epilogue is what bounds the GEGLU GEMM (ncu r2l: 46 instructions per hidden unit, issue-active 48 %, tensor 34 %).
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 a = make_float2(fabsf(x.x), fabsf(x.y));
+    float2 t = __ffma2_rn(a, make_float2(-1.9449223600531695e-06f, -1.9449223600531695e-06f), make_float2(6.386057066265494e-05f, 6.386057066265494e-05f));
+    t = __ffma2_rn(t, a, make_float2(-0.0009488713694736362f, -0.0009488713694736362f));
+    t = __ffma2_rn(t, a, make_float2(0.008582375012338161f, 0.008582375012338161f));
+    t = __ffma2_rn(t, a, make_float2(-0.0541183240711689f, -0.0541183240711689f));
+    t = __ffma2_rn(t, a, make_float2(-0.4582974314689636f, -0.4582974314689636f));
+    t = __ffma2_rn(t, a, make_float2(-1.1513246297836304f, -1.1513246297836304f));
+    t = __ffma2_rn(t, a, make_float2(-0.9999869465827942f, -0.9999869465827942f));   // -h(a)
+    float ex, ey;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(t.y));
+    return __ffma2_rn(make_float2(-a.x, -a.y), make_float2(ex, ey), make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 
 template <int BN, bool A_MN, bool B_MN, int MH, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                    const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                    const __grid_constant__ CUtensorMap tmD2, const GemmParams p) {
     using S = GemmSmem<BN, MH, CG>;
     static_assert(CG == 1 || (CG == 2 && MH == 1 && BN == 256), "pair kernel: 2 x (128 x 256) tile");
     static_assert(2 * MH * BN <= 512, "accumulators must fit TMEM");
@@ -118,12 +123,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smA = smem;
     uint8_t* smB = smem + kStages * S::A_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES);
+    uint8_t* stg_base = smem + S::TILE_BYTES;     // 1024-byte aligned (TILE_BYTES is a multiple of 1024)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::TILE_BYTES + S::STG_BYTES);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    uint8_t* stg_base = smem + S::TILE_BYTES + S::BAR_BYTES;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -132,6 +137,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmA2);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmD);
+        tma_prefetch_desc(&tmD2);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -267,48 +274,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int q = warp & 3;            // TMEM lane quadrant this warp may access
         const int chalf = (warp - 2) >> 2; // which half of the tile columns (two 32-column chunks) this warp drains
         const int ew = warp - 2;           // epilogue warp index -> private staging tile
+        uint32_t nstore = 0;               // GEGLU path: TMA stores issued by this warp (selects the staging half)
         int iter = 0;
         for (int w = w_first; w < p.num_work; w += w_step, ++iter) {
             const int tm = (w % p.tiles_m) * CG + (int)rank;   // 128*MH-row tile index of this CTA
             const int tn = (w / p.tiles_m) % p.tiles_n;
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
-            // ---- epilogue vectors of this warp's column half, fetched while the accumulator is still being produced:
-            //      plain path : lane l holds columns colh0 + 4l .. +3 (BN/2 columns -> BN/8 lanes)
-            //      GEGLU path : per 128-column group [64 u | 64 gate]: lanes 16*sub + 0..7 hold this warp's 32 u columns, +8..15 its 32 gates
-            float4 bsl = make_float4(0.f, 0.f, 0.f, 0.f);
-            int slice_col = -1;
-            if (!p.geglu) {
-                if (lane * 4 < BN / 2) slice_col = tn * BN + chalf * (BN / 2) + lane * 4;
-            } else {
-                if ((lane >> 4) < BN / 128) slice_col = tn * BN + (lane >> 4) * 128 + ((lane >> 3) & 1) * 64 + chalf * 32 + (lane & 7) * 4;
-            }
-            auto load_slice = [&](const float* vec, float fill) {
-                float4 o = make_float4(fill, fill, fill, fill);
-                if (slice_col >= 0 && slice_col < p.N) {
-                    if (slice_col + 4 <= p.N && ((reinterpret_cast<uintptr_t>(vec + slice_col) & 15) == 0)) {
-                        o = __ldg(reinterpret_cast<const float4*>(vec + slice_col));
-                    } else {
-                        o.x = __ldg(vec + slice_col);
-                        if (slice_col + 1 < p.N) o.y = __ldg(vec + slice_col + 1);
-                        if (slice_col + 2 < p.N) o.z = __ldg(vec + slice_col + 2);
-                        if (slice_col + 3 < p.N) o.w = __ldg(vec + slice_col + 3);
-                    }
-                }
-                return o;
-            };
-            if (p.bias) bsl = load_slice(p.bias, 0.f);
-            float4 csl_mh[MH];
-            bool csu_mh[MH];
+            // bias / gate slices of this warp's column half (BN/2 fp32 = up to 4 lines each): pulled into L1 while the accumulator is
+            // still being produced, so the broadcast loads behind the TMEM read hit
+            {
+                const int colh = tn * BN + chalf * (BN / 2) + lane * 32;
+                if (lane < BN / 64 && colh < p.N) {
+                    if (p.bias) prefetch_l1(p.bias + colh);
+                    if (p.bias && p.geglu) prefetch_l1(p.bias + min(colh + BN / 2, p.N - 1));   // GEGLU warps read u and gate columns of both halves
+                    if (p.colscale) {
 #pragma unroll
-            for (int mh = 0; mh < MH; ++mh) {
-                csl_mh[mh] = make_float4(1.f, 1.f, 1.f, 1.f);
-                csu_mh[mh] = false;
-                if (p.colscale) {
-                    const int rfirst = tm * BMT + mh * BM + q * 32, rlast = min(rfirst + 31, p.M - 1);
-                    if (rfirst < p.M && rfirst / p.rows_per_batch == rlast / p.rows_per_batch) {   // warp-uniform batch element
-                        csu_mh[mh] = true;
-                        csl_mh[mh] = load_slice(p.colscale + (long long)(rfirst / p.rows_per_batch) * p.N, 1.f);
+                        for (int mh = 0; mh < MH; ++mh) {
+                            const int rf = tm * BMT + mh * BM + q * 32;
+                            if (rf < p.M) prefetch_l1(p.colscale + (long long)(rf / p.rows_per_batch) * p.N + colh);
+                        }
                     }
                 }
             }
@@ -316,177 +301,166 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
 #pragma unroll 1
             for (int mh = 0; mh < MH; ++mh) {
-            const int row = tm * BMT + mh * BM + q * 32 + lane;
+            const int row0 = tm * BMT + mh * BM + q * 32;   // first of the warp's 32 rows
+            const int row = row0 + lane;
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + as * (MH * BN) + mh * BN + ((uint32_t)(q * 32) << 16);
             const bool masked = p.rowmask && row_ok && (p.rowmask[row] == 0);
+            // AdaLN gate row: per batch element. When the warp's 32 rows lie in one batch element (the usual case) the gate row is
+            // warp-uniform and is fetched with broadcast vector loads; a warp that straddles two elements loads per lane.
             const float* cs = (p.colscale && row_ok) ? p.colscale + (long long)(row / p.rows_per_batch) * p.N : nullptr;
-            const float4 csl = (MH == 1 || mh == 0) ? csl_mh[0] : csl_mh[MH - 1];
-            const bool cs_uniform = (MH == 1 || mh == 0) ? csu_mh[0] : csu_mh[MH - 1];
+            const int rlast = min(row0 + 31, p.M - 1);
+            const float* csu = (p.colscale && row0 < p.M && row0 / p.rows_per_batch == rlast / p.rows_per_batch)
+                                   ? p.colscale + (long long)(row0 / p.rows_per_batch) * p.N : nullptr;
+            uint8_t* stg = stg_base + ew * S::STG_WARP;
 
             if (!p.geglu) {
-                uint8_t* stg = stg_base + ew * 4224;
-                const int row0 = tm * BMT + mh * BM + q * 32;
-                uint4 held[8];   // bf16 pieces of an even chunk, kept until its odd partner completes a 128-byte row segment
 #pragma unroll 1
-                for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
-                    uint32_t r[32];
-                    __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated tail of the previous chunk
-                    tmem_ld32(taddr + c * 32, r);
-                    tmem_ld_wait();
-                    const int col0 = tn * BN + c * 32;
-                    if (col0 >= p.N) continue;                       // warp-uniform
-                    const int nvalid = min(32, p.N - col0);
-                    const bool pair_full = !p.d_fp32 && (tn * BN + (c & ~1) * 32 + 64 <= p.N);   // warp-uniform: staged 128-byte rows
-                    float v[32];
+                for (int cpair = chalf * (BN / 128); cpair < (chalf + 1) * (BN / 128); ++cpair) {   // 64 output columns = one 128-byte bf16 row segment
+                    if (tn * BN + cpair * 64 >= p.N) continue;       // warp-uniform
+                    uint4 held[8];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    // bias / gate vectors: the warp's slice was fetched before the accumulator wait (one float4 per lane) and is
-                    // broadcast with shuffles — a global load here would sit on the epilogue's critical path once per chunk
-                    const int sl = (c - chalf * (BN / 64)) * 8;   // first lane holding this chunk's 32 columns
-                    if (p.bias) {
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int c = cpair * 2 + hh;
+                        const int col0 = tn * BN + c * 32;
+                        if (col0 >= p.N) {                           // warp-uniform: the TMA store clips these columns anyway
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float comp = (j & 3) == 0 ? bsl.x : (j & 3) == 1 ? bsl.y : (j & 3) == 2 ? bsl.z : bsl.w;
-                            v[j] += __shfl_sync(0xffffffffu, comp, sl + (j >> 2));
+                            for (int g = 0; g < 4; ++g) held[hh * 4 + g] = make_uint4(0u, 0u, 0u, 0u);
+                            continue;
                         }
-                    }
-                    if (p.colscale) {
-                        if (cs_uniform) {
+                        uint32_t r[32];
+                        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated tails of the previous chunk
+                        tmem_ld32(taddr + c * 32, r);
+                        tmem_ld_wait();
+                        const int nvalid = min(32, p.N - col0);
+                        float v[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float comp = (j & 3) == 0 ? csl.x : (j & 3) == 1 ? csl.y : (j & 3) == 2 ? csl.z : csl.w;
-                                v[j] *= __shfl_sync(0xffffffffu, comp, sl + (j >> 2));
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        // bias / gate vectors: warp-uniform addresses -> one broadcast sector per 16-byte load (the shuffle broadcast
+                        // of round 1 was 20 % of the instructions of the gated out-projection GEMMs)
+                        if (p.bias) {
+                            if (nvalid == 32 && (reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0) {
+#pragma unroll
+                                for (int g = 0; g < 8; ++g) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + g);
+                                    v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + col0 + j);
                             }
-                        } else if (cs) {   // the warp's 32 rows straddle two batch elements: per-lane gate rows
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] *= __ldg(cs + col0 + j);
                         }
-                    }
-                    if (masked) {
+                        if (p.colscale) {
+                            if (csu && nvalid == 32 && (reinterpret_cast<uintptr_t>(csu + col0) & 15) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                    }
-                    if (p.resid && row_ok) {
-                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + (long long)row * p.ldr + col0;
-                        if (nvalid == 32) {
+                                for (int g = 0; g < 8; ++g) {
+                                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(csu + col0) + g);
+                                    v[4 * g] *= c4.x; v[4 * g + 1] *= c4.y; v[4 * g + 2] *= c4.z; v[4 * g + 3] *= c4.w;
+                                }
+                            } else if (cs) {   // per-lane gate rows
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const uint4 u = *reinterpret_cast<const uint4*>(rp + g * 8);
-                                v[g * 8 + 0] += bf16_lo(u.x); v[g * 8 + 1] += bf16_hi(u.x);
-                                v[g * 8 + 2] += bf16_lo(u.y); v[g * 8 + 3] += bf16_hi(u.y);
-                                v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
-                                v[g * 8 + 6] += bf16_lo(u.w); v[g * 8 + 7] += bf16_hi(u.w);
+                                for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] *= __ldg(cs + col0 + j);
                             }
-                        } else {   // (unrolled + predicated: a runtime trip count would index v[] dynamically and push it to local memory)
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __bfloat162float(rp[j]);
                         }
-                    }
-                    if (p.d_fp32 && p.atomic_out) {
-                        warp_red_rows_f32(reinterpret_cast<float*>(stg), v, reinterpret_cast<float*>(p.D) + col0, p.ldd, row0, p.M, nvalid, lane);
-                    } else if (p.d_fp32) {
-                        float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
-                        if (!row_ok) {
-                        } else if (nvalid == 32 && (p.ldd & 3) == 0) {
+                        if (masked) {
 #pragma unroll
-                            for (int g = 0; g < 8; ++g)
-                                *reinterpret_cast<float4*>(dp + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        }
+                        if (p.resid && row_ok) {
+                            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + (long long)row * p.ldr + col0;
+                            if (nvalid == 32) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    const uint4 u = *reinterpret_cast<const uint4*>(rp + g * 8);
+                                    v[g * 8 + 0] += bf16_lo(u.x); v[g * 8 + 1] += bf16_hi(u.x);
+                                    v[g * 8 + 2] += bf16_lo(u.y); v[g * 8 + 3] += bf16_hi(u.y);
+                                    v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
+                                    v[g * 8 + 6] += bf16_lo(u.w); v[g * 8 + 7] += bf16_hi(u.w);
+                                }
+                            } else {   // (unrolled + predicated: a runtime trip count would index v[] dynamically and push it to local memory)
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+                            }
+                        }
+                        if (p.d_fp32 && p.atomic_out) {
+                            warp_red_rows_f32(reinterpret_cast<float*>(stg), v, reinterpret_cast<float*>(p.D) + col0, p.ldd, row0, p.M, nvalid, lane);
+                        } else if (p.d_fp32) {
+                            float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
+                            if (!row_ok) {
+                            } else if (nvalid == 32 && (p.ldd & 3) == 0) {
+#pragma unroll
+                                for (int g = 0; g < 8; ++g)
+                                    *reinterpret_cast<float4*>(dp + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (j < nvalid) dp[j] = v[j];
+                            }
                         } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (j < nvalid) dp[j] = v[j];
-                        }
-                    } else if (pair_full) {
-                        uint4 pk[4];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            pk[g] = make_uint4(pack_bf16(v[g * 8], v[g * 8 + 1]), pack_bf16(v[g * 8 + 2], v[g * 8 + 3]),
-                                               pack_bf16(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16(v[g * 8 + 6], v[g * 8 + 7]));
-                        if (c & 1) {
-                            held[4] = pk[0]; held[5] = pk[1]; held[6] = pk[2]; held[7] = pk[3];
-                            warp_store_rows<8>(stg, held, reinterpret_cast<__nv_bfloat16*>(p.D) + (col0 - 32), p.ldd, row0, p.M, lane);
-                        } else {
-                            held[0] = pk[0]; held[1] = pk[1]; held[2] = pk[2]; held[3] = pk[3];
-                        }
-                    } else if (row_ok) {
-                        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)row * p.ldd + col0;
-                        if (nvalid == 32) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g)
-                                *reinterpret_cast<uint4*>(dp + g * 8) =
-                                    make_uint4(pack_bf16(v[g * 8], v[g * 8 + 1]), pack_bf16(v[g * 8 + 2], v[g * 8 + 3]),
-                                               pack_bf16(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16(v[g * 8 + 6], v[g * 8 + 7]));
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (j < nvalid) dp[j] = __float2bfloat16(v[j]);
+                                held[hh * 4 + g] = make_uint4(pack_bf16(v[g * 8], v[g * 8 + 1]), pack_bf16(v[g * 8 + 2], v[g * 8 + 3]),
+                                                              pack_bf16(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16(v[g * 8 + 6], v[g * 8 + 7]));
                         }
                     }
+                    if (!p.d_fp32) warp_store_tma<8, 0>(stg, held, &tmD, tn * BN + cpair * 64, row0, lane);
                 }
             } else {
                 // GEGLU: every 128 packed columns hold [0,64) = u, [64,128) = gate of the same 64 hidden units
-                const float keep_scale = p.dropout_p > 0.f ? 65536.f / (65536.f - (float)(uint32_t)(p.dropout_p * 65536.f)) : 1.f;
+                const bool do_drop = p.dropout_p > 0.f;
+                const float keep_scale = do_drop ? 65536.f / (65536.f - (float)(uint32_t)(p.dropout_p * 65536.f)) : 1.f;
+                const uint32_t seedmix = do_drop ? seed_mix32(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull)) : 0u;
+                const uint32_t thr32 = drop_thresh32((uint32_t)(p.dropout_p * 65536.f));
 #pragma unroll 1
                 for (int sub = 0; sub < BN / 128; ++sub) {
                     const int c = chalf;
                     if (tn * BN + sub * 128 >= p.N) continue;   // warp-uniform (N % 128 == 0: a 128-column group is all in or all out)
                     uint32_t ru[32], rg[32];
+                    const int colp = tn * BN + sub * 128 + c * 32;         // packed column of u
                     __syncwarp();
                     tmem_ld32(taddr + sub * 128 + c * 32, ru);
                     tmem_ld32(taddr + sub * 128 + 64 + c * 32, rg);
                     tmem_ld_wait();
-                    const int colp = tn * BN + sub * 128 + c * 32;         // packed column of u
+                    // packed bias of this warp's 32 u / 32 gate columns (N % 128 == 0, base 16-byte aligned): warp-uniform addresses, one
+                    // broadcast sector per load (the shuffle broadcast of round 1 cost 64 SHFL + selects per 32 hidden units)
+                    const float4* pbu = reinterpret_cast<const float4*>(p.bias + (p.bias ? colp : 0));
                     const int hcol0 = tn * (BN / 2) + sub * 64 + c * 32;   // hidden-unit column
-                    uint8_t* stg = stg_base + ew * 4224;
-                    const int row0 = tm * BMT + mh * BM + q * 32;
-                    float u[32], g[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { u[j] = __uint_as_float(ru[j]); g[j] = __uint_as_float(rg[j]); }
-                    if (p.bias) {   // packed bias: slices fetched before the accumulator wait, broadcast by shuffle
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float comp = (j & 3) == 0 ? bsl.x : (j & 3) == 1 ? bsl.y : (j & 3) == 2 ? bsl.z : bsl.w;
-                            u[j] += __shfl_sync(0xffffffffu, comp, sub * 16 + (j >> 2));
-                            g[j] += __shfl_sync(0xffffffffu, comp, sub * 16 + 8 + (j >> 2));
-                        }
-                    }
+                    // everything below works on column PAIRS (2k, 2k+1): packed fp32x2 adds / FMAs, one bf16x2 conversion per pair
                     uint4 pu[4], pg[4], ph[4];
+                    uint32_t* wu = reinterpret_cast<uint32_t*>(pu);
+                    uint32_t* wg = reinterpret_cast<uint32_t*>(pg);
+                    uint32_t* wh = reinterpret_cast<uint32_t*>(ph);
 #pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
-                        pu[gq] = make_uint4(pack_bf16(u[gq * 8], u[gq * 8 + 1]), pack_bf16(u[gq * 8 + 2], u[gq * 8 + 3]),
-                                            pack_bf16(u[gq * 8 + 4], u[gq * 8 + 5]), pack_bf16(u[gq * 8 + 6], u[gq * 8 + 7]));
-                        pg[gq] = make_uint4(pack_bf16(g[gq * 8], g[gq * 8 + 1]), pack_bf16(g[gq * 8 + 2], g[gq * 8 + 3]),
-                                            pack_bf16(g[gq * 8 + 4], g[gq * 8 + 5]), pack_bf16(g[gq * 8 + 6], g[gq * 8 + 7]));
+                    for (int i = 0; i < 8; ++i) {
+                        float4 bu = make_float4(0.f, 0.f, 0.f, 0.f), bg = bu;
+                        if (p.bias) { bu = __ldg(pbu + i); bg = __ldg(pbu + 16 + i); }
+                        const float2 ua = __fadd2_rn(make_float2(__uint_as_float(ru[4 * i]), __uint_as_float(ru[4 * i + 1])), make_float2(bu.x, bu.y));
+                        const float2 ub = __fadd2_rn(make_float2(__uint_as_float(ru[4 * i + 2]), __uint_as_float(ru[4 * i + 3])), make_float2(bu.z, bu.w));
+                        const float2 ga = __fadd2_rn(make_float2(__uint_as_float(rg[4 * i]), __uint_as_float(rg[4 * i + 1])), make_float2(bg.x, bg.y));
+                        const float2 gb = __fadd2_rn(make_float2(__uint_as_float(rg[4 * i + 2]), __uint_as_float(rg[4 * i + 3])), make_float2(bg.z, bg.w));
+                        wu[2 * i] = pack_bf16(ua.x, ua.y); wu[2 * i + 1] = pack_bf16(ub.x, ub.y);
+                        wg[2 * i] = pack_bf16(ga.x, ga.y); wg[2 * i + 1] = pack_bf16(gb.x, gb.y);
                     }
+                    // 2 KB tiles (32 rows x 64 B) alternate between the two halves of the staging buffer: before a half is rewritten, at
+                    // most ONE later store group may still be pending
                     if (p.D2) {
-                        __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.D2) + colp;
-                        warp_store_rows<4>(stg, pu, d2, p.ldd2, row0, p.M, lane);
-                        warp_store_rows<4>(stg, pg, d2 + 64, p.ldd2, row0, p.M, lane);
+                        warp_store_tma<4, 1>(stg + (nstore++ & 1) * 2048, pu, &tmD2, colp, row0, lane);
+                        warp_store_tma<4, 1>(stg + (nstore++ & 1) * 2048, pg, &tmD2, colp + 64, row0, lane);
                     }
-                    float h[32];
+                    // hidden-unit pairs (2k, 2k+1) of one row share a 32-bit hash; N/2 is even, so (row * N/2 + hcol) >> 1 pairs them
+                    const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned long long)(p.N / 2) + hcol0) >> 1);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         // the backward pass recomputes from the bf16-rounded pre-activations: use them here too
-                        const float ub = __bfloat162float(__float2bfloat16(u[j]));
-                        const float gb = __bfloat162float(__float2bfloat16(g[j]));
-                        h[j] = ub * gelu_erf(gb);
-                    }
-                    if (p.dropout_p > 0.f) {
-                        // hidden-unit pairs (2k, 2k+1) of one row share a 32-bit hash; N/2 is even, so (row * N/2 + hcol) >> 1 pairs them
-                        const uint32_t pbase = (uint32_t)(((unsigned long long)row * (unsigned long long)(p.N / 2) + hcol0) >> 1);
-                        const uint32_t seedmix = seed_mix32(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull));
-                        const uint32_t thr32 = drop_thresh32((uint32_t)(p.dropout_p * 65536.f));
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const DropWords hsh = drop_words(seedmix, pbase + (j >> 1));
-                            h[j] = (hsh.a >= thr32) ? h[j] * keep_scale : 0.f;
-                            h[j + 1] = (hsh.b >= thr32) ? h[j + 1] * keep_scale : 0.f;
+                        const float2 ub = make_float2(bf16_lo(wu[j]), bf16_hi(wu[j]));
+                        const float2 gb = make_float2(bf16_lo(wg[j]), bf16_hi(wg[j]));
+                        float2 h2 = __fmul2_rn(ub, gelu_erf2(gb));
+                        if (do_drop) {
+                            const DropWords hsh = drop_words(seedmix, pbase + j);
+                            h2 = __fmul2_rn(h2, make_float2(hsh.a >= thr32 ? keep_scale : 0.f, hsh.b >= thr32 ? keep_scale : 0.f));
                         }
+                        wh[j] = pack_bf16(h2.x, h2.y);
                     }
-#pragma unroll
-                    for (int gq = 0; gq < 4; ++gq)
-                        ph[gq] = make_uint4(pack_bf16(h[gq * 8], h[gq * 8 + 1]), pack_bf16(h[gq * 8 + 2], h[gq * 8 + 3]),
-                                            pack_bf16(h[gq * 8 + 4], h[gq * 8 + 5]), pack_bf16(h[gq * 8 + 6], h[gq * 8 + 7]));
-                    warp_store_rows<4>(stg, ph, reinterpret_cast<__nv_bfloat16*>(p.D) + hcol0, p.ldd, row0, p.M, lane);
+                    warp_store_tma<4, 1>(stg + (nstore++ & 1) * 2048, ph, &tmD, hcol0, row0, lane);
                 }
             }
             }  // mh
@@ -497,6 +471,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 else mbar_arrive(&tempty_bar[as]);
             }
         }
+        if (lane == 0) bulk_wait_group_read<0>();   // the staging tiles must stay valid until the copy engine has read them
     }
 
     tc_fence_before();
@@ -527,46 +502,49 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements; box = 64 x box_outer, 128B swizzle.
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements; box = box_inner x box_outer with the swizzle
+// whose span equals the box's row bytes (64 elements / 128B swizzle for operand tiles and plain output tiles, 32 elements / 64B
+// swizzle for the GEGLU output pieces).
 // A descriptor is a pure function of (pointer, extents, pitch, box): the caching allocator hands the same addresses back every
-// training step, so a small per-thread direct-mapped cache removes ~1000 driver encode calls per step from the host critical path.
-struct MapKey { const void* ptr; int64_t inner, outer, ld; int box; };
+// training step, so a small per-thread direct-mapped cache removes ~1500 driver encode calls per step from the host critical path.
+struct MapKey { const void* ptr; int64_t inner, outer, ld; int box, box_inner; };
 struct MapSlot { MapKey k; CUtensorMap m; bool valid; };
-static int make_map_uncached(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer);
-static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
-    constexpr int kSlots = 512;
+static int make_map_uncached(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer, int box_inner);
+static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer, int box_inner = 64) {
+    constexpr int kSlots = 1024;
     static thread_local MapSlot cache[kSlots];
     uint64_t h = reinterpret_cast<uintptr_t>(ptr) >> 4;
-    h = (h ^ (uint64_t)inner * 0x9E3779B97F4A7C15ull ^ (uint64_t)outer * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)ld * 0x165667B19E3779F9ull ^ (uint64_t)box_outer) * 0xFF51AFD7ED558CCDull;
+    h = (h ^ (uint64_t)inner * 0x9E3779B97F4A7C15ull ^ (uint64_t)outer * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)ld * 0x165667B19E3779F9ull ^ (uint64_t)(box_outer * 131 + box_inner)) * 0xFF51AFD7ED558CCDull;
     MapSlot& sl = cache[(h >> 40) % kSlots];
-    if (sl.valid && sl.k.ptr == ptr && sl.k.inner == inner && sl.k.outer == outer && sl.k.ld == ld && sl.k.box == box_outer) {
+    if (sl.valid && sl.k.ptr == ptr && sl.k.inner == inner && sl.k.outer == outer && sl.k.ld == ld && sl.k.box == box_outer && sl.k.box_inner == box_inner) {
         *m = sl.m;
         return 0;
     }
-    if (int rc = make_map_uncached(m, ptr, inner, outer, ld, box_outer)) return rc;
-    sl.k = MapKey{ptr, inner, outer, ld, box_outer};
+    if (int rc = make_map_uncached(m, ptr, inner, outer, ld, box_outer, box_inner)) return rc;
+    sl.k = MapKey{ptr, inner, outer, ld, box_outer, box_inner};
     sl.m = *m;
     sl.valid = true;
     return 0;
 }
-static int make_map_uncached(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+static int make_map_uncached(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer, int box_inner) {
     PFN_encodeTiled enc = get_encode_fn();
     B200_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
     B200_REQUIRE((ld % 8) == 0, "gemm: row pitch %lld not a multiple of 8 elements", (long long)ld);
     B200_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm: operand not 16-byte aligned");
     cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
 
 template <int BN, bool A_MN, bool B_MN, int MH, int CG = 1>
-static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUtensorMap& tB, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap (&tm)[5], const GemmParams& p, cudaStream_t st) {
+    const CUtensorMap &tA = tm[0], &tA2 = tm[1], &tB = tm[2], &tD = tm[3], &tD2 = tm[4];
     using S = GemmSmem<BN, MH, CG>;
     auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, MH, CG>;
     static DeviceOnce once;   // one flag per template instantiation and device
@@ -594,12 +572,12 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tA2, const CUte
             pairs_cache[current_device()].store(pairs, std::memory_order_relaxed);
         }
         cfg.gridDim = dim3(2 * (p.num_work < pairs ? p.num_work : pairs));
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA, tA2, tB, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA, tA2, tB, tD, tD2, p);
         B200_REQUIRE(e == cudaSuccess, "gemm: cluster launch: %s", cudaGetErrorString(e));
         return check_launch("gemm_tcgen05_kernel<pair>");
     }
     const int grid = p.num_work < num_sms() ? p.num_work : num_sms();
-    B200_LAUNCH(kern, grid, kGemmThreads, S::TOTAL, st, tA, tA2, tB, p);
+    B200_LAUNCH(kern, grid, kGemmThreads, S::TOTAL, st, tA, tA2, tB, tD, tD2, p);
     return check_launch("gemm_tcgen05_kernel");
 }
 
@@ -664,11 +642,13 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
     if (a->geglu) {
         B200_REQUIRE((a->N % 128) == 0 && !a->d_fp32 && !a->colscale && !a->rowmask && !a->resid, "gemm: GEGLU needs N %% 128 == 0, bf16 out, no other epilogue");
         B200_REQUIRE((a->ldd % 8) == 0 && (!a->D2 || (a->ldd2 % 8) == 0), "gemm: GEGLU output pitch must be a multiple of 8");
+        B200_REQUIRE(!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "gemm: GEGLU bias must be 16-byte aligned");
     }
     if (!a->d_fp32) B200_REQUIRE((a->ldd % 8) == 0, "gemm: bf16 output pitch must be a multiple of 8");
     if (a->resid) B200_REQUIRE((a->ldr % 8) == 0, "gemm: residual pitch must be a multiple of 8");
 
-    CUtensorMap tA, tA2, tB;
+    CUtensorMap tm[5];
+    CUtensorMap &tA = tm[0], &tA2 = tm[1], &tB = tm[2], &tD = tm[3], &tD2 = tm[4];
     int rc;
     const int64_t KA = a->A2 ? a->K1 : a->K;
     if (!a_mn) rc = make_map(&tA, a->A, KA, a->M, a->lda, BM);
@@ -683,6 +663,17 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
     if (!b_mn) rc = make_map(&tB, a->B, a->K, a->N, a->ldb, 128);   // 128 B rows per CTA for both the 128-wide tile and the pair's half of 256
     else rc = make_map(&tB, a->B, a->N, a->K, a->ldb, BK);
     if (rc) return rc;
+    // bf16 outputs leave through TMA tile stores of 32 rows: [M, N] in 64-column pieces, GEGLU [M, N/2] (+ pre-activations [M, N]) in 32-column pieces
+    tD = tA; tD2 = tA;   // (placeholders when the fp32 paths write the output)
+    if (!a->d_fp32) {
+        if (a->geglu) rc = make_map(&tD, a->D, a->N / 2, a->M, a->ldd, 32, 32);
+        else rc = make_map(&tD, a->D, a->N, a->M, a->ldd, 32, 64);
+        if (rc) return rc;
+        if (a->geglu && a->D2) {
+            B200_REQUIRE((reinterpret_cast<uintptr_t>(a->D2) & 15) == 0, "gemm: GEGLU pre-activation buffer must be 16-byte aligned");
+            if ((rc = make_map(&tD2, a->D2, a->N, a->M, a->ldd2, 32, 32))) return rc;
+        }
+    }
 
     {
         static const bool trace = getenv("B200_GEMM_TRACE") != nullptr;   // developer aid: correlate ncu launch lists with problem shapes
@@ -691,19 +682,19 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
                     p.geglu, a->A2 != nullptr, pair ? 3 : MH, p.bias != nullptr, p.colscale != nullptr, p.rowmask != nullptr, p.resid != nullptr);
     }
     if (pair) {
-        if (!a_mn && !b_mn) return launch_gemm<256, false, false, 1, 2>(tA, tA2, tB, p, st);
-        if (!a_mn && b_mn) return launch_gemm<256, false, true, 1, 2>(tA, tA2, tB, p, st);
-        if (a_mn && !b_mn) return launch_gemm<256, true, false, 1, 2>(tA, tA2, tB, p, st);
-        return launch_gemm<256, true, true, 1, 2>(tA, tA2, tB, p, st);
+        if (!a_mn && !b_mn) return launch_gemm<256, false, false, 1, 2>(tm, p, st);
+        if (!a_mn && b_mn) return launch_gemm<256, false, true, 1, 2>(tm, p, st);
+        if (a_mn && !b_mn) return launch_gemm<256, true, false, 1, 2>(tm, p, st);
+        return launch_gemm<256, true, true, 1, 2>(tm, p, st);
     }
     if (MH == 2) {
-        if (!a_mn && !b_mn) return launch_gemm<128, false, false, 2>(tA, tA2, tB, p, st);
-        if (!a_mn && b_mn) return launch_gemm<128, false, true, 2>(tA, tA2, tB, p, st);
-        if (a_mn && !b_mn) return launch_gemm<128, true, false, 2>(tA, tA2, tB, p, st);
-        return launch_gemm<128, true, true, 2>(tA, tA2, tB, p, st);
+        if (!a_mn && !b_mn) return launch_gemm<128, false, false, 2>(tm, p, st);
+        if (!a_mn && b_mn) return launch_gemm<128, false, true, 2>(tm, p, st);
+        if (a_mn && !b_mn) return launch_gemm<128, true, false, 2>(tm, p, st);
+        return launch_gemm<128, true, true, 2>(tm, p, st);
     }
-    if (!a_mn && !b_mn) return launch_gemm<128, false, false, 1>(tA, tA2, tB, p, st);
-    if (!a_mn && b_mn) return launch_gemm<128, false, true, 1>(tA, tA2, tB, p, st);
-    if (a_mn && !b_mn) return launch_gemm<128, true, false, 1>(tA, tA2, tB, p, st);
-    return launch_gemm<128, true, true, 1>(tA, tA2, tB, p, st);
+    if (!a_mn && !b_mn) return launch_gemm<128, false, false, 1>(tm, p, st);
+    if (!a_mn && b_mn) return launch_gemm<128, false, true, 1>(tm, p, st);
+    if (a_mn && !b_mn) return launch_gemm<128, true, false, 1>(tm, p, st);
+    return launch_gemm<128, true, true, 1>(tm, p, st);
 }

@@ -306,13 +306,12 @@ __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(c
 //   (2) tcgen05 GEMM   : G = R^T C over all (token, stream) rows (split-K), then hc_param_finalize_kernel turns G into
 //                        d(dynamic_alpha_fn), d(dynamic_beta_fn), d(norm.gamma).
 // grid.y = batch element: a block never straddles two batch elements (adaptive-gain gradient is per batch).
-constexpr int HC_TOK_PER_BLOCK = 64;
-#ifndef HC_BWD_MIN_BLOCKS
-#define HC_BWD_MIN_BLOCKS 1
-#endif
-
+// Tokens per block are chosen by the host so that the whole grid is ONE wave of co-resident blocks (hc_tokens_per_block): with a fixed 64
+// the cfg2 grid was 272 blocks on 148 one-block SMs — a second round with 16 % of the machine idle.
+// D <= 256 (VPT == 1) fits 128 registers, so two blocks (16 warps) share an SM: the per-token critical path (two warp-wide 32-value
+// reductions, tanh, ~70 shuffles) is latency-bound, and at D = 256 the backward took 70 % of the D = 512 time for half the bytes.
 template <int VPT, bool PF>
-__global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(const HcP p, __nv_bfloat16* __restrict__ cmat) {
+__global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(const HcP p, __nv_bfloat16* __restrict__ cmat, int tok_per_block) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float4 sp[];
     __shared__ float s_scal[32];
@@ -323,8 +322,8 @@ __global__ void __launch_bounds__(256, HC_BWD_MIN_BLOCKS) hc_width_bwd_kernel(co
     const int D = p.D, nchunk = D >> 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    const int n0 = blockIdx.x * HC_TOK_PER_BLOCK;
-    const int n1 = min(p.rows_per_batch, n0 + HC_TOK_PER_BLOCK);
+    const int n0 = blockIdx.x * tok_per_block;
+    const int n1 = min(p.rows_per_batch, n0 + tok_per_block);
     // PF: per-warp double buffer {r [HS][D], d_res [HS][D], d_branch [D]} filled by bulk (TMA) copies one token ahead
     const uint32_t tok_bytes = (uint32_t)(HS * D * 2), br_bytes = (uint32_t)(D * 2), buf_bytes = 2 * tok_bytes + br_bytes;
     uint8_t* wbuf = reinterpret_cast<uint8_t*>(sp) + hc_param_smem(D) + (size_t)warp * 2 * buf_bytes;
@@ -709,20 +708,27 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     __nv_bfloat16* cmat = reinterpret_cast<__nv_bfloat16*>(a->ws_records);
     float* G = a->ws_records + (size_t)a->T * 16;
     B200_REQUIRE((size_t)a->T * 24 >= (size_t)a->D * 8, "hc_width_bwd: workspace too small for D=%d at T=%lld", a->D, (long long)a->T);
-    dim3 grid((a->rows_per_batch + HC_TOK_PER_BLOCK - 1) / HC_TOK_PER_BLOCK, a->T / a->rows_per_batch);
+    // one wave: as many blocks per batch element as fit the co-resident slots (8 warps x >= 1 token each), tokens rounded up to the warp count
+    const int nbatch = a->T / a->rows_per_batch;
+    const int slots = num_sms() * (a->D <= 256 ? 2 : 1);
+    int per_batch = slots / nbatch > 0 ? slots / nbatch : 1;
+    int tpb = (a->rows_per_batch + per_batch - 1) / per_batch;
+    tpb = (tpb + 7) / 8 * 8;
+    if (tpb < 32) tpb = 32;                     // amortise the per-block parameter staging
+    dim3 grid((a->rows_per_batch + tpb - 1) / tpb, nbatch);
     const size_t smem_par = hc_param_smem(a->D);
     if (a->D <= 512 && hc_prefetch_enabled()) {
         const size_t smem = smem_par + (size_t)8 * 2 * (2 * HS + 1) * a->D * 2;   // + per-warp {r, d_res, d_branch} double buffers
         if (a->D <= 256) {
             if (int rc = set_smem<hc_width_bwd_kernel<1, true>>(smem)) return rc;
-            B200_LAUNCH((hc_width_bwd_kernel<1, true>), grid, 256, smem, st, p, cmat);
+            B200_LAUNCH((hc_width_bwd_kernel<1, true>), grid, 256, smem, st, p, cmat, tpb);
         } else {
             if (int rc = set_smem<hc_width_bwd_kernel<2, true>>(smem)) return rc;
-            B200_LAUNCH((hc_width_bwd_kernel<2, true>), grid, 256, smem, st, p, cmat);
+            B200_LAUNCH((hc_width_bwd_kernel<2, true>), grid, 256, smem, st, p, cmat, tpb);
         }
-    } else if (a->D <= 256) B200_LAUNCH((hc_width_bwd_kernel<1, false>), grid, 256, smem_par, st, p, cmat);
-    else if (a->D <= 512) B200_LAUNCH((hc_width_bwd_kernel<2, false>), grid, 256, smem_par, st, p, cmat);
-    else B200_LAUNCH((hc_width_bwd_kernel<4, false>), grid, 256, smem_par, st, p, cmat);
+    } else if (a->D <= 256) B200_LAUNCH((hc_width_bwd_kernel<1, false>), grid, 256, smem_par, st, p, cmat, tpb);
+    else if (a->D <= 512) B200_LAUNCH((hc_width_bwd_kernel<2, false>), grid, 256, smem_par, st, p, cmat, tpb);
+    else B200_LAUNCH((hc_width_bwd_kernel<4, false>), grid, 256, smem_par, st, p, cmat, tpb);
     if (int rc = check_launch("hc_width_bwd_kernel")) return rc;
     // G = R^T C on the tensor cores: A = residual streams [T*S, D] read MN-major, B = C [T*S, 8] MN-major, split-K over the tokens
     b200_gemm_args g = {};

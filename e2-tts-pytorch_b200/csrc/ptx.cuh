@@ -87,6 +87,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// TMA tile STORE (shared -> global, bulk async group): rows / columns of the box that fall outside the tensor are clipped by the hardware.
+// The issuing thread must have ordered the generic-proxy smem writes of the whole warp before it (fence.proxy.async by every writer,
+// then a warp barrier); the staging buffer may be rewritten once cp.async.bulk.wait_group.read has returned.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 // Programmatic dependent launch (PDL). Every kernel of the library executes pdl_wait() before its first global-memory access: when
 // the kernel was launched with the programmatic-stream-serialisation attribute (B200_PDL=1, common.cuh) its CTAs may become resident
@@ -220,36 +232,42 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// stg: 32 x 32 fp32 staging tile (4 KB), 16-byte groups XOR-swizzled by the row so that both the row-per-lane writes and the
+// 8-lanes-per-row reads are bank-conflict free without padding (the 4 KB tile doubles as the TMA-store staging buffer of the bf16 path)
 __device__ __forceinline__ void warp_red_rows_f32(float* stg, const float (&v)[32], float* base, long long ld, int row0, int nrows_total,
                                                   int ncols_valid, int lane) {
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = v[c];
+    for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((g ^ (lane & 7)) << 2)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     __syncwarp();
     if (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
         // 16-byte vector reductions (REDG.F32x4): 8 lanes cover the 128 bytes of a row, 4 rows per instruction
-        const int cg = (lane & 7) * 4, rsub = lane >> 3;
+        const int g = lane & 7, cg = g * 4, rsub = lane >> 3;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub;
             if (row0 + r < nrows_total) {
-                const float* sp = stg + r * 33 + cg;
+                const float4 s4 = *reinterpret_cast<const float4*>(stg + r * 32 + ((g ^ (r & 7)) << 2));
                 float* dst = base + (long long)(row0 + r) * ld + cg;
-                if (cg + 4 <= ncols_valid) red_add_v4(dst, sp[0], sp[1], sp[2], sp[3]);
-                else
+                if (cg + 4 <= ncols_valid) red_add_v4(dst, s4.x, s4.y, s4.z, s4.w);
+                else {
+                    const float sp[4] = {s4.x, s4.y, s4.z, s4.w};
                     for (int j = 0; j < 4; ++j)
                         if (cg + j < ncols_valid) atomicAdd(dst + j, sp[j]);
+                }
             }
         }
     } else if (lane < ncols_valid) {
 #pragma unroll 4
         for (int r = 0; r < 32; ++r)
-            if (row0 + r < nrows_total) atomicAdd(base + (long long)(row0 + r) * ld + lane, stg[r * 33 + lane]);
+            if (row0 + r < nrows_total) atomicAdd(base + (long long)(row0 + r) * ld + lane, stg[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))]);
     }
     __syncwarp();
 }
 
 // ---------------------------------------------------------------- misc
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

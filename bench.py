@@ -14,7 +14,8 @@ the CUDA-graph replay of forward + backward.
 One JSON line is printed by rank 0 (contract: see DESIGN.md §measurement):
   value     whole-job mel-frames/s with the batch already resident in HBM (device-timed, max over ranks)
   e2e       same metric through the public API with HOST (pinned) inputs: H2D of the inputs every step + D2H of the result
-  roofline  tcgen05 GEMM kernel family: algorithmic FLOPs / CUDA-event time vs the measured bf16 peak (MEASURED_PEAKS.json)
+  roofline  tcgen05 GEMM kernel family: algorithmic FLOPs of one step's GEMM launches / their device time (the recorded launches replayed
+            back to back as one CUDA graph, one CUDA-event pair around the replay) vs the measured bf16 peak (MEASURED_PEAKS.json)
   cpu_baseline  the oracle port (oracle/e2tts_oracle.py = the reference algorithm in fp32 PyTorch) on the host cores, on
                 BASELINE cfg1 exactly (B = 2 x 1024 frames, same d512 / depth-8 model): 2 warm-up + 5 timed steps, median
 `--impl reference` times that CPU path alone (the reference itself is pure Python + unvendored deps and cannot travel
@@ -258,19 +259,46 @@ def run_gpu(args):
     warm = max(args.warmup, 3) if kind != 'sample' else 1
     for _ in range(warm):
         step(dev_mel, False)
-    # -- per-kernel-family CUDA-event timing of the tcgen05 GEMM inside real steps (roofline numerator/denominator)
-    prof = dict(flops=0.0, events=[])
+    # -- time of the tcgen05 GEMM family inside one real step (roofline numerator / denominator): every ops.gemm call of ONE step is
+    #    recorded with its live operands, then the same calls are captured into one CUDA graph and replayed — the kernels run back to
+    #    back exactly as launched in the step, and the whole list is bracketed by ONE event pair. (Bracketing each launch of an eager
+    #    step with its own event pair also brackets the host's launch latency whenever the GPU waits for the host: h + max(kernel, h'),
+    #    which inflated the round-1/2 figures by up to 70 % on slow hosts.)
+    prof = dict(flops=0.0, calls=[])
     orig_gemm = ops.gemm
 
-    def gemm_timed(A, Bm, M, Nn, K, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    def gemm_recorded(A, Bm, M, Nn, K, **kw):
         out = orig_gemm(A, Bm, M, Nn, K, **kw)
-        e1.record()
-        prof['events'].append((e0, e1, (M, Nn, K, int(kw.get('a_mn', False)), int(kw.get('b_mn', False)), int(kw.get('split_k', 1)),
-                                        int(bool(kw.get('geglu'))), int(kw.get('A2') is not None))))
+        kw2 = dict(kw)
+        kw2['out'] = out          # the replay overwrites this step's outputs in place (nothing reads them afterwards)
+        prof['calls'].append((A, Bm, M, Nn, K, kw2))
         prof['flops'] += 2.0 * M * Nn * K
         return out
+
+    def replay_gemms():
+        calls = prof['calls']
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for c in calls[:8]:      # warm the descriptor cache / lazy init off the capture
+                orig_gemm(c[0], c[1], c[2], c[3], c[4], **c[5])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for c in calls:
+                orig_gemm(c[0], c[1], c[2], c[3], c[4], **c[5])
+        times = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        del g
+        times.sort()
+        return times[len(times) // 2]
 
     step_mode, graph_note, eager_ms = 'eager', None, None
     with ClockSampler(local) as clk:
@@ -278,23 +306,21 @@ def run_gpu(args):
         ms_dev = timed(lambda: step(dev_mel, False), steps)
         launches = (lib.launch_count() - n0) // steps
         ms_e2e = timed(lambda: step(host_mel.to(dev, non_blocking=True), True), steps)
-        ops.gemm = gemm_timed
-        two_stream, pkg.modules.TWO_STREAM = pkg.modules.TWO_STREAM, False   # per-kernel event times need the kernels serialised on one stream
-        nprof = 1 if kind == 'sample' else min(steps, 3)
+        ops.gemm = gemm_recorded
+        nprof = 1
         if kind == 'sample':    # profile ONE function evaluation (text pass + null pass) instead of all 62
             with torch.no_grad():
                 x = torch.randn(B, N, 100, device=dev)
                 model.cfg_transformer_with_pred_head(x, torch.zeros_like(x), times=torch.tensor(0.5, device=dev), text=text_dev,
                                                      mask=torch.ones(B, N, dtype=torch.bool, device=dev), cfg_strength=1.0)
         else:
-            for _ in range(nprof):
-                # park the GPU (~40 ms spin kernel) while the host enqueues the step: with the queue full, the event pair around a
-                # GEMM brackets the kernel alone — on a host-bound eager step it would also bracket the wait for the next launch
-                torch.cuda._sleep(80_000_000)
-                step(dev_mel, False)
+            step(dev_mel, False)
         torch.cuda.synchronize()
         ops.gemm = orig_gemm
-        pkg.modules.TWO_STREAM = two_stream
+        gemm_ms = replay_gemms()
+        n_gemm = len(prof['calls'])
+        prof['calls'] = None      # release the step's operands before the graphed step allocates its own pool
+        torch.cuda.empty_cache()
         # -- the same train step through pkg.GraphedTrainStep (forward + backward captured in one CUDA graph, then — N > 1 — ONE flat
         #    all-reduce): identical kernels and work, no per-launch host cost. Falls back to the eager numbers if capture fails.
         if kind == 'train' and not args.no_graph:
@@ -319,17 +345,6 @@ def run_gpu(args):
                     graph_note = f'captured but not faster ({ms_g:.2f} ms)'
             except Exception as e:  # noqa: BLE001 - any capture problem: keep the eager measurement
                 graph_note = f'unavailable: {type(e).__name__}: {str(e)[:160]}'
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof['events'])
-    if os.environ.get('B200_GEMM_BREAKDOWN') and rank == 0:
-        agg = {}
-        for a, b, key in prof['events']:
-            t = agg.setdefault(key, [0, 0.0])
-            t[0] += 1
-            t[1] += a.elapsed_time(b)
-        print('GEMM breakdown over %d profiled steps: (M, N, K, a_mn, b_mn, split, geglu, two_src) count ms TF/s' % nprof, file=sys.stderr)
-        for key, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            print('  %-44s n=%4d  %8.3f ms  %7.1f TF/s' % (str(key), n, ms, 2.0 * key[0] * key[1] * key[2] * n / ms * 1e-9), file=sys.stderr)
-    n_gemm = len(prof['events'])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -357,7 +372,7 @@ def run_gpu(args):
                    'step': (what + ' replayed through e2_tts_pytorch_b200.GraphedTrainStep (one CUDA graph, same kernels)'
                             if step_mode == 'cuda_graph' else what + ', eager launches'),
                    'streams': ('text sub-blocks of layer i+1 overlap the audio sub-blocks of layer i on a second CUDA stream (fork/join inside the step); '
-                               'the roofline pass times the GEMMs serialised on one stream') if pkg.modules.TWO_STREAM else 'one stream',
+                               'the roofline pass replays the step\'s GEMM launches back to back as one CUDA graph') if pkg.modules.TWO_STREAM else 'one stream',
                    **({'eager_ms_per_step': eager_ms} if eager_ms is not None else {}), **({'cuda_graph': graph_note} if graph_note else {})},
         'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': 'mel-frames/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': host_mel.numel() * 4,
                 'd2h_bytes_per_step': d2h_bytes},

@@ -198,8 +198,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BMT / 64; ++i)
-                            load(a_dst + i * (BK * 128), &tmA, &full_bar[stage], arow + i * 64, kb * BK);
+                        for (int i = 0; i < BMT / 64; ++i) {
+                            if (kb < p.kb_a1) load(a_dst + i * (BK * 128), &tmA, &full_bar[stage], arow + i * 64, kb * BK);
+                            else load(a_dst + i * (BK * 128), &tmA2, &full_bar[stage], arow + i * 64, (kb - p.kb_a1) * BK);
+                        }
                     }
                     if constexpr (!B_MN) {
                         load(b_dst, &tmB, &full_bar[stage], kb * BK, brow);
@@ -604,7 +606,6 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
     p.kb_total = (p.K + BK - 1) / BK;
     p.kb_a1 = p.kb_total;
     if (a->A2) {
-        B200_REQUIRE(!a_mn, "gemm: two-source A requires K-major A");
         B200_REQUIRE(a->K1 > 0 && a->K1 < a->K && (a->K1 % BK) == 0, "gemm: K1=%lld must be a multiple of %d inside (0,K)", (long long)a->K1, BK);
         p.kb_a1 = (int)(a->K1 / BK);
     }
@@ -655,7 +656,8 @@ extern "C" int b200_gemm(const b200_gemm_args* a, b200_stream_t stream) {
     else rc = make_map(&tA, a->A, a->M, a->K, a->lda, BK);
     if (rc) return rc;
     if (a->A2) {
-        rc = make_map(&tA2, a->A2, a->K - a->K1, a->M, a->lda2, BM);
+        if (!a_mn) rc = make_map(&tA2, a->A2, a->K - a->K1, a->M, a->lda2, BM);
+        else rc = make_map(&tA2, a->A2, a->M, a->K - a->K1, a->lda2, BK);   // second run of K rows of an MN-major A (same M extent and box)
         if (rc) return rc;
     } else {
         tA2 = tA;

@@ -27,6 +27,12 @@ struct HcP {
     int rows_per_batch, T, D;
     __nv_bfloat16 *branch, *res_out;
     float* beta_out;
+    // fused preceding depth connection (optional): the streams entering this width connection are xres + beta_prev (x) y_prev and are
+    // never materialised in HBM
+    const __nv_bfloat16* y_prev;   // [T, D]
+    const float* beta_prev;        // [T, S]
+    __nv_bfloat16* d_y_prev;       // backward outputs of the fused depth connection
+    float* d_beta_prev;
     // backward
     const __nv_bfloat16 *d_branch, *d_res;
     const float* d_beta;
@@ -128,10 +134,13 @@ __device__ __forceinline__ void stage_params(const HcP& p, float4* sp) {
     __syncthreads();
 }
 
-template <int VPT>
-__device__ __forceinline__ void token_forward(const HcP& p, const float4* __restrict__ sp, const __nv_bfloat16* __restrict__ rsrc, int lane,
+// FUSED: r_s = rsrc_s + bprev[s] * ysrc (the depth connection of the previous sub-block, fp32 — one rounding less than the unfused pair)
+template <int VPT, bool FUSED>
+__device__ __forceinline__ void token_forward(const HcP& p, const float4* __restrict__ sp, const __nv_bfloat16* __restrict__ rsrc,
+                                              const __nv_bfloat16* __restrict__ ysrc, const float4 bprev, int lane,
                                               const LaneConst& lc, TokState<VPT>& st) {   // rsrc: this token's [HS][D] block (HBM or smem copy)
     const int nchunk = p.D >> 3;
+    const float bpv[HS] = {bprev.x, bprev.y, bprev.z, bprev.w};
     f2 ss2[HS], acc[HS][6];
 #pragma unroll
     for (int s = 0; s < HS; ++s) {
@@ -145,6 +154,14 @@ __device__ __forceinline__ void token_forward(const HcP& p, const float4* __rest
         if (c < nchunk) {
 #pragma unroll
             for (int s = 0; s < HS; ++s) unpack8p(*reinterpret_cast<const uint4*>(rsrc + (size_t)s * p.D + c * 8), st.r[s][v]);
+            if constexpr (FUSED) {
+                f2 yv[4];
+                unpack8p(*reinterpret_cast<const uint4*>(ysrc + c * 8), yv);
+#pragma unroll
+                for (int s = 0; s < HS; ++s)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st.r[s][v][j] = ffma2(splat(bpv[s]), yv[j], st.r[s][v][j]);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 q0 = sp[sp_idx(nchunk, c, j, 0)], q1 = sp[sp_idx(nchunk, c, j, 1)], q2 = sp[sp_idx(nchunk, c, j, 2)];
@@ -210,7 +227,7 @@ __device__ __forceinline__ void load_gain8(const float* g, f2 (&o)[4]) {   // 8 
 // PF: every warp prefetches its NEXT token's 4 streams into a private shared-memory double buffer with one bulk (TMA) copy while
 // it works on the current one. Without it the kernel alternates load and math phases with ~8 warps per SM and sits on
 // long-scoreboard stalls (profiles/r1g_ncu_full_hc_width_*).
-template <int VPT, bool PF>
+template <int VPT, bool PF, bool FUSED>
 __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(const HcP p) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float4 sp[];
@@ -219,35 +236,46 @@ __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(c
     const long long warp_global = (long long)blockIdx.x * 8 + warp;
     const long long nwarps = (long long)gridDim.x * 8;
     const int nchunk = p.D >> 3;
-    const uint32_t tok_bytes = (uint32_t)(HS * p.D * 2);
+    // per-warp buffer of one token: [4 streams][D] bf16 (+ FUSED: y [D] bf16, beta_prev 4 x fp32)
+    const uint32_t res_bytes = (uint32_t)(HS * p.D * 2), y_bytes = (uint32_t)(p.D * 2);
+    const uint32_t tok_bytes = res_bytes + (FUSED ? y_bytes + 16u : 0u);
     uint8_t* wbuf = reinterpret_cast<uint8_t*>(sp) + hc_param_smem(p.D) + (size_t)warp * 2 * tok_bytes;
+    auto prefetch = [&](long long tk, int buf) {
+        uint8_t* dst = wbuf + (size_t)buf * tok_bytes;
+        mbar_arrive_expect_tx(&bars[warp][buf], tok_bytes);
+        bulk_load_1d(dst, p.xres + (size_t)tk * HS * p.D, res_bytes, &bars[warp][buf]);
+        if constexpr (FUSED) {
+            bulk_load_1d(dst + res_bytes, p.y_prev + (size_t)tk * p.D, y_bytes, &bars[warp][buf]);
+            bulk_load_1d(dst + res_bytes + y_bytes, p.beta_prev + (size_t)tk * HS, 16u, &bars[warp][buf]);
+        }
+    };
     if (PF && lane == 0) {
         mbar_init(&bars[warp][0], 1);
         mbar_init(&bars[warp][1], 1);
         fence_barrier_init();
-        if (warp_global < p.T) {
-            mbar_arrive_expect_tx(&bars[warp][0], tok_bytes);
-            bulk_load_1d(wbuf, p.xres + (size_t)warp_global * HS * p.D, tok_bytes, &bars[warp][0]);
-        }
+        if (warp_global < p.T) prefetch(warp_global, 0);
     }
     stage_params(p, sp);
     const LaneConst lc = lane_const(p, lane);
     int it = 0;
     for (long long tok = warp_global; tok < p.T; tok += nwarps, ++it) {
         const __nv_bfloat16* rsrc = p.xres + (size_t)tok * HS * p.D;
+        const __nv_bfloat16* ysrc = FUSED ? p.y_prev + (size_t)tok * p.D : nullptr;
+        const float* bsrc = FUSED ? p.beta_prev + (size_t)tok * HS : nullptr;
         if (PF) {
             const int buf = it & 1;
             const long long nxt = tok + nwarps;
             __syncwarp();   // every lane is done reading the other buffer (previous token)
-            if (lane == 0 && nxt < p.T) {
-                mbar_arrive_expect_tx(&bars[warp][buf ^ 1], tok_bytes);
-                bulk_load_1d(wbuf + (size_t)(buf ^ 1) * tok_bytes, p.xres + (size_t)nxt * HS * p.D, tok_bytes, &bars[warp][buf ^ 1]);
-            }
+            if (lane == 0 && nxt < p.T) prefetch(nxt, buf ^ 1);
             mbar_wait(&bars[warp][buf], (uint32_t)(it >> 1) & 1u);
-            rsrc = reinterpret_cast<const __nv_bfloat16*>(wbuf + (size_t)buf * tok_bytes);
+            const uint8_t* src = wbuf + (size_t)buf * tok_bytes;
+            rsrc = reinterpret_cast<const __nv_bfloat16*>(src);
+            ysrc = reinterpret_cast<const __nv_bfloat16*>(src + res_bytes);
+            bsrc = reinterpret_cast<const float*>(src + res_bytes + y_bytes);
         }
+        const float4 bprev = FUSED ? *reinterpret_cast<const float4*>(bsrc) : make_float4(0.f, 0.f, 0.f, 0.f);
         TokState<VPT> st;
-        token_forward<VPT>(p, sp, rsrc, lane, lc, st);
+        token_forward<VPT, FUSED>(p, sp, rsrc, ysrc, bprev, lane, lc, st);
         f2 br[VPT][4];
         f2 bss2 = splat(0.f);
 #pragma unroll
@@ -310,7 +338,11 @@ __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(c
 // the cfg2 grid was 272 blocks on 148 one-block SMs — a second round with 16 % of the machine idle.
 // D <= 256 (VPT == 1) fits 128 registers, so two blocks (16 warps) share an SM: the per-token critical path (two warp-wide 32-value
 // reductions, tanh, ~70 shuffles) is latency-bound, and at D = 256 the backward took 70 % of the D = 512 time for half the bytes.
-template <int VPT, bool PF>
+// FUSED (preceding depth connection folded in): the streams are recomputed as xres + beta_prev (x) y_prev, and the kernel also emits the
+// depth connection's gradients d_y_prev = sum_s beta_prev[s] d_r_s, d_beta_prev[s] = <d_r_s, y_prev> (d_xres is then d(residual') of the
+// previous width connection) plus one extra coefficient row per token, C'[t] = sum_s beta_prev[s] C[(t,s)], so that the parameter GEMM
+// R^T C = xres^T C + y_prev^T C' needs no materialised R.
+template <int VPT, bool PF, bool FUSED>
 __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(const HcP p, __nv_bfloat16* __restrict__ cmat, int tok_per_block) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
     extern __shared__ float4 sp[];
@@ -325,7 +357,8 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
     const int n0 = blockIdx.x * tok_per_block;
     const int n1 = min(p.rows_per_batch, n0 + tok_per_block);
     // PF: per-warp double buffer {r [HS][D], d_res [HS][D], d_branch [D]} filled by bulk (TMA) copies one token ahead
-    const uint32_t tok_bytes = (uint32_t)(HS * D * 2), br_bytes = (uint32_t)(D * 2), buf_bytes = 2 * tok_bytes + br_bytes;
+    const uint32_t tok_bytes = (uint32_t)(HS * D * 2), br_bytes = (uint32_t)(D * 2);
+    const uint32_t buf_bytes = 2 * tok_bytes + br_bytes + (FUSED ? br_bytes + 16u : 0u);   // FUSED: + y_prev [D], beta_prev [4] fp32
     uint8_t* wbuf = reinterpret_cast<uint8_t*>(sp) + hc_param_smem(D) + (size_t)warp * 2 * buf_bytes;
     auto prefetch = [&](int n, int buf) {
         const size_t tk = (size_t)b * p.rows_per_batch + n;
@@ -334,6 +367,10 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
         bulk_load_1d(dst, p.xres + tk * HS * D, tok_bytes, &bars[warp][buf]);
         bulk_load_1d(dst + tok_bytes, p.d_res + tk * HS * D, tok_bytes, &bars[warp][buf]);
         bulk_load_1d(dst + 2 * tok_bytes, p.d_branch + tk * D, br_bytes, &bars[warp][buf]);
+        if constexpr (FUSED) {
+            bulk_load_1d(dst + 2 * tok_bytes + br_bytes, p.y_prev + tk * D, br_bytes, &bars[warp][buf]);
+            bulk_load_1d(dst + 2 * tok_bytes + 2 * br_bytes, p.beta_prev + tk * HS, 16u, &bars[warp][buf]);
+        }
     };
     if (PF && lane == 0) {
         mbar_init(&bars[warp][0], 1);
@@ -360,6 +397,8 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
         const __nv_bfloat16* rsrc = p.xres + (size_t)tok * HS * D;
         const __nv_bfloat16* drsrc = p.d_res + (size_t)tok * HS * D;
         const __nv_bfloat16* dbsrc = p.d_branch + (size_t)tok * D;
+        const __nv_bfloat16* ysrc = FUSED ? p.y_prev + (size_t)tok * D : nullptr;
+        const float* bsrc = FUSED ? p.beta_prev + (size_t)tok * HS : nullptr;
         if (PF) {
             const int buf = it & 1;
             __syncwarp();   // every lane is done reading the other buffer (previous token)
@@ -369,9 +408,12 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
             rsrc = reinterpret_cast<const __nv_bfloat16*>(src);
             drsrc = reinterpret_cast<const __nv_bfloat16*>(src + tok_bytes);
             dbsrc = reinterpret_cast<const __nv_bfloat16*>(src + 2 * tok_bytes);
+            ysrc = reinterpret_cast<const __nv_bfloat16*>(src + 2 * tok_bytes + br_bytes);
+            bsrc = reinterpret_cast<const float*>(src + 2 * tok_bytes + 2 * br_bytes);
         }
+        const float4 bprev = FUSED ? *reinterpret_cast<const float4*>(bsrc) : make_float4(0.f, 0.f, 0.f, 0.f);
         TokState<VPT> st;
-        token_forward<VPT>(p, sp, rsrc, lane, lc, st);
+        token_forward<VPT, FUSED>(p, sp, rsrc, ysrc, bprev, lane, lc, st);
 
         // ---- branch (mix_0), its norm, and d(mix_0)
         f2 dm0[VPT][4];
@@ -491,6 +533,22 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
                 nk3[s] = -(st.inv[s] * st.inv[s] * st.inv[s] * invD * Rs);
             }
         }
+        const float bpv[HS] = {bprev.x, bprev.y, bprev.z, bprev.w};
+        if constexpr (FUSED) {
+            // coefficient row of the y_prev operand of the parameter GEMM: C'[tok][k] = sum_s beta_prev[s] * C[(tok, s)][k]  (k < 6, else 0)
+            if (lane < 8) {
+                float cp = 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float ck = bpv[0] * cw[0][k] + bpv[1] * cw[1][k] + bpv[2] * cw[2][k] + bpv[3] * cw[3][k];
+                    cp = (lane == k) ? ck : cp;
+                }
+                cmat[((size_t)p.T * HS + (size_t)tok) * 8 + lane] = __float2bfloat16(cp);
+            }
+        }
+        f2 dbp[HS];   // FUSED: <d_r_s, y_prev> partial sums of this lane
+#pragma unroll
+        for (int s = 0; s < HS; ++s) dbp[s] = splat(0.f);
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int c = lane + 32 * v;
@@ -510,7 +568,26 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
 #pragma unroll
                 for (int s = 0; s < HS; ++s)
                     *reinterpret_cast<uint4*>(p.d_xres + ((size_t)tok * HS + s) * D + c * 8) = pack8p(dr[s][v]);
+                if constexpr (FUSED) {
+                    f2 yv[4], dy[4];
+                    unpack8p(*reinterpret_cast<const uint4*>(ysrc + c * 8), yv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        dy[j] = fmul2(splat(bpv[0]), dr[0][v][j]);
+                        dbp[0] = ffma2(dr[0][v][j], yv[j], dbp[0]);
+#pragma unroll
+                        for (int s = 1; s < HS; ++s) {
+                            dy[j] = ffma2(splat(bpv[s]), dr[s][v][j], dy[j]);
+                            dbp[s] = ffma2(dr[s][v][j], yv[j], dbp[s]);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(p.d_y_prev + (size_t)tok * D + c * 8) = pack8p(dy);
+                }
             }
+        }
+        if constexpr (FUSED) {
+            float d0 = warp_sum(hsum(dbp[0])), d1 = warp_sum(hsum(dbp[1])), d2 = warp_sum(hsum(dbp[2])), d3 = warp_sum(hsum(dbp[3]));
+            if (lane == 0) *reinterpret_cast<float4*>(p.d_beta_prev + (size_t)tok * HS) = make_float4(d0, d1, d2, d3);
         }
     }
     if (p.norm_mode) {
@@ -658,6 +735,12 @@ static int fill_hc(HcP& p, const b200_hc_width_args* a) {
     p.gamma = a->norm_gamma; p.afn = a->dynamic_alpha_fn; p.ascale = a->dynamic_alpha_scale; p.salpha = a->static_alpha;
     p.bfn = a->dynamic_beta_fn; p.bscale = a->dynamic_beta_scale; p.sbeta = a->static_beta;
     p.norm_mode = a->norm_mode; p.ng = a->norm_gain; p.rows_per_batch = a->rows_per_batch; p.T = a->T; p.D = a->D;
+    if (a->y_prev) {
+        B200_REQUIRE(a->beta_prev, "hyper-connections: fused depth connection needs beta_prev next to y_prev");
+        B200_REQUIRE((reinterpret_cast<uintptr_t>(a->y_prev) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->beta_prev) & 15) == 0,
+                     "hyper-connections: y_prev / beta_prev must be 16-byte aligned");
+        p.y_prev = (const __nv_bfloat16*)a->y_prev; p.beta_prev = a->beta_prev;
+    }
     return 0;
 }
 
@@ -665,49 +748,41 @@ static int fill_hc(HcP& p, const b200_hc_width_args* a) {
 
 using namespace b200;
 
+template <bool FUSED>
+static int launch_hc_fwd(const HcP& p, const b200_hc_width_args* a, cudaStream_t st) {
+    const size_t smem_par = hc_param_smem(a->D);
+    if (a->D <= 512 && hc_prefetch_enabled()) {
+        // prefetching variant: 2 blocks per SM, each warp owns a double buffer of one token {4 streams (+ y_prev, beta_prev)}
+        const size_t tok = (size_t)HS * a->D * 2 + (FUSED ? (size_t)a->D * 2 + 16 : 0);
+        const size_t smem = smem_par + 8 * 2 * tok;
+        const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 2);
+        if (a->D <= 256) {
+            if (int rc = set_smem<hc_width_fwd_kernel<1, true, FUSED>>(smem)) return rc;
+            B200_LAUNCH((hc_width_fwd_kernel<1, true, FUSED>), grid, 256, smem, st, p);
+        } else {
+            if (int rc = set_smem<hc_width_fwd_kernel<2, true, FUSED>>(smem)) return rc;
+            B200_LAUNCH((hc_width_fwd_kernel<2, true, FUSED>), grid, 256, smem, st, p);
+        }
+        return check_launch("hc_width_fwd_kernel");
+    }
+    const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 8);
+    if (a->D <= 256) B200_LAUNCH((hc_width_fwd_kernel<1, false, FUSED>), grid, 256, smem_par, st, p);
+    else if (a->D <= 512) B200_LAUNCH((hc_width_fwd_kernel<2, false, FUSED>), grid, 256, smem_par, st, p);
+    else B200_LAUNCH((hc_width_fwd_kernel<4, false, FUSED>), grid, 256, smem_par, st, p);
+    return check_launch("hc_width_fwd_kernel");
+}
+
 extern "C" int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     B200_REQUIRE(a && a->xres && a->branch && a->res_out && a->beta_out, "hc_width_fwd: null pointer");
     HcP p{};
     if (fill_hc(p, a)) return -1;
     p.branch = (__nv_bfloat16*)a->branch; p.res_out = (__nv_bfloat16*)a->res_out; p.beta_out = a->beta_out;
-    const size_t smem_par = hc_param_smem(a->D);
-    if (a->D <= 512 && hc_prefetch_enabled()) {
-        // prefetching variant: 2 blocks per SM, each warp owns a 2 x (HS*D*2)-byte token double buffer
-        const size_t smem = smem_par + (size_t)8 * 2 * HS * a->D * 2;
-        const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 2);
-        if (a->D <= 256) {
-            if (int rc = set_smem<hc_width_fwd_kernel<1, true>>(smem)) return rc;
-            B200_LAUNCH((hc_width_fwd_kernel<1, true>), grid, 256, smem, st, p);
-        } else {
-            if (int rc = set_smem<hc_width_fwd_kernel<2, true>>(smem)) return rc;
-            B200_LAUNCH((hc_width_fwd_kernel<2, true>), grid, 256, smem, st, p);
-        }
-        return check_launch("hc_width_fwd_kernel");
-    }
-    const int grid = (int)min((long long)(a->T + 7) / 8, (long long)num_sms() * 8);
-    if (a->D <= 256) B200_LAUNCH((hc_width_fwd_kernel<1, false>), grid, 256, smem_par, st, p);
-    else if (a->D <= 512) B200_LAUNCH((hc_width_fwd_kernel<2, false>), grid, 256, smem_par, st, p);
-    else B200_LAUNCH((hc_width_fwd_kernel<4, false>), grid, 256, smem_par, st, p);
-    return check_launch("hc_width_fwd_kernel");
+    return a->y_prev ? launch_hc_fwd<true>(p, a, st) : launch_hc_fwd<false>(p, a, st);
 }
 
-extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stream) {
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    B200_REQUIRE(a && a->xres && a->d_branch && a->d_res && a->d_xres && a->g_norm_gamma && a->g_dynamic_alpha_fn && a->g_dynamic_alpha_scale &&
-                 a->g_static_alpha && a->g_dynamic_beta_fn && a->g_dynamic_beta_scale && a->g_static_beta, "hc_width_bwd: null pointer");
-    HcP p{};
-    if (fill_hc(p, a)) return -1;
-    B200_REQUIRE(a->norm_mode == 0 || a->g_norm_gain, "hc_width_bwd: missing gain gradient buffer");
-    p.d_branch = (const __nv_bfloat16*)a->d_branch; p.d_res = (const __nv_bfloat16*)a->d_res; p.d_beta = a->d_beta;
-    p.d_xres = (__nv_bfloat16*)a->d_xres;
-    p.g_gamma = a->g_norm_gamma; p.g_afn = a->g_dynamic_alpha_fn; p.g_ascale = a->g_dynamic_alpha_scale; p.g_salpha = a->g_static_alpha;
-    p.g_bfn = a->g_dynamic_beta_fn; p.g_bscale = a->g_dynamic_beta_scale; p.g_sbeta = a->g_static_beta; p.g_ng = a->g_norm_gain;
-    B200_REQUIRE(a->ws_records, "hc_width_bwd: missing workspace (T * 40 floats)");
-    // workspace: coefficient matrix C bf16 [T*S, 8] (64 B per token), then G fp32 [D, 8]
-    __nv_bfloat16* cmat = reinterpret_cast<__nv_bfloat16*>(a->ws_records);
-    float* G = a->ws_records + (size_t)a->T * 16;
-    B200_REQUIRE((size_t)a->T * 24 >= (size_t)a->D * 8, "hc_width_bwd: workspace too small for D=%d at T=%lld", a->D, (long long)a->T);
+template <bool FUSED>
+static int launch_hc_bwd(const HcP& p, const b200_hc_width_args* a, __nv_bfloat16* cmat, cudaStream_t st) {
     // one wave: as many blocks per batch element as fit the co-resident slots (8 warps x >= 1 token each), tokens rounded up to the warp count
     const int nbatch = a->T / a->rows_per_batch;
     const int slots = num_sms() * (a->D <= 256 ? 2 : 1);
@@ -718,23 +793,51 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     dim3 grid((a->rows_per_batch + tpb - 1) / tpb, nbatch);
     const size_t smem_par = hc_param_smem(a->D);
     if (a->D <= 512 && hc_prefetch_enabled()) {
-        const size_t smem = smem_par + (size_t)8 * 2 * (2 * HS + 1) * a->D * 2;   // + per-warp {r, d_res, d_branch} double buffers
+        // + per-warp {r, d_res, d_branch (, y_prev, beta_prev)} double buffers
+        const size_t smem = smem_par + (size_t)8 * 2 * ((2 * HS + 1 + (FUSED ? 1 : 0)) * a->D * 2 + (FUSED ? 16 : 0));
         if (a->D <= 256) {
-            if (int rc = set_smem<hc_width_bwd_kernel<1, true>>(smem)) return rc;
-            B200_LAUNCH((hc_width_bwd_kernel<1, true>), grid, 256, smem, st, p, cmat, tpb);
+            if (int rc = set_smem<hc_width_bwd_kernel<1, true, FUSED>>(smem)) return rc;
+            B200_LAUNCH((hc_width_bwd_kernel<1, true, FUSED>), grid, 256, smem, st, p, cmat, tpb);
         } else {
-            if (int rc = set_smem<hc_width_bwd_kernel<2, true>>(smem)) return rc;
-            B200_LAUNCH((hc_width_bwd_kernel<2, true>), grid, 256, smem, st, p, cmat, tpb);
+            if (int rc = set_smem<hc_width_bwd_kernel<2, true, FUSED>>(smem)) return rc;
+            B200_LAUNCH((hc_width_bwd_kernel<2, true, FUSED>), grid, 256, smem, st, p, cmat, tpb);
         }
-    } else if (a->D <= 256) B200_LAUNCH((hc_width_bwd_kernel<1, false>), grid, 256, smem_par, st, p, cmat, tpb);
-    else if (a->D <= 512) B200_LAUNCH((hc_width_bwd_kernel<2, false>), grid, 256, smem_par, st, p, cmat, tpb);
-    else B200_LAUNCH((hc_width_bwd_kernel<4, false>), grid, 256, smem_par, st, p, cmat, tpb);
-    if (int rc = check_launch("hc_width_bwd_kernel")) return rc;
-    // G = R^T C on the tensor cores: A = residual streams [T*S, D] read MN-major, B = C [T*S, 8] MN-major, split-K over the tokens
+    } else if (a->D <= 256) B200_LAUNCH((hc_width_bwd_kernel<1, false, FUSED>), grid, 256, smem_par, st, p, cmat, tpb);
+    else if (a->D <= 512) B200_LAUNCH((hc_width_bwd_kernel<2, false, FUSED>), grid, 256, smem_par, st, p, cmat, tpb);
+    else B200_LAUNCH((hc_width_bwd_kernel<4, false, FUSED>), grid, 256, smem_par, st, p, cmat, tpb);
+    return check_launch("hc_width_bwd_kernel");
+}
+
+extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    B200_REQUIRE(a && a->xres && a->d_branch && a->d_res && a->d_xres && a->g_norm_gamma && a->g_dynamic_alpha_fn && a->g_dynamic_alpha_scale &&
+                 a->g_static_alpha && a->g_dynamic_beta_fn && a->g_dynamic_beta_scale && a->g_static_beta, "hc_width_bwd: null pointer");
+    HcP p{};
+    if (fill_hc(p, a)) return -1;
+    B200_REQUIRE(a->norm_mode == 0 || a->g_norm_gain, "hc_width_bwd: missing gain gradient buffer");
+    const bool fused = a->y_prev != nullptr;
+    if (fused) {
+        B200_REQUIRE(a->d_y_prev && a->d_beta_prev, "hc_width_bwd: fused depth connection needs d_y_prev and d_beta_prev");
+        B200_REQUIRE(((int64_t)a->T * HS) % 64 == 0, "hc_width_bwd: fused depth connection needs T * S to be a multiple of 64 (T=%lld)", (long long)a->T);
+        p.d_y_prev = (__nv_bfloat16*)a->d_y_prev; p.d_beta_prev = a->d_beta_prev;
+    }
+    p.d_branch = (const __nv_bfloat16*)a->d_branch; p.d_res = (const __nv_bfloat16*)a->d_res; p.d_beta = a->d_beta;
+    p.d_xres = (__nv_bfloat16*)a->d_xres;
+    p.g_gamma = a->g_norm_gamma; p.g_afn = a->g_dynamic_alpha_fn; p.g_ascale = a->g_dynamic_alpha_scale; p.g_salpha = a->g_static_alpha;
+    p.g_bfn = a->g_dynamic_beta_fn; p.g_bscale = a->g_dynamic_beta_scale; p.g_sbeta = a->g_static_beta; p.g_ng = a->g_norm_gain;
+    B200_REQUIRE(a->ws_records, "hc_width_bwd: missing workspace (T * 40 floats)");
+    // workspace: coefficient matrix C bf16 [T*S (+ T fused rows), 8] (80 B per token), then G fp32 [D, 8]
+    __nv_bfloat16* cmat = reinterpret_cast<__nv_bfloat16*>(a->ws_records);
+    float* G = a->ws_records + (size_t)a->T * 20;
+    B200_REQUIRE((size_t)a->T * 20 >= (size_t)a->D * 8, "hc_width_bwd: workspace too small for D=%d at T=%lld", a->D, (long long)a->T);
+    if (int rc = fused ? launch_hc_bwd<true>(p, a, cmat, st) : launch_hc_bwd<false>(p, a, cmat, st)) return rc;
+    // G = R^T C on the tensor cores: A = residual streams [T*S, D] read MN-major (fused: followed by y_prev [T, D] against the C' rows),
+    // B = C [T*S (+ T), 8] MN-major, split-K over the tokens
     b200_gemm_args g = {};
     g.A = a->xres; g.lda = a->D; g.a_mn_major = 1;
     g.B = cmat; g.ldb = 8; g.b_mn_major = 1;
     g.M = a->D; g.N = 8; g.K = (int64_t)a->T * HS;
+    if (fused) { g.A2 = a->y_prev; g.lda2 = a->D; g.K1 = g.K; g.K += a->T; }
     g.D = G; g.ldd = 8; g.d_fp32 = 1;
     const int tiles = (a->D + 255) / 256;
     g.split_k = num_sms() / tiles > 1 ? num_sms() / tiles : 2;   // >= 2: the split-K path zeroes and accumulates G

@@ -29,6 +29,8 @@ SOFTCLAMP = 50.0  # x-transformers logit_softclamp_value default (A.4)
 # B200_TWO_STREAM=0 serialises them on the current stream (developer A/B switch)
 import os as _os
 TWO_STREAM = _os.environ.get('B200_TWO_STREAM', '1') != '0'
+# depth connection of a sub-block fused into the next sub-block's width connection (ops.HcDepthWidth); B200_FUSE_HC=0: separate kernels
+FUSE_HC = _os.environ.get('B200_FUSE_HC', '1') != '0'
 _SIDE_STREAMS = {}
 
 
@@ -490,26 +492,42 @@ class Transformer(Module):
             nseed[0] = (nseed[0] * 6364136223846793005 + 1442695040888963407) & 0x7FFFFFFFFFFFFFFF
             return nseed[0]
 
+        # Hyper-connection plumbing of one stream: a sub-block returns its depth connection PENDING — (residual', branch_out, beta) — and
+        # the next sub-block's width connection consumes it in one fused kernel (ops.HcDepthWidth); `close` materialises the streams
+        # where something else reads them (cross-conditioning, skip path, final norm).
+        fuse = FUSE_HC and ops.hc_can_fuse(xs.shape[0], xs.shape[1])
+
+        def width(res, hcm, gain, mode):
+            if isinstance(res, tuple):
+                return ops.HcDepthWidth.apply(*res, *hcm.params(), gain, mode, Np)
+            return ops.HcWidth.apply(res, *hcm.params(), gain, mode, Np)
+
+        def depth(rest, y, beta):
+            return (rest, y, beta) if fuse else ops.HcDepth.apply(rest, y, beta)
+
+        def close(res):
+            return ops.HcDepth.apply(*res) if isinstance(res, tuple) else res
+
         def sub_conv(res, hcm, conv):
-            br, rest, beta = ops.HcWidth.apply(res, *hcm.params(), None, 0, Np)
+            br, rest, beta = width(res, hcm, None, 0)
             y = ops.DwConv.apply(br, conv.dw_conv1d[0].weight, conv.dw_conv1d[0].bias, mask_u8, B, Np)
-            return ops.HcDepth.apply(rest, y, beta)
+            return depth(rest, y, beta)
 
         def sub_attn(res, hcm, gain, mode, attn, pk, vf, colscale):
-            br, rest, beta = ops.HcWidth.apply(res, *hcm.params(), gain, mode, Np)
+            br, rest, beta = width(res, hcm, gain, mode)
             mix = attn.to_value_residual_mix
             og, v = ops.Attention.apply(br, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_v_head_gate.weight,
                                         attn.to_v_head_gate.bias, mix[0].weight if mix is not None else None,
                                         mix[0].bias if mix is not None else None, vf if mix is not None else None,
                                         pk['qkv'], cs, sn, mask_u8, B, Np, H, p_drop, next_seed(), SOFTCLAMP, self._seed_dev)
             y = ops.OutProj.apply(og, attn.to_out.weight, pk['out'], colscale, mask_u8, B, Np)
-            return ops.HcDepth.apply(rest, y, beta), (v if vf is None else vf)
+            return depth(rest, y, beta), (v if vf is None else vf)
 
         def sub_ff(res, hcm, gain, mode, ff, pk, colscale):
-            br, rest, beta = ops.HcWidth.apply(res, *hcm.params(), gain, mode, Np)
+            br, rest, beta = width(res, hcm, gain, mode)
             y = ops.FeedForward.apply(br, ff.ff[0].proj.weight, ff.ff[0].proj.bias, ff.ff[2].weight, ff.ff[2].bias,
                                       pk['w1'], pk['b1'], pk['w2'], colscale, B, Np, p_drop, next_seed(), self._seed_dev)
-            return ops.HcDepth.apply(rest, y, beta)
+            return close(depth(rest, y, beta))
 
         def text_block(i, ts, tvf):  # the three text sub-blocks of layer i (:853-882)
             text, thc, pk = self.layers[i][1], self.hyper_conns[i][1], P[i]['t']

@@ -109,51 +109,99 @@ def rotary_table(Np, device):
 
 
 # ---------------------------------------------------------------------------------------------------- hyper-connections
+def _hc_width_fwd(xres, y_prev, beta_prev, params, norm_gain, norm_mode, rows_per_batch):
+    gamma, afn, ascale, salpha, bfn, bscale, sbeta = params
+    T, S, D = xres.shape
+    branch = torch.empty((T, D), device=xres.device, dtype=BF16)
+    res = torch.empty_like(xres)
+    beta = torch.empty((T, S), device=xres.device, dtype=F32)
+    a = lib.make_args('b200_hc_width_args', xres=xres, norm_gamma=gamma, dynamic_alpha_fn=afn, dynamic_alpha_scale=ascale,
+                      static_alpha=salpha, dynamic_beta_fn=bfn, dynamic_beta_scale=bscale, static_beta=sbeta,
+                      norm_mode=norm_mode, norm_gain=norm_gain, rows_per_batch=rows_per_batch, T=T, D=D, num_streams=S,
+                      branch=branch, res_out=res, beta_out=beta, y_prev=y_prev, beta_prev=beta_prev)
+    lib.call('b200_hc_width_fwd', a, _stream())
+    return branch, res, beta
+
+
+def _hc_width_bwd(xres, y_prev, beta_prev, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta):
+    gamma, afn, ascale, salpha, bfn, bscale, sbeta = params
+    T, S, D = xres.shape
+    dev = xres.device
+    d_xres = torch.empty_like(xres)
+    d_y = torch.empty_like(y_prev) if y_prev is not None else None
+    d_bp = torch.empty_like(beta_prev) if y_prev is not None else None
+    if d_branch is None:
+        d_branch = torch.zeros((T, D), device=dev, dtype=BF16)
+    if d_res is None:
+        d_res = torch.zeros_like(xres)
+    # one zero-filled fp32 slab for all parameter-gradient accumulators
+    n_gain = 0 if norm_mode == 0 else norm_gain.numel()
+    sizes = [D, D * (S + 1), 1, S * (S + 1), D, 1, S, n_gain]
+    slab = _zeros(sum(sizes), dev)
+    parts, o = [], 0
+    for n in sizes:
+        parts.append(slab[o:o + n])
+        o += n
+    g_gamma, g_afn, g_as, g_sal, g_bfn, g_bs, g_sbe, g_gain = parts
+    a = lib.make_args('b200_hc_width_args', xres=xres, norm_gamma=gamma, dynamic_alpha_fn=afn, dynamic_alpha_scale=ascale,
+                      static_alpha=salpha, dynamic_beta_fn=bfn, dynamic_beta_scale=bscale, static_beta=sbeta,
+                      norm_mode=norm_mode, norm_gain=norm_gain, rows_per_batch=rpb, T=T, D=D, num_streams=S,
+                      d_branch=_c(d_branch), d_res=_c(d_res), d_beta=_c(d_beta), d_xres=d_xres,
+                      g_norm_gamma=g_gamma, g_dynamic_alpha_fn=g_afn, g_dynamic_alpha_scale=g_as, g_static_alpha=g_sal,
+                      g_dynamic_beta_fn=g_bfn, g_dynamic_beta_scale=g_bs, g_static_beta=g_sbe,
+                      g_norm_gain=g_gain if norm_mode else None, ws_records=torch.empty((T, 40), device=dev, dtype=F32),
+                      y_prev=y_prev, beta_prev=beta_prev, d_y_prev=d_y, d_beta_prev=d_bp)
+    lib.call('b200_hc_width_bwd', a, _stream())
+    pg = (g_gamma, g_afn.view(D, S + 1), g_as.view(()), g_sal.view(S, S + 1), g_bfn, g_bs.view(()), g_sbe,
+          g_gain.view_as(norm_gain) if norm_mode else None)
+    return d_xres, d_y, d_bp, pg
+
+
 class HcWidth(Function):
     """HyperConnections width connection + consumer (Adaptive)RMSNorm (A.5, A.1; e2_tts.py:870-882, 900-939)."""
 
     @staticmethod
     def forward(ctx, xres, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain, norm_mode, rows_per_batch):
-        T, S, D = xres.shape
-        branch = torch.empty((T, D), device=xres.device, dtype=BF16)
-        res = torch.empty_like(xres)
-        beta = torch.empty((T, S), device=xres.device, dtype=F32)
-        a = lib.make_args('b200_hc_width_args', xres=xres, norm_gamma=gamma, dynamic_alpha_fn=afn, dynamic_alpha_scale=ascale,
-                          static_alpha=salpha, dynamic_beta_fn=bfn, dynamic_beta_scale=bscale, static_beta=sbeta,
-                          norm_mode=norm_mode, norm_gain=norm_gain, rows_per_batch=rows_per_batch, T=T, D=D, num_streams=S,
-                          branch=branch, res_out=res, beta_out=beta)
-        lib.call('b200_hc_width_fwd', a, _stream())
+        out = _hc_width_fwd(xres, None, None, (gamma, afn, ascale, salpha, bfn, bscale, sbeta), norm_gain, norm_mode, rows_per_batch)
         ctx.save_for_backward(xres, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain)
         ctx.meta = (norm_mode, rows_per_batch)
-        return branch, res, beta
+        return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_branch, d_res, d_beta):
-        xres, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain = ctx.saved_tensors
+        xres, *params, norm_gain = ctx.saved_tensors
         norm_mode, rpb = ctx.meta
-        T, S, D = xres.shape
-        dev = xres.device
-        d_xres = torch.empty_like(xres)
-        # one zero-filled fp32 slab for all parameter-gradient accumulators
-        n_gain = 0 if norm_mode == 0 else norm_gain.numel()
-        sizes = [D, D * (S + 1), 1, S * (S + 1), D, 1, S, n_gain]
-        slab = _zeros(sum(sizes), dev)
-        parts, o = [], 0
-        for n in sizes:
-            parts.append(slab[o:o + n])
-            o += n
-        g_gamma, g_afn, g_as, g_sal, g_bfn, g_bs, g_sbe, g_gain = parts
-        a = lib.make_args('b200_hc_width_args', xres=xres, norm_gamma=gamma, dynamic_alpha_fn=afn, dynamic_alpha_scale=ascale,
-                          static_alpha=salpha, dynamic_beta_fn=bfn, dynamic_beta_scale=bscale, static_beta=sbeta,
-                          norm_mode=norm_mode, norm_gain=norm_gain, rows_per_batch=rpb, T=T, D=D, num_streams=S,
-                          d_branch=_c(d_branch), d_res=_c(d_res), d_beta=_c(d_beta), d_xres=d_xres,
-                          g_norm_gamma=g_gamma, g_dynamic_alpha_fn=g_afn, g_dynamic_alpha_scale=g_as, g_static_alpha=g_sal,
-                          g_dynamic_beta_fn=g_bfn, g_dynamic_beta_scale=g_bs, g_static_beta=g_sbe,
-                          g_norm_gain=g_gain if norm_mode else None, ws_records=torch.empty((T, 40), device=dev, dtype=F32))
-        lib.call('b200_hc_width_bwd', a, _stream())
-        return (d_xres, g_gamma, g_afn.view(D, S + 1), g_as.view(()), g_sal.view(S, S + 1), g_bfn, g_bs.view(()), g_sbe,
-                g_gain.view_as(norm_gain) if norm_mode else None, None, None)
+        d_xres, _, _, pg = _hc_width_bwd(xres, None, None, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta)
+        return (d_xres, *pg, None, None)
+
+
+def hc_can_fuse(T, S):
+    """The fused depth -> width backward feeds the parameter GEMM with two K runs (residual' rows, then branch rows): the first run must
+    end on a 64-row k-block boundary (include/b200_e2tts.h, b200_hc_width_args)."""
+    return (T * S) % 64 == 0
+
+
+class HcDepthWidth(Function):
+    """Depth connection of sub-block k (residual' + beta * branch_out, A.5 add_residual) FUSED into the width connection of sub-block
+    k+1 (e2_tts.py:870-882, 900-939 apply them back to back): the updated streams are formed in registers and never written to HBM
+    (forward: one [T,S,D] write + read less per sub-block; backward: the depth gradients come out of the width backward kernel)."""
+
+    @staticmethod
+    def forward(ctx, rest_prev, y_prev, beta_prev, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain, norm_mode, rows_per_batch):
+        y_prev, beta_prev = _c(y_prev), _c(beta_prev)
+        out = _hc_width_fwd(rest_prev, y_prev, beta_prev, (gamma, afn, ascale, salpha, bfn, bscale, sbeta), norm_gain, norm_mode, rows_per_batch)
+        ctx.save_for_backward(rest_prev, y_prev, beta_prev, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain)
+        ctx.meta = (norm_mode, rows_per_batch)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_branch, d_res, d_beta):
+        rest_prev, y_prev, beta_prev, *params, norm_gain = ctx.saved_tensors
+        norm_mode, rpb = ctx.meta
+        d_rest, d_y, d_bp, pg = _hc_width_bwd(rest_prev, y_prev, beta_prev, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta)
+        return (d_rest, d_y, d_bp, *pg, None, None)
 
 
 class HcDepth(Function):
@@ -303,6 +351,7 @@ class Attention(Function):
 
     @staticmethod
     def forward(ctx, xn, wq, wk, wv, wg, bg, wm, bm, v_first, wpack, cs, sn, mask, B, Np, H, dropout_p, seed, softclamp, seed_dev):
+        ctx.set_materialize_grads(False)   # only the first layer's values are consumed downstream: no zero-filled d_v for the others
         T, Din = xn.shape
         I = H * 64
         dev = xn.device
@@ -330,6 +379,8 @@ class Attention(Function):
     @once_differentiable
     def backward(ctx, d_og, d_v_extra):
         xn, qkvg, gate, v_first, wpack, cs, sn, bg, bm, q, k, v, o, lse, mask = ctx.saved_tensors
+        if d_og is None:   # (only the values were used: not a case the model produces, kept for completeness)
+            d_og = torch.zeros((xn.shape[0], ctx.meta[2] * 64), device=xn.device, dtype=BF16)
         B, Np, H, ncat, ld, has_mix, dropout_p, seed, softclamp, seed_dev = ctx.meta
         T, Din = xn.shape
         I = H * 64
@@ -439,6 +490,7 @@ class CrossCondition(Function):
 
     @staticmethod
     def forward(ctx, xs, ts, w_ta, w_at, wstack):
+        ctx.set_materialize_grads(False)   # the text stream's last output has no consumer: its gradient stays None instead of a zero fill
         T, S, D = xs.shape
         Dt = ts.shape[-1]
         R = T * S
@@ -460,7 +512,11 @@ class CrossCondition(Function):
         Dt = ts.shape[-1]
         R, Kc = T * S, D + Dt
         x2, t2 = xs.view(R, D), ts.view(R, Dt)
-        dxo2, dto2 = _c(dxo).view(R, D), _c(dto).view(R, Dt)
+        if dxo is None:
+            dxo = torch.zeros_like(xs)
+        if dto is None and ctx.has_at:
+            dto = torch.zeros_like(ts)
+        dxo2, dto2 = _c(dxo).view(R, D), (_c(dto).view(R, Dt) if dto is not None else None)
         dWta = torch.empty((D, Kc), device=xs.device, dtype=F32)
         grad_weight(dxo2, x2, R, D, D, out=dWta, ldd=Kc)
         grad_weight(dxo2, t2, R, D, Dt, out=dWta[:, D:], ldd=Kc)
@@ -472,7 +528,7 @@ class CrossCondition(Function):
             grad_weight(dto2, t2, R, Dt, Dt, out=dWat[:, D:], ldd=Kc)
         else:
             dx = gemm(dxo2, wstack, R, D, D, lda=D, ldb=Kc, b_mn=True, resid=dxo2, ldr=D)
-            dt = gemm(dxo2, wstack[:, D:], R, Dt, D, lda=D, ldb=Kc, b_mn=True, resid=dto2, ldr=Dt)
+            dt = gemm(dxo2, wstack[:, D:], R, Dt, D, lda=D, ldb=Kc, b_mn=True, resid=dto2, ldr=Dt if dto2 is not None else 0)
             dWat = None
         return dx.view(T, S, D), dt.view(T, S, Dt), dWta, dWat, None
 

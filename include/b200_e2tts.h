@@ -39,7 +39,7 @@ uint64_t b200_launch_count(void);
  * :1296, and all of their backward contractions (dX = dY*W, dW = dY^T*X).
  *
  * A: bf16. a_mn_major=0: A stored [M,K] (lda = row pitch in elements); 1: A stored [K,M] (M contiguous).
- *    Optional second K source (a_mn_major=0 only): k in [0,K1) from A, k in [K1,K) from A2 — the concat
+ *    Optional second K source: k in [0,K1) from A, k in [K1,K) from A2 (same major-ness as A) — the concat
  *    of skip / cross-condition inputs is never materialised. K1 % 64 == 0.
  * B: bf16. b_mn_major=0: stored [N,K] (an nn.Linear weight); 1: stored [K,N].
  * Row pitches must be multiples of 8 elements (16 B, TMA requirement); M, N, K otherwise arbitrary.
@@ -130,6 +130,11 @@ int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t stream);  /*
  * width bwd : d_branch [T,D], d_res [T,S,D], d_beta [T,S] -> d_xres [T,S,D]; parameter gradients are ADDED
  *   (fp32 atomics) into the g_* buffers, which the caller zero-initialises: g_norm_gain is [D] (mode 1) or
  *   [T/rows_per_batch, D] (mode 2).
+ * Fused depth connection (optional, y_prev != NULL): the streams entering the width connection are
+ *   xres + beta_prev (x) y_prev — the depth connection `residual' + beta * branch_out` of the PREVIOUS sub-block
+ *   (A.5 add_residual) — and are never written to HBM: xres is then that sub-block's residual' [T,S,D], y_prev its branch
+ *   output bf16 [T,D], beta_prev its beta fp32 [T,S]. bwd additionally returns d_y_prev bf16 [T,D], d_beta_prev fp32 [T,S]
+ *   (d_xres is d residual'); it needs T*S % 64 == 0. Otherwise use b200_hc_depth_* between the sub-blocks.
  */
 typedef struct {
     const void* xres;
@@ -141,7 +146,9 @@ typedef struct {
     void* d_xres;
     float *g_norm_gamma, *g_dynamic_alpha_fn, *g_dynamic_alpha_scale, *g_static_alpha, *g_dynamic_beta_fn, *g_dynamic_beta_scale,
         *g_static_beta, *g_norm_gain;
-    float* ws_records;   /* bwd workspace: T * 40 floats (bf16 coefficient matrix [T*S, 8] + fp32 [D, 8] result of the parameter GEMM) */
+    float* ws_records;   /* bwd workspace: T * 40 floats (bf16 coefficient matrix [T*S (+T), 8] + fp32 [D, 8] result of the parameter GEMM) */
+    const void* y_prev; const float* beta_prev;              /* fused preceding depth connection (both or neither) */
+    void* d_y_prev; float* d_beta_prev;                      /* its backward outputs */
 } b200_hc_width_args;
 int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stream);
 int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stream);

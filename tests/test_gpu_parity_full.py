@@ -131,6 +131,51 @@ def test_hyper_width_depth_all_widths(pkg, D):
             check(f'{nm} m{mode} D{D}', a.reshape(-1), b.reshape(-1), 3e-2)
 
 
+# (b') the depth connection of sub-block k fused into the width connection of sub-block k+1 (ops.HcDepthWidth): forward outputs and every
+#      gradient — d residual', d branch_out, d beta of the folded depth connection and all parameter gradients (the parameter GEMM runs on
+#      two K sources, residual' rows then branch rows) — against the oracle's hyper_depth followed by hyper_width
+@pytest.mark.parametrize('D', [128, 256, 512, 1024])
+def test_hyper_depth_width_fused(pkg, D):
+    torch.manual_seed(40 + D)
+    ops = pkg.ops
+    B, n, S = 2, 1312, 4          # T * S = 10496 = 64 * 164
+    T = B * n
+    assert ops.hc_can_fuse(T, S)
+    rest = (torch.randn(T, S, D, device=dev()) * 1.5).to(torch.bfloat16).requires_grad_()
+    yp = bf(torch.randn(T, D, device=dev())).requires_grad_()
+    bp = (1 + 0.3 * torch.randn(T, S, device=dev())).requires_grad_()
+    P = dict(gamma=torch.randn(D) * 0.1, afn=torch.randn(D, S + 1) * 0.05, ascale=torch.tensor(0.5), salpha=torch.randn(S, S + 1) * 0.5 + 0.3,
+             bfn=torch.randn(D) * 0.05, bscale=torch.tensor(0.7), sbeta=torch.randn(S) * 0.3 + 1)
+    P = {k: v.to(dev()).requires_grad_() for k, v in P.items()}
+    gain = (1 + 0.2 * torch.randn(B, D, device=dev())).requires_grad_()
+    for mode, ng in ((2, gain), (0, None)):
+        br, res, beta = ops.HcDepthWidth.apply(rest, yp, bp, P['gamma'], P['afn'], P['ascale'], P['salpha'], P['bfn'], P['bscale'], P['sbeta'], ng, mode, n)
+        wb, wr, wbe = torch.randn_like(br, dtype=torch.float32), torch.randn_like(res, dtype=torch.float32), torch.randn_like(beta)
+        loss = (br.float() * wb).sum() + (res.float() * wr).sum() + (beta * wbe).sum()
+        leaves = [rest, yp, bp] + list(P.values()) + ([ng] if ng is not None else [])
+        grads = torch.autograd.grad(loss, leaves)
+        rr = rest.detach().float().cpu().view(B, n, S, D).requires_grad_()
+        yr = yp.detach().float().cpu().view(B, n, D).requires_grad_()
+        br_ = bp.detach().cpu().view(B, n, S).requires_grad_()
+        sd = {'p.norm.gamma': P['gamma'], 'p.dynamic_alpha_fn': P['afn'], 'p.dynamic_alpha_scale': P['ascale'], 'p.static_alpha': P['salpha'],
+              'p.dynamic_beta_fn': P['bfn'], 'p.dynamic_beta_scale': P['bscale'], 'p.static_beta': P['sbeta']}
+        sd = {k: v.detach().cpu().clone().requires_grad_() for k, v in sd.items()}
+        ngr = ng.detach().cpu().clone().requires_grad_() if ng is not None else None
+        x_in = O.hyper_depth(rr, br_, yr)                     # the streams the fused kernel never writes out
+        b0, rst, be = O.hyper_width(sd, 'p', x_in, S)
+        if mode == 2:
+            b0 = F.normalize(b0, dim=-1) * D ** 0.5 * ngr[:, None, :]
+        lr = (b0 * wb.cpu().view(B, n, D)).sum() + (rst * wr.cpu().view(B, n, S, D)).sum() + (be * wbe.cpu().view(B, n, S)).sum()
+        rleaves = [rr, yr, br_] + list(sd.values()) + ([ngr] if ng is not None else [])
+        rgrads = torch.autograd.grad(lr, rleaves)
+        check(f'branch m{mode}', br, b0.reshape(T, D), 2e-2)
+        check(f'res m{mode}', res, rst.reshape(T, S, D), 2e-2)
+        check(f'beta m{mode}', beta, be.reshape(T, S), 1e-3)
+        names = ['d_rest', 'd_y_prev', 'd_beta_prev', 'gamma', 'afn', 'ascale', 'salpha', 'bfn', 'bscale', 'sbeta', 'gain']
+        for nm, a, b in zip(names, grads, rgrads):
+            check(f'{nm} m{mode} D{D}', a.reshape(-1), b.reshape(-1), 3e-2)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # (d) tcgen05 attention core at the benchmark's sequence length against an fp32 softmax written here (x-transformers Attend as the
 #     reference configures it, SURVEY A.4 steps 4-5: scale, tanh soft clamp 50, key-padding mask, fp32 softmax, per-head gate)

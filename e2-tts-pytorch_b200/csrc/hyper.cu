@@ -29,6 +29,8 @@ struct HcP {
     float* beta_out;
     // fused preceding depth connection (optional): the streams entering this width connection are xres + beta_prev (x) y_prev and are
     // never materialised in HBM
+    float* stats_out;              // forward: [T, 32] per-token reduction results (24 raw dots, branch norm factor, 4 sums of squares)
+    const float* stats;            // backward: the same rows
     const __nv_bfloat16* y_prev;   // [T, D]
     const float* beta_prev;        // [T, S]
     __nv_bfloat16* d_y_prev;       // backward outputs of the fused depth connection
@@ -135,10 +137,13 @@ __device__ __forceinline__ void stage_params(const HcP& p, float4* sp) {
 }
 
 // FUSED: r_s = rsrc_s + bprev[s] * ysrc (the depth connection of the previous sub-block, fp32 — one rounding less than the unfused pair)
-template <int VPT, bool FUSED>
+// STATS: the 24 raw dot products and 4 sums of squares of this token were saved by the forward kernel (32 fp32 per token, lane l owns
+// word l) and arrive in `mine`: the backward pass then only LOADS the streams — no 28 x D FMAs, no smem parameter reads, no 32-value
+// warp reduction on its critical path (~15 % of its instructions; the kernel is latency-bound with 8-16 warps per SM).
+template <int VPT, bool FUSED, bool STATS>
 __device__ __forceinline__ void token_forward(const HcP& p, const float4* __restrict__ sp, const __nv_bfloat16* __restrict__ rsrc,
                                               const __nv_bfloat16* __restrict__ ysrc, const float4 bprev, int lane,
-                                              const LaneConst& lc, TokState<VPT>& st) {   // rsrc: this token's [HS][D] block (HBM or smem copy)
+                                              const LaneConst& lc, TokState<VPT>& st, float mine = 0.f) {   // rsrc: this token's [HS][D] block (HBM or smem copy)
     const int nchunk = p.D >> 3;
     const float bpv[HS] = {bprev.x, bprev.y, bprev.z, bprev.w};
     f2 ss2[HS], acc[HS][6];
@@ -162,6 +167,7 @@ __device__ __forceinline__ void token_forward(const HcP& p, const float4* __rest
 #pragma unroll
                     for (int j = 0; j < 4; ++j) st.r[s][v][j] = ffma2(splat(bpv[s]), yv[j], st.r[s][v][j]);
             }
+            if constexpr (!STATS)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 q0 = sp[sp_idx(nchunk, c, j, 0)], q1 = sp[sp_idx(nchunk, c, j, 1)], q2 = sp[sp_idx(nchunk, c, j, 2)];
@@ -181,16 +187,18 @@ __device__ __forceinline__ void token_forward(const HcP& p, const float4* __rest
                 for (int j = 0; j < 4; ++j) st.r[s][v][j] = splat(0.f);
         }
     }
-    float red[32];
+    if constexpr (!STATS) {
+        float red[32];
 #pragma unroll
-    for (int s = 0; s < HS; ++s) {
+        for (int s = 0; s < HS; ++s) {
 #pragma unroll
-        for (int t = 0; t < HT; ++t) red[s * HT + t] = hsum(acc[s][t]);
-        red[HS * HT + s] = hsum(acc[s][5]);
-        red[24 + s] = 0.f;
-        red[28 + s] = hsum(ss2[s]);   // the four sums of squares ride along in the same reduction
+            for (int t = 0; t < HT; ++t) red[s * HT + t] = hsum(acc[s][t]);
+            red[HS * HT + s] = hsum(acc[s][5]);
+            red[24 + s] = 0.f;
+            red[28 + s] = hsum(ss2[s]);   // the four sums of squares ride along in the same reduction
+        }
+        mine = warp_reduce32(red, lane);         // lane l owns total #l
     }
-    const float mine = warp_reduce32(red, lane);         // lane l owns total #l
     const float sqrtD = sqrtf((float)p.D);
     float invs[HS];
 #pragma unroll
@@ -275,7 +283,8 @@ __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(c
         }
         const float4 bprev = FUSED ? *reinterpret_cast<const float4*>(bsrc) : make_float4(0.f, 0.f, 0.f, 0.f);
         TokState<VPT> st;
-        token_forward<VPT, FUSED>(p, sp, rsrc, ysrc, bprev, lane, lc, st);
+        token_forward<VPT, FUSED, false>(p, sp, rsrc, ysrc, bprev, lane, lc, st);
+        if (p.stats_out && lane != 24) p.stats_out[(size_t)tok * 32 + lane] = st.myraw;   // word 24: the branch norm factor, below
         f2 br[VPT][4];
         f2 bss2 = splat(0.f);
 #pragma unroll
@@ -311,6 +320,7 @@ __global__ void __launch_bounds__(256, (VPT <= 2) ? 2 : 1) hc_width_fwd_kernel(c
             c_norm = sqrtf((float)p.D) / fmaxf(sqrtf(warp_sum(hsum(bss2))), 1e-12f);
             ng = norm_gain(p, tok);
         }
+        if (p.stats_out && lane == 24) p.stats_out[(size_t)tok * 32 + 24] = c_norm;
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             const int c = lane + 32 * v;
@@ -399,6 +409,7 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
         const __nv_bfloat16* dbsrc = p.d_branch + (size_t)tok * D;
         const __nv_bfloat16* ysrc = FUSED ? p.y_prev + (size_t)tok * D : nullptr;
         const float* bsrc = FUSED ? p.beta_prev + (size_t)tok * HS : nullptr;
+        const float mystat = __ldg(p.stats + (size_t)tok * 32 + lane);   // issued before the wait for the token's tiles
         if (PF) {
             const int buf = it & 1;
             __syncwarp();   // every lane is done reading the other buffer (previous token)
@@ -413,14 +424,14 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
         }
         const float4 bprev = FUSED ? *reinterpret_cast<const float4*>(bsrc) : make_float4(0.f, 0.f, 0.f, 0.f);
         TokState<VPT> st;
-        token_forward<VPT, FUSED>(p, sp, rsrc, ysrc, bprev, lane, lc, st);
+        token_forward<VPT, FUSED, true>(p, sp, rsrc, ysrc, bprev, lane, lc, st, mystat);
+        const float cn_saved = __shfl_sync(0xffffffffu, mystat, 24);
 
         // ---- branch (mix_0), its norm, and d(mix_0)
         f2 dm0[VPT][4];
         float cn = 1.f;
         {
             f2 br[VPT][4];
-            f2 bss2 = splat(0.f);
 #pragma unroll
             for (int v = 0; v < VPT; ++v) {
                 const int c = lane + 32 * v;
@@ -436,11 +447,10 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
 #pragma unroll
                     for (int s = 1; s < HS; ++s) acc = ffma2(splat(st.alpha[s][0]), st.r[s][v][j], acc);
                     br[v][j] = acc;
-                    bss2 = ffma2(acc, acc, bss2);
                 }
             }
             if (p.norm_mode) {
-                cn = sqrtf((float)D) / fmaxf(sqrtf(warp_sum(hsum(bss2))), 1e-12f);
+                cn = cn_saved;
                 const float* ng = norm_gain(p, tok);
                 f2 dot2 = splat(0.f);
 #pragma unroll
@@ -778,6 +788,7 @@ extern "C" int b200_hc_width_fwd(const b200_hc_width_args* a, b200_stream_t stre
     HcP p{};
     if (fill_hc(p, a)) return -1;
     p.branch = (__nv_bfloat16*)a->branch; p.res_out = (__nv_bfloat16*)a->res_out; p.beta_out = a->beta_out;
+    p.stats_out = a->stats_out;
     return a->y_prev ? launch_hc_fwd<true>(p, a, st) : launch_hc_fwd<false>(p, a, st);
 }
 
@@ -825,6 +836,8 @@ extern "C" int b200_hc_width_bwd(const b200_hc_width_args* a, b200_stream_t stre
     p.d_xres = (__nv_bfloat16*)a->d_xres;
     p.g_gamma = a->g_norm_gamma; p.g_afn = a->g_dynamic_alpha_fn; p.g_ascale = a->g_dynamic_alpha_scale; p.g_salpha = a->g_static_alpha;
     p.g_bfn = a->g_dynamic_beta_fn; p.g_bscale = a->g_dynamic_beta_scale; p.g_sbeta = a->g_static_beta; p.g_ng = a->g_norm_gain;
+    B200_REQUIRE(a->stats, "hc_width_bwd: the per-token reduction results saved by b200_hc_width_fwd (stats_out) are required");
+    p.stats = a->stats;
     B200_REQUIRE(a->ws_records, "hc_width_bwd: missing workspace (T * 40 floats)");
     // workspace: coefficient matrix C bf16 [T*S (+ T fused rows), 8] (80 B per token), then G fp32 [D, 8]
     __nv_bfloat16* cmat = reinterpret_cast<__nv_bfloat16*>(a->ws_records);

@@ -109,21 +109,22 @@ def rotary_table(Np, device):
 
 
 # ---------------------------------------------------------------------------------------------------- hyper-connections
-def _hc_width_fwd(xres, y_prev, beta_prev, params, norm_gain, norm_mode, rows_per_batch):
+def _hc_width_fwd(xres, y_prev, beta_prev, params, norm_gain, norm_mode, rows_per_batch, want_stats):
     gamma, afn, ascale, salpha, bfn, bscale, sbeta = params
     T, S, D = xres.shape
     branch = torch.empty((T, D), device=xres.device, dtype=BF16)
     res = torch.empty_like(xres)
     beta = torch.empty((T, S), device=xres.device, dtype=F32)
+    stats = torch.empty((T, 32), device=xres.device, dtype=F32) if want_stats else None   # 128 B per token: the backward's reductions
     a = lib.make_args('b200_hc_width_args', xres=xres, norm_gamma=gamma, dynamic_alpha_fn=afn, dynamic_alpha_scale=ascale,
                       static_alpha=salpha, dynamic_beta_fn=bfn, dynamic_beta_scale=bscale, static_beta=sbeta,
                       norm_mode=norm_mode, norm_gain=norm_gain, rows_per_batch=rows_per_batch, T=T, D=D, num_streams=S,
-                      branch=branch, res_out=res, beta_out=beta, y_prev=y_prev, beta_prev=beta_prev)
+                      branch=branch, res_out=res, beta_out=beta, y_prev=y_prev, beta_prev=beta_prev, stats_out=stats)
     lib.call('b200_hc_width_fwd', a, _stream())
-    return branch, res, beta
+    return branch, res, beta, stats
 
 
-def _hc_width_bwd(xres, y_prev, beta_prev, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta):
+def _hc_width_bwd(xres, y_prev, beta_prev, stats, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta):
     gamma, afn, ascale, salpha, bfn, bscale, sbeta = params
     T, S, D = xres.shape
     dev = xres.device
@@ -150,7 +151,7 @@ def _hc_width_bwd(xres, y_prev, beta_prev, params, norm_gain, norm_mode, rpb, d_
                       g_norm_gamma=g_gamma, g_dynamic_alpha_fn=g_afn, g_dynamic_alpha_scale=g_as, g_static_alpha=g_sal,
                       g_dynamic_beta_fn=g_bfn, g_dynamic_beta_scale=g_bs, g_static_beta=g_sbe,
                       g_norm_gain=g_gain if norm_mode else None, ws_records=torch.empty((T, 40), device=dev, dtype=F32),
-                      y_prev=y_prev, beta_prev=beta_prev, d_y_prev=d_y, d_beta_prev=d_bp)
+                      y_prev=y_prev, beta_prev=beta_prev, d_y_prev=d_y, d_beta_prev=d_bp, stats=stats)
     lib.call('b200_hc_width_bwd', a, _stream())
     pg = (g_gamma, g_afn.view(D, S + 1), g_as.view(()), g_sal.view(S, S + 1), g_bfn, g_bs.view(()), g_sbe,
           g_gain.view_as(norm_gain) if norm_mode else None)
@@ -162,17 +163,18 @@ class HcWidth(Function):
 
     @staticmethod
     def forward(ctx, xres, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain, norm_mode, rows_per_batch):
-        out = _hc_width_fwd(xres, None, None, (gamma, afn, ascale, salpha, bfn, bscale, sbeta), norm_gain, norm_mode, rows_per_batch)
-        ctx.save_for_backward(xres, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain)
+        *out, stats = _hc_width_fwd(xres, None, None, (gamma, afn, ascale, salpha, bfn, bscale, sbeta), norm_gain, norm_mode, rows_per_batch,
+                                    any(ctx.needs_input_grad))
+        ctx.save_for_backward(xres, stats, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain)
         ctx.meta = (norm_mode, rows_per_batch)
-        return out
+        return tuple(out)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_branch, d_res, d_beta):
-        xres, *params, norm_gain = ctx.saved_tensors
+        xres, stats, *params, norm_gain = ctx.saved_tensors
         norm_mode, rpb = ctx.meta
-        d_xres, _, _, pg = _hc_width_bwd(xres, None, None, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta)
+        d_xres, _, _, pg = _hc_width_bwd(xres, None, None, stats, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta)
         return (d_xres, *pg, None, None)
 
 
@@ -190,17 +192,18 @@ class HcDepthWidth(Function):
     @staticmethod
     def forward(ctx, rest_prev, y_prev, beta_prev, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain, norm_mode, rows_per_batch):
         y_prev, beta_prev = _c(y_prev), _c(beta_prev)
-        out = _hc_width_fwd(rest_prev, y_prev, beta_prev, (gamma, afn, ascale, salpha, bfn, bscale, sbeta), norm_gain, norm_mode, rows_per_batch)
-        ctx.save_for_backward(rest_prev, y_prev, beta_prev, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain)
+        *out, stats = _hc_width_fwd(rest_prev, y_prev, beta_prev, (gamma, afn, ascale, salpha, bfn, bscale, sbeta), norm_gain, norm_mode,
+                                    rows_per_batch, any(ctx.needs_input_grad))
+        ctx.save_for_backward(rest_prev, y_prev, beta_prev, stats, gamma, afn, ascale, salpha, bfn, bscale, sbeta, norm_gain)
         ctx.meta = (norm_mode, rows_per_batch)
-        return out
+        return tuple(out)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_branch, d_res, d_beta):
-        rest_prev, y_prev, beta_prev, *params, norm_gain = ctx.saved_tensors
+        rest_prev, y_prev, beta_prev, stats, *params, norm_gain = ctx.saved_tensors
         norm_mode, rpb = ctx.meta
-        d_rest, d_y, d_bp, pg = _hc_width_bwd(rest_prev, y_prev, beta_prev, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta)
+        d_rest, d_y, d_bp, pg = _hc_width_bwd(rest_prev, y_prev, beta_prev, stats, params, norm_gain, norm_mode, rpb, d_branch, d_res, d_beta)
         return (d_rest, d_y, d_bp, *pg, None, None)
 
 

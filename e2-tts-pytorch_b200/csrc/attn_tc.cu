@@ -324,6 +324,254 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, two CTAs per SM
+// Same algorithm on 64-key tiles with HALF the resources per CTA — 320 threads (TMA producer, MMA issuer, 8 softmax warps: thread =
+// query row x key half, still 32 scores per thread and tile), 96 KB of shared memory, 256 TMEM columns (S[2] x 64 + O 64) — so that
+// two CTAs share an SM. The softmax of this attention flavour is bound by the CUDA-core pipes (tanh polynomial on FMA, exp on MUFU,
+// dropout hash on ALU), and inside one CTA its phases run in lockstep on all softmax warps; two independent CTAs interleave their
+// phases on the schedulers, overlap one CTA's prologue / epilogue with the other's main loop, and give the SM two MMA issuers.
+// 64-key tiles also waste less of the ragged last tile (17 x 64 = 1088 keys for N' = 1056 instead of 9 x 128 = 1152).
+constexpr int TKV2 = 64, KV2_STAGES = 3;
+constexpr int TILE8 = 64 * 64 * 2;            // 8 KB: K or V tile of 64 keys
+
+__global__ void __launch_bounds__(320, 2)
+attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const AttnTcP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;                         // 16 KB
+    uint8_t* sK = sQ + TILE16;                  // [3] x 8 KB
+    uint8_t* sV = sK + KV2_STAGES * TILE8;      // [3] x 8 KB
+    uint8_t* sP = sV + KV2_STAGES * TILE8;      // [2] x 16 KB (128 rows x 64 keys bf16 = one 128-byte swizzle atom per row)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE16);
+    uint64_t* q_full = bars;                    // 1
+    uint64_t* k_full = bars + 1;                // 3
+    uint64_t* v_full = bars + 4;                // 3
+    uint64_t* kv_empty = bars + 7;              // 3
+    uint64_t* s_full = bars + 10;               // 2
+    uint64_t* s_empty = bars + 12;              // 2
+    uint64_t* p_full = bars + 14;               // 2
+    uint64_t* p_empty = bars + 16;              // 2
+    uint64_t* o_full = bars + 18;               // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    float* s_xch = reinterpret_cast<float*>(bars + 20);   // [2 halves][128 rows] row sums
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+    const int bh = b * p.H + hh;
+    const int q0 = qt * TQ;
+    const int nkv = (p.Np + TKV2 - 1) / TKV2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        mbar_init(q_full, 1);
+        mbar_init(o_full, 1);
+        for (int i = 0; i < KV2_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+            mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tO = tmem_base + 128;   // S[2] at +0 / +64, O at +128 (64 columns)
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            const int row_base = bh * p.Np;
+            mbar_arrive_expect_tx(q_full, TILE16);
+            tma_load_2d(sQ, &tmQ, q_full, 0, row_base + q0);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < nkv; ++j) {
+                mbar_wait(&kv_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[st], TILE8);
+                tma_load_2d(sK + st * TILE8, &tmK, &k_full[st], 0, row_base + j * TKV2);
+                mbar_arrive_expect_tx(&v_full[st], TILE8);
+                tma_load_2d(sV + st * TILE8, &tmV, &v_full[st], 0, row_base + j * TKV2);
+                if (++st == KV2_STAGES) { st = 0; ph ^= 1; }
+            }
+            pdl_launch_dependents();
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- MMA issuer
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+            mbar_wait(q_full, 0);
+            const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+            int kst = 0; uint32_t kph = 0;       // K ring position of S_j
+            int vst = 0; uint32_t vph = 0;       // V ring position of O_{j-1}
+            for (int j = 0; j <= nkv; ++j) {
+                if (j < nkv) {
+                    const int ss = j & 1;
+                    mbar_wait(&k_full[kst], kph);
+                    mbar_wait(&s_empty[ss], ((j >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + kst * TILE8), 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < DH / 16; ++k) umma_f16(tS + ss * 64, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit(&s_full[ss]);
+                    if (++kst == KV2_STAGES) { kst = 0; kph ^= 1; }
+                }
+                if (j >= 1) {
+                    const int jj = j - 1, ps = jj & 1;
+                    mbar_wait(&p_full[ps], (jj >> 1) & 1);
+                    mbar_wait(&v_full[vst], vph);
+                    tc_fence_after();
+                    const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + vst * TILE8), 128 * 128, 1024);
+                    const uint32_t pbase = smem_u32(sP + ps * TILE16);
+#pragma unroll
+                    for (int k = 0; k < TKV2 / 16; ++k) {
+                        const uint64_t pdesc = make_smem_desc_sw128(pbase + k * 32, 0, 1024);
+                        umma_f16(tO, pdesc, vdesc + (uint64_t)(k * 128), idesc_o, (jj > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&kv_empty[vst]);     // K_jj was consumed by S_jj earlier: the slot is free once O_jj has read V_jj
+                    umma_commit(&p_empty[ps]);
+                    if (jj == nkv - 1) umma_commit(o_full);
+                    if (++vst == KV2_STAGES) { vst = 0; vph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // -------------------------------------------------------------------- softmax warps: thread = (row, key half)
+        const int qd = warp & 3, half = (warp - 2) >> 2;
+        const int row = qd * 32 + lane;
+        const int qi = q0 + row;
+        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + half;
+        const uint32_t seedmix = seed_mix32(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull));
+        const unsigned long long drop_row = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride;
+        const float2 soc2 = make_float2(p.scale_over_clamp, p.scale_over_clamp);
+        const float2 cl2 = make_float2(p.clamp * LOG2E_F, p.clamp * LOG2E_F);
+        const float soc = p.scale_over_clamp, soc2s = soc * soc;
+        const float k1 = soc * p.clamp * LOG2E_F, k3 = k1 * soc2s * (-1.f / 3.f), k5 = k1 * soc2s * soc2s * (2.f / 15.f),
+                    k7 = k1 * soc2s * soc2s * soc2s * (-17.f / 315.f), k9 = k1 * soc2s * soc2s * soc2s * soc2s * (62.f / 2835.f);
+        const float lim5 = 0.15f / fabsf(soc), lim9 = TANH_POLY_MAX / fabsf(soc);
+        const uint32_t thr32 = drop_thresh32(p.drop_thresh);
+        float2 l2 = make_float2(0.f, 0.f);
+
+        for (int j = 0; j < nkv; ++j) {
+            const int st = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            const unsigned int mbits = mb[j * 2];
+            mbar_wait(&s_full[st], ph);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld32(tS + st * 64 + half * 32 + lane_off, r);
+            tmem_ld_wait();
+            tc_fence_before();          // the scores are in registers: hand the S buffer back before doing the math
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
+            float pv[32];
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { pv[i] = __uint_as_float(r[i]); amax = fmaxf(amax, fabsf(pv[i])); }
+            // clamp * log2(e) * tanh(s * scale / clamp) as an odd polynomial in the raw score (see attn_fwd_tc_kernel)
+            if (__all_sync(0xffffffffu, amax <= lim5)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 s = make_float2(pv[i], pv[i + 1]);
+                    const float2 s2 = __fmul2_rn(s, s);
+                    float2 q = __ffma2_rn(s2, make_float2(k5, k5), make_float2(k3, k3));
+                    q = __ffma2_rn(q, s2, make_float2(k1, k1));
+                    const float2 y = __fmul2_rn(s, q);
+                    pv[i] = ex2_approx(y.x);
+                    pv[i + 1] = ex2_approx(y.y);
+                }
+            } else if (__all_sync(0xffffffffu, amax <= lim9)) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 s = make_float2(pv[i], pv[i + 1]);
+                    const float2 s2 = __fmul2_rn(s, s);
+                    float2 q = __ffma2_rn(s2, make_float2(k9, k9), make_float2(k7, k7));
+                    q = __ffma2_rn(q, s2, make_float2(k5, k5));
+                    q = __ffma2_rn(q, s2, make_float2(k3, k3));
+                    q = __ffma2_rn(q, s2, make_float2(k1, k1));
+                    const float2 y = __fmul2_rn(s, q);
+                    pv[i] = ex2_approx(y.x);
+                    pv[i + 1] = ex2_approx(y.y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 x = __fmul2_rn(make_float2(pv[i], pv[i + 1]), soc2);
+                    const float2 y = __fmul2_rn(make_float2(tanh_approx(x.x), tanh_approx(x.y)), cl2);
+                    pv[i] = ex2_approx(y.x);
+                    pv[i + 1] = ex2_approx(y.y);
+                }
+            }
+            if (mbits != 0xffffffffu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pv[i] = ((mbits >> i) & 1u) ? pv[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) l2 = __fadd2_rn(l2, make_float2(pv[i], pv[i + 1]));
+            if (p.dropout_p > 0.f) {   // the 1/(1-p) factor is applied once, to the normalised output
+                const uint32_t pbase = (uint32_t)((drop_row + (unsigned long long)(j * TKV2 + half * 32)) >> 1);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const DropWords h = drop_words(seedmix, pbase + (i >> 1));
+                    pv[i] = (h.a >= thr32) ? pv[i] : 0.f;
+                    pv[i + 1] = (h.b >= thr32) ? pv[i + 1] : 0.f;
+                }
+            }
+            mbar_wait(&p_empty[st], ph ^ 1);     // the P buffer was last read by the PV MMA of tile j-2
+            uint8_t* pdst = sP + st * TILE16 + row * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int chunk = half * 4 + g;
+                *reinterpret_cast<uint4*>(pdst + ((chunk ^ (row & 7)) << 4)) =
+                    make_uint4(pack_bf16(pv[g * 8], pv[g * 8 + 1]), pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]),
+                               pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[st]);
+        }
+        // ---- epilogue: row sum over the two halves, normalise, write O (ungated), Og (gated, head-merged) and LSE
+        s_xch[half * 128 + row] = l2.x + l2.y;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float l_tot = s_xch[row] + s_xch[128 + row];
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        uint32_t ro[32];
+        tmem_ld32(tO + half * 32 + lane_off, ro);
+        tmem_ld_wait();
+        if (qi < p.Np) {
+            const float inv = l_tot > 0.f ? p.keep_scale / l_tot : 0.f;
+            const float gt = p.gate ? p.gate[((size_t)b * p.Np + qi) * p.H + hh] : 1.f;
+            __nv_bfloat16* orow = p.o + ((size_t)bh * p.Np + qi) * DH + half * 32;
+            __nv_bfloat16* grow = p.og + ((size_t)b * p.Np + qi) * (size_t)(p.H * DH) + hh * DH + half * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(ro[g * 8 + i]) * inv;
+                const uint4 u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                *reinterpret_cast<uint4*>(orow + g * 8) = u;
+                // gate the bf16-rounded output (what the backward pass sees) for consistency
+                *reinterpret_cast<uint4*>(grow + g * 8) =
+                    make_uint4(pack_bf16(bf16_lo(u.x) * gt, bf16_hi(u.x) * gt), pack_bf16(bf16_lo(u.y) * gt, bf16_hi(u.y) * gt),
+                               pack_bf16(bf16_lo(u.z) * gt, bf16_hi(u.z) * gt), pack_bf16(bf16_lo(u.w) * gt, bf16_hi(u.w) * gt));
+            }
+            if (half == 0) p.lse[(size_t)bh * p.Np + qi] = logf(l_tot);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 // ================================================================================================ backward
 // One CTA per (128-key tile, head, batch), 576 threads:
 //   warp 0 lane 0 : TMA producer — K, V once; Q_i / dO_i tiles (128 queries) through a 2-stage ring
@@ -621,7 +869,7 @@ typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_head_map(CUtensorMap* m, const void* ptr, long long rows) {
+static int make_head_map(CUtensorMap* m, const void* ptr, long long rows, int box_rows = 128) {
     static PFN_encodeTiled2 enc = nullptr;
     if (!enc) {
         void* fn = nullptr;
@@ -633,7 +881,7 @@ static int make_head_map(CUtensorMap* m, const void* ptr, long long rows) {
     B200_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "attention: operand not 16-byte aligned");
     cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {128};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -650,6 +898,14 @@ extern "C" size_t b200_attn_workspace_bytes(int32_t B, int32_t Np) {
     return (size_t)B * words * sizeof(unsigned int);
 }
 
+extern "C" int b200_attn_maskbits(const uint8_t* keymask, void* ws_maskbits, int32_t B, int32_t Np, b200_stream_t stream) {
+    B200_REQUIRE(ws_maskbits && B > 0 && Np > 0, "attn_maskbits: bad arguments");
+    const int words = ((Np + TKV - 1) / TKV) * 4;
+    B200_LAUNCH(attn_maskbits_kernel, (B * words + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream), keymask,
+                reinterpret_cast<unsigned int*>(ws_maskbits), B, Np, words);
+    return check_launch("attn_maskbits_kernel");
+}
+
 extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     B200_REQUIRE(a && a->q && a->k && a->v && a->o && a->og && a->lse && a->ws_maskbits, "attn_fwd: null pointer");
@@ -664,7 +920,7 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     p.nkv = (a->Np + TKV - 1) / TKV;
     p.mask_words = p.nkv * 4;
     p.maskbits = reinterpret_cast<const unsigned int*>(a->ws_maskbits);
-    {
+    if (!a->maskbits_ready) {
         const int total = a->B * p.mask_words;
         B200_LAUNCH(attn_maskbits_kernel, (total + 127) / 128, 128, 0, st, a->keymask, reinterpret_cast<unsigned int*>(a->ws_maskbits), a->B, a->Np, p.mask_words);
         if (int rc = check_launch("attn_maskbits_kernel")) return rc;
@@ -679,6 +935,17 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     p.drop_stride = (a->Np + 1) & ~1;
     CUtensorMap tq, tk, tv;
     const long long rows = (long long)a->B * a->H * a->Np;
+    static const bool fwd64 = !(getenv("B200_ATTN_FWD64") && atoi(getenv("B200_ATTN_FWD64")) == 0);   // developer A/B switch, default on
+    if (fwd64) {
+        if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows, TKV2) || make_head_map(&tv, a->v, rows, TKV2)) return -1;
+        const int smem64 = TILE16 + 2 * KV2_STAGES * TILE8 + 2 * TILE16 + 160 + 1024 + 1024;
+        static DeviceOnce once64;
+        cudaError_t e64 = set_max_smem_once(once64, attn_fwd_tc64_kernel, smem64);
+        B200_REQUIRE(e64 == cudaSuccess, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e64));
+        dim3 grid64((a->Np + TQ - 1) / TQ, a->H, a->B);
+        B200_LAUNCH(attn_fwd_tc64_kernel, grid64, 320, smem64, st, tq, tk, tv, p);
+        return check_launch("attn_fwd_tc64_kernel");
+    }
     if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows)) return -1;
     const int smem = 5 * TILE16 + 2 * PTILE + 256 + 4096 + 1024;
     static DeviceOnce once;
@@ -704,7 +971,7 @@ extern "C" int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream) 
     p.nq = (a->Np + TQ - 1) / TQ;
     p.mask_words = p.nq * 4;
     p.maskbits = reinterpret_cast<const unsigned int*>(a->ws_maskbits);
-    {
+    if (!a->maskbits_ready) {
         const int total = a->B * p.mask_words;
         B200_LAUNCH(attn_maskbits_kernel, (total + 127) / 128, 128, 0, st, a->keymask, reinterpret_cast<unsigned int*>(a->ws_maskbits), a->B, a->Np, p.mask_words);
         if (int rc = check_launch("attn_maskbits_kernel")) return rc;

@@ -484,6 +484,7 @@ class Transformer(Module):
         H = self.heads
         cs, sn = self._rotary(Np, xs.device)
         p_drop = self.dropout if self.training else 0.0
+        mbits = ops.attn_maskbits(mask_u8, B, Np, xs.device) if xs.is_cuda else None   # one key-mask bitmask for all 2 * depth attention calls
         skips = []
         v_first, tv_first = None, None
         nseed = [seed]
@@ -519,7 +520,7 @@ class Transformer(Module):
             og, v = ops.Attention.apply(br, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_v_head_gate.weight,
                                         attn.to_v_head_gate.bias, mix[0].weight if mix is not None else None,
                                         mix[0].bias if mix is not None else None, vf if mix is not None else None,
-                                        pk['qkv'], cs, sn, mask_u8, B, Np, H, p_drop, next_seed(), SOFTCLAMP, self._seed_dev)
+                                        pk['qkv'], cs, sn, mask_u8, B, Np, H, p_drop, next_seed(), SOFTCLAMP, self._seed_dev, mbits)
             y = ops.OutProj.apply(og, attn.to_out.weight, pk['out'], colscale, mask_u8, B, Np)
             return depth(rest, y, beta), (v if vf is None else vf)
 
@@ -544,7 +545,7 @@ class Transformer(Module):
         two = TWO_STREAM and has_text(0) and xs.is_cuda
         if two:
             main, side = torch.cuda.current_stream(xs.device), _side_stream(xs.device)
-            for t in (mask_u8, cs, sn):
+            for t in (mask_u8, cs, sn, mbits):
                 if t is not None:
                     t.record_stream(side)
 

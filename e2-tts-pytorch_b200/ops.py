@@ -353,7 +353,7 @@ class Attention(Function):
     One autograd node: q/k/v never enter the graph, and dq stays fp32 from the attention backward into the rotary inverse."""
 
     @staticmethod
-    def forward(ctx, xn, wq, wk, wv, wg, bg, wm, bm, v_first, wpack, cs, sn, mask, B, Np, H, dropout_p, seed, softclamp, seed_dev):
+    def forward(ctx, xn, wq, wk, wv, wg, bg, wm, bm, v_first, wpack, cs, sn, mask, B, Np, H, dropout_p, seed, softclamp, seed_dev, maskbits=None):
         ctx.set_materialize_grads(False)   # only the first layer's values are consumed downstream: no zero-filled d_v for the others
         T, Din = xn.shape
         I = H * 64
@@ -370,10 +370,12 @@ class Attention(Function):
         lib.call('b200_qkv_post_fwd', a, _stream())
         og = torch.empty((T, I), device=dev, dtype=BF16)
         lse = torch.empty((B, H, Np), device=dev, dtype=F32)
-        ws = torch.empty(((Np + 127) // 128) * 4 * B, device=dev, dtype=torch.int32)
+        ws = maskbits if maskbits is not None else torch.empty(((Np + 127) // 128) * 4 * B, device=dev, dtype=torch.int32)
         a = lib.make_args('b200_attn_fwd_args', q=q, k=k, v=v, keymask=mask, gate=gate, o=o, og=og, lse=lse, B=B, H=H, Np=Np,
-                          dim_head=64, scale=0.125, softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws, seed_dev=seed_dev)
+                          dim_head=64, scale=0.125, softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws, seed_dev=seed_dev,
+                          maskbits_ready=int(maskbits is not None))
         lib.call(ATTN_FWD_ENTRY, a, _stream())
+        ctx.maskbits = maskbits
         ctx.save_for_backward(xn, qkvg, gate, v_first, wpack, cs, sn, bg, bm, q, k, v, o, lse, mask)
         ctx.meta = (B, Np, H, ncat, ld, has_mix, dropout_p, seed, softclamp, seed_dev)
         return og, v
@@ -393,10 +395,11 @@ class Attention(Function):
         dk, dv, ws_dO = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
         ws_delta = torch.empty_like(lse)
         d_gate = torch.empty_like(gate)
-        ws = torch.empty(((Np + 127) // 128) * 4 * B, device=dev, dtype=torch.int32)
+        ws = ctx.maskbits if ctx.maskbits is not None else torch.empty(((Np + 127) // 128) * 4 * B, device=dev, dtype=torch.int32)
         a = lib.make_args('b200_attn_bwd_args', q=q, k=k, v=v, o=o, d_og=_c(d_og), keymask=mask, gate=gate, lse=lse, ws_dO=ws_dO,
                           ws_delta=ws_delta, d_gate=d_gate, dq=dq, dk=dk, dv=dv, B=B, H=H, Np=Np, dim_head=64, scale=0.125,
-                          softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws, seed_dev=seed_dev)
+                          softclamp=softclamp, dropout_p=dropout_p, seed=seed, ws_maskbits=ws, seed_dev=seed_dev,
+                          maskbits_ready=int(ctx.maskbits is not None))
         lib.call(ATTN_BWD_ENTRY, a, _stream())
         d_qkvg = torch.empty((T, ld), device=dev, dtype=BF16)
         d_vfirst = torch.empty_like(v_first) if v_first is not None else None
@@ -409,7 +412,14 @@ class Attention(Function):
         db = colsum(d_qkvg[:, 3 * I:], T, ld - 3 * I, ld)   # only the head-gate / value-residual-mix logits have biases
         return (dx, dW[:I], dW[I:2 * I], dW[2 * I:3 * I], dW[3 * I:3 * I + H], db[:H],
                 dW[3 * I + H:3 * I + 2 * H] if has_mix else None, db[H:2 * H] if has_mix else None,
-                d_vfirst, None, None, None, None, None, None, None, None, None, None, None)
+                d_vfirst, None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+def attn_maskbits(mask_u8, B, Np, device):
+    """Key-validity bitmask shared by every attention call of one forward/backward (all layers see the same key mask)."""
+    ws = torch.empty(((Np + 127) // 128) * 4 * B, device=device, dtype=torch.int32)
+    lib.call('b200_attn_maskbits', mask_u8, ws, B, Np, _stream())
+    return ws
 
 
 def _rowgate_bwd(dy, y, cs, mask, B, rpb, D, want_bias=False):

@@ -97,8 +97,12 @@ typedef struct {
     uint64_t seed;
     void* ws_maskbits;   /* workspace of b200_attn_workspace_bytes(B, Np) bytes (key-validity bitmask built by the call) */
     const uint64_t* seed_dev;   /* optional device addend of `seed` (dropout seeds, above) */
+    int32_t maskbits_ready;     /* != 0: ws_maskbits already holds b200_attn_maskbits(keymask) — every layer of a forward/backward shares
+                                   one key mask, so the model builds the bitmask once instead of once per attention call */
 } b200_attn_fwd_args;
 size_t b200_attn_workspace_bytes(int32_t B, int32_t Np);
+/* key-validity bitmask of `keymask` (u8 [B,Np], NULL = all valid) into ws_maskbits, in the layout the tcgen05 kernels read */
+int b200_attn_maskbits(const uint8_t* keymask, void* ws_maskbits, int32_t B, int32_t Np, b200_stream_t stream);
 int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream);        /* tcgen05 / TMEM / TMA kernel */
 int b200_attn_fwd_legacy(const b200_attn_fwd_args* a, b200_stream_t stream); /* mma.sync bring-up kernel, kept for cross-checks */
 
@@ -117,6 +121,7 @@ typedef struct {
     uint64_t seed;
     void* ws_maskbits;
     const uint64_t* seed_dev;   /* optional device addend of `seed` (must be the forward's) */
+    int32_t maskbits_ready;     /* as in b200_attn_fwd_args */
 } b200_attn_bwd_args;
 int b200_attn_bwd(const b200_attn_bwd_args* a, b200_stream_t stream);         /* tcgen05 / TMEM / TMA kernel, dq fp32 */
 int b200_attn_bwd_legacy(const b200_attn_bwd_args* a, b200_stream_t stream);  /* mma.sync bring-up kernels, dq bf16 */

@@ -323,7 +323,7 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         # -- the same train step through pkg.GraphedTrainStep (forward + backward captured in one CUDA graph, then — N > 1 — ONE flat
         #    all-reduce): identical kernels and work, no per-launch host cost. Falls back to the eager numbers if capture fails.
-        if kind == 'train' and not args.no_graph:
+        if kind in ('train', 'duration') and not args.no_graph:
             try:
                 eager_loss = step(dev_mel, True)
                 torch.cuda.empty_cache()      # the eager pool and the graph's private pool each hold a full set of activations

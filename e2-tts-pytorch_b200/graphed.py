@@ -27,15 +27,20 @@ from . import lib
 from .optim import GradSync, broadcast_module
 
 
+class _Loss:
+    def __init__(self, loss):
+        self.loss = loss
+
+
 class GraphedTrainStep:
     def __init__(self, model, mel, *, text=None, lens=None, warmup=3, process_group=None, flat_grads=None):
-        """model: an E2TTS (NOT wrapped in DistributedDataParallel — the exchange is done here). flat_grads: True forces the flat
+        """model: an E2TTS or a DurationPredictor (NOT wrapped in DistributedDataParallel — the exchange is done here). flat_grads: True forces the flat
         gradient buffer even on one rank (for the fused optimiser); default = only when world_size > 1."""
         import torch.distributed as dist
         if hasattr(model, 'module') and not hasattr(model, 'transformer'):
             raise ValueError('GraphedTrainStep: pass the bare E2TTS module, not a DistributedDataParallel wrapper '
                              '(gradients are averaged by one flat all-reduce after the replay)')
-        if model.training and 0.0 < float(model.cond_drop_prob) < 1.0:
+        if model.training and 0.0 < float(getattr(model, 'cond_drop_prob', 0.0)) < 1.0:
             raise ValueError('GraphedTrainStep: cond_drop_prob must be 0 or 1 (the text-drop branch is decided on the host)')
         if not mel.is_cuda:
             raise ValueError('GraphedTrainStep: inputs must live on the GPU')
@@ -84,6 +89,8 @@ class GraphedTrainStep:
     def _eager(self):
         lib.call('b200_seed_advance', self._seed_dev, torch.cuda.current_stream().cuda_stream)
         out = self.model(self.mel, text=self.text, lens=self.lens)
+        if torch.is_tensor(out):       # DurationPredictor.forward returns the scalar loss itself (e2_tts.py:1113)
+            out = _Loss(out)
         out.loss.backward()
         return out
 

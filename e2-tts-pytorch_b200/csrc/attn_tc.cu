@@ -1,17 +1,16 @@
-// tcgen05 / TMEM / TMA flash attention FORWARD for the softclamped, key-masked, head-gated attention of the
-// E2-TTS multistream block (x-transformers Attend as configured by the reference: SURVEY A.4 steps 4-5).
+// tcgen05 / TMEM / TMA flash attention for the softclamped, key-masked, head-gated attention of the E2-TTS multistream block
+// (x-transformers Attend as configured by the reference: SURVEY A.4 steps 4-5) — forward and backward.
 //
-// One CTA per (128-query tile, head, batch), 576 threads, warp-specialised:
-//   warp 0 lane 0 : TMA producer  — Q once, then K_j / V_j tiles (128 keys x 64) into a 2-stage smem ring
-//   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T  (tcgen05.mma 128x128x16 x4, both operands K-major) into TMEM S[j%2]
-//                                   O_j = P_j V_j  (tcgen05.mma 128x64x16 x8, A = P from smem (K-major), B = V MN-major)
+// Forward: one CTA per (128-query tile, head, batch) on 64-key tiles, 320 threads, two CTAs per SM (see attn_fwd_tc64_kernel):
+//   warp 0 lane 0 : TMA producer  — Q once, then K_j / V_j tiles (64 keys x 64) into a 3-stage smem ring
+//   warp 1 lane 0 : MMA issuer    — S_j = Q K_j^T  (tcgen05.mma 128x64x16 x4, both operands K-major) into TMEM S[j%2]
+//                                   O_j = P_j V_j  (tcgen05.mma 128x64x16 x4, A = P from smem (K-major), B = V MN-major)
 //                                   accumulating into TMEM O; S_{j+1} is issued before O_j so the tensor pipe never waits on softmax
-//   warps 2..17   : softmax       — thread = (query row, key quarter): 32 of the 128 scores of its row (tcgen05.ld 32x32b:
-//                                   lane == row; 4 warps per scheduler hide the MUFU / TMEM latencies). The softclamp bounds the
-//                                   logits to [-clamp, clamp], so exp() needs no running maximum: one pass softclamp (tanh) +
-//                                   exp2 + dropout, P_j written as bf16 into 128B-swizzled smem (the A operand of the PV MMA);
-//                                   P V accumulates in ONE TMEM accumulator over all key tiles and is read back once.
-// mbarrier pipelines: q_full, k_full/v_full/kv_empty[2], s_full/s_empty[2], p_full/p_empty[2], o_full.
+//   warps 2..9    : softmax       — thread = (query row, key half): 32 of the 64 scores of its row (tcgen05.ld 32x32b: lane == row).
+//                                   The softclamp bounds the logits to [-clamp, clamp], so exp() needs no running maximum: one pass
+//                                   softclamp (tanh) + exp2 + dropout, P_j written as bf16 into 128B-swizzled smem (the A operand of
+//                                   the PV MMA); P V accumulates in ONE TMEM accumulator over all key tiles and is read back once.
+// mbarrier pipelines: q_full, k_full/v_full/kv_empty[3], s_full/s_empty[2], p_full/p_empty[2], o_full.
 #include <type_traits>
 
 #include "common.cuh"
@@ -82,252 +81,10 @@ __global__ void attn_maskbits_kernel(const unsigned char* mask, unsigned int* bi
     bits[w] = v;
 }
 
-__global__ void __launch_bounds__(576, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const AttnTcP p) {
-    extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment by OFFSET, not by integer round-trip: the pointer keeps its shared-memory provenance, so tile / staging
-    // accesses compile to LDS / STS instead of generic LD / ST (+ a full MEMBAR before the async-proxy fence)
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + TILE16;          // [2]
-    uint8_t* sV = sK + 2 * TILE16;      // [2]
-    uint8_t* sP = sV + 2 * TILE16;      // [2] x 32 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PTILE);
-    uint64_t* q_full = bars;            // 1
-    uint64_t* k_full = bars + 1;        // 2
-    uint64_t* v_full = bars + 3;        // 2
-    uint64_t* kv_empty = bars + 5;      // 2
-    uint64_t* s_full = bars + 7;        // 2
-    uint64_t* s_empty = bars + 9;       // 2
-    uint64_t* p_full = bars + 11;       // 2
-    uint64_t* p_empty = bars + 13;      // 2
-    uint64_t* o_full = bars + 15;       // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-    float* s_xch = reinterpret_cast<float*>(bars + 20);   // [4 quarters][128 rows] row sums
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
-    const int bh = b * p.H + hh;
-    const int q0 = qt * TQ;
-    const int nkv = p.nkv;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-        mbar_init(q_full, 1);
-        mbar_init(o_full, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 16);
-            mbar_init(&p_full[i], 16); mbar_init(&p_empty[i], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tO = tmem_base + 256;   // S[2] at +0/+128, O at +256 (64 columns, accumulated over all key tiles)
-    pdl_wait();   // prologue above overlaps the previous kernel's tail (ptx.cuh)
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ---------------------------------------------------------------- TMA producer
-            const int row_base = bh * p.Np;
-            mbar_arrive_expect_tx(q_full, TILE16);
-            tma_load_2d(sQ, &tmQ, q_full, 0, row_base + q0);
-            for (int j = 0; j < nkv; ++j) {
-                const int st = j & 1;
-                mbar_wait(&kv_empty[st], (((j >> 1) & 1) ^ 1));
-                mbar_arrive_expect_tx(&k_full[st], TILE16);
-                tma_load_2d(sK + st * TILE16, &tmK, &k_full[st], 0, row_base + j * TKV);
-                mbar_arrive_expect_tx(&v_full[st], TILE16);
-                tma_load_2d(sV + st * TILE16, &tmV, &v_full[st], 0, row_base + j * TKV);
-            }
-            pdl_launch_dependents();
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------------------------------------------------------- MMA issuer
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-            mbar_wait(q_full, 0);
-            const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
-            for (int j = 0; j <= nkv; ++j) {
-                if (j < nkv) {
-                    const int st = j & 1;
-                    const uint32_t ph = (j >> 1) & 1;
-                    mbar_wait(&k_full[st], ph);
-                    mbar_wait(&s_empty[st], ph ^ 1);
-                    tc_fence_after();
-                    const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + st * TILE16), 0, 1024);
-#pragma unroll
-                    for (int k = 0; k < DH / 16; ++k) umma_f16(tS + st * 128, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
-                    umma_commit(&s_full[st]);
-                }
-                if (j >= 1) {
-                    const int jj = j - 1, st = jj & 1;
-                    const uint32_t ph = (jj >> 1) & 1;
-                    mbar_wait(&p_full[st], ph);
-                    mbar_wait(&v_full[st], ph);
-                    tc_fence_after();
-                    const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + st * TILE16), 128 * 128, 1024);
-                    const uint32_t pbase = smem_u32(sP + st * PTILE);
-#pragma unroll
-                    for (int k = 0; k < TKV / 16; ++k) {
-                        const uint64_t pdesc = make_smem_desc_sw128(pbase + (k >> 2) * TILE16 + (k & 3) * 32, 0, 1024);
-                        umma_f16(tO, pdesc, vdesc + (uint64_t)(k * 128), idesc_o, (jj > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&kv_empty[st]);
-                    umma_commit(&p_empty[st]);
-                    if (jj == nkv - 1) umma_commit(o_full);
-                }
-            }
-        }
-    } else {
-        // -------------------------------------------------------------------- softmax warps: thread = (row, key quarter)
-        // The softclamp bounds every logit to [-clamp, clamp] (clamp <= 64 on this path), so exp(logit) stays inside the fp32 / bf16
-        // range without a running row maximum: no max pass, no cross-warp exchange per tile, no rescale — P V accumulates in TMEM
-        // over all key tiles and is read once. LSE = log(sum exp(logit)).
-        const int qd = warp & 3, part = (warp - 2) >> 2;
-        const int row = qd * 32 + lane;
-        const int qi = q0 + row;
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        const unsigned int* mb = p.maskbits + (size_t)b * p.mask_words + part;
-        const uint32_t seedmix = seed_mix32(p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull));
-        const unsigned long long drop_row = ((unsigned long long)bh * p.Np + (unsigned long long)qi) * (unsigned long long)p.drop_stride;
-        const float2 soc2 = make_float2(p.scale_over_clamp, p.scale_over_clamp);
-        const float2 cl2 = make_float2(p.clamp * LOG2E_F, p.clamp * LOG2E_F);
-        const float soc = p.scale_over_clamp, soc2s = soc * soc;
-        const float k1 = soc * p.clamp * LOG2E_F, k3 = k1 * soc2s * (-1.f / 3.f), k5 = k1 * soc2s * soc2s * (2.f / 15.f),
-                    k7 = k1 * soc2s * soc2s * soc2s * (-17.f / 315.f), k9 = k1 * soc2s * soc2s * soc2s * soc2s * (62.f / 2835.f);
-        const float lim5 = 0.15f / fabsf(soc), lim9 = TANH_POLY_MAX / fabsf(soc);
-        float2 l2 = make_float2(0.f, 0.f);
-
-        for (int j = 0; j < nkv; ++j) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            const unsigned int mbits = mb[j * 4];
-            mbar_wait(&s_full[st], ph);
-            tc_fence_after();
-            uint32_t r[32];
-            tmem_ld32(tS + st * 128 + part * 32 + lane_off, r);
-            tmem_ld_wait();
-            tc_fence_before();          // the scores are in registers: hand the S buffer back before doing the math
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[st]);
-            // clamp * log2(e) * tanh(u), u = s * scale / clamp, evaluated as an odd polynomial in the RAW score s with the constants folded
-            // in: s * (k1 + s^2 (k3 + s^2 (k5 + ...))) — 4 (degree 5, |u| <= 0.15: exact to 1e-7) or 6 (degree 9, |u| <= 0.5) packed
-            // instructions per key pair instead of 8 (ncu r2c: FMUL2 + FFMA2 were 128 of the 509 instructions per warp and tile)
-            float pv[32];
-            float amax = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { pv[i] = __uint_as_float(r[i]); amax = fmaxf(amax, fabsf(pv[i])); }
-            if (__all_sync(0xffffffffu, amax <= lim5)) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float2 s = make_float2(pv[i], pv[i + 1]);
-                    const float2 s2 = __fmul2_rn(s, s);
-                    float2 q = __ffma2_rn(s2, make_float2(k5, k5), make_float2(k3, k3));
-                    q = __ffma2_rn(q, s2, make_float2(k1, k1));
-                    const float2 y = __fmul2_rn(s, q);
-                    pv[i] = ex2_approx(y.x);
-                    pv[i + 1] = ex2_approx(y.y);
-                }
-            } else if (__all_sync(0xffffffffu, amax <= lim9)) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float2 s = make_float2(pv[i], pv[i + 1]);
-                    const float2 s2 = __fmul2_rn(s, s);
-                    float2 q = __ffma2_rn(s2, make_float2(k9, k9), make_float2(k7, k7));
-                    q = __ffma2_rn(q, s2, make_float2(k5, k5));
-                    q = __ffma2_rn(q, s2, make_float2(k3, k3));
-                    q = __ffma2_rn(q, s2, make_float2(k1, k1));
-                    const float2 y = __fmul2_rn(s, q);
-                    pv[i] = ex2_approx(y.x);
-                    pv[i + 1] = ex2_approx(y.y);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float2 x = __fmul2_rn(make_float2(pv[i], pv[i + 1]), soc2);
-                    const float2 y = __fmul2_rn(make_float2(tanh_approx(x.x), tanh_approx(x.y)), cl2);
-                    pv[i] = ex2_approx(y.x);
-                    pv[i + 1] = ex2_approx(y.y);
-                }
-            }
-            if (mbits != 0xffffffffu) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pv[i] = ((mbits >> i) & 1u) ? pv[i] : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) l2 = __fadd2_rn(l2, make_float2(pv[i], pv[i + 1]));
-            if (p.dropout_p > 0.f) {   // the 1/(1-p) factor is applied once, to the normalised output
-                const uint32_t pbase = (uint32_t)((drop_row + (unsigned long long)(j * TKV + part * 32)) >> 1);
-                const uint32_t thr32 = drop_thresh32(p.drop_thresh);
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const DropWords h = drop_words(seedmix, pbase + (i >> 1));
-                    pv[i] = (h.a >= thr32) ? pv[i] : 0.f;
-                    pv[i + 1] = (h.b >= thr32) ? pv[i + 1] : 0.f;
-                }
-            }
-            // the P buffer was last read by the PV MMA of tile j-2
-            mbar_wait(&p_empty[st], ph ^ 1);
-            uint8_t* pdst = sP + st * PTILE + (part >> 1) * TILE16 + row * 128;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int chunk = (part & 1) * 4 + g;
-                *reinterpret_cast<uint4*>(pdst + ((chunk ^ (row & 7)) << 4)) =
-                    make_uint4(pack_bf16(pv[g * 8], pv[g * 8 + 1]), pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]),
-                               pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]), pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]));
-            }
-            fence_proxy_async();        // make the generic-proxy smem writes of P visible to the tensor-core (async) proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[st]);
-        }
-        // ---- epilogue: total row sum over the four quarters, normalise, write O (ungated), Og (gated, head-merged) and LSE
-        s_xch[part * 128 + row] = l2.x + l2.y;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        const float l_tot = (s_xch[row] + s_xch[128 + row]) + (s_xch[256 + row] + s_xch[384 + row]);
-        mbar_wait(o_full, 0);
-        tc_fence_after();
-        uint32_t ro[16];
-        tmem_ld16(tO + part * 16 + lane_off, ro);
-        tmem_ld_wait();
-        if (qi < p.Np) {
-            const float inv = l_tot > 0.f ? p.keep_scale / l_tot : 0.f;
-            const float gt = p.gate ? p.gate[((size_t)b * p.Np + qi) * p.H + hh] : 1.f;
-            __nv_bfloat16* orow = p.o + ((size_t)bh * p.Np + qi) * DH + part * 16;
-            __nv_bfloat16* grow = p.og + ((size_t)b * p.Np + qi) * (size_t)(p.H * DH) + hh * DH + part * 16;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(ro[g * 8 + i]) * inv;
-                const uint4 u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                *reinterpret_cast<uint4*>(orow + g * 8) = u;
-                // gate the bf16-rounded output (what the backward pass sees) for consistency
-                *reinterpret_cast<uint4*>(grow + g * 8) =
-                    make_uint4(pack_bf16(bf16_lo(u.x) * gt, bf16_hi(u.x) * gt), pack_bf16(bf16_lo(u.y) * gt, bf16_hi(u.y) * gt),
-                               pack_bf16(bf16_lo(u.z) * gt, bf16_hi(u.z) * gt), pack_bf16(bf16_lo(u.w) * gt, bf16_hi(u.w) * gt));
-            }
-            if (part == 0) p.lse[(size_t)bh * p.Np + qi] = logf(l_tot);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ forward, two CTAs per SM
-// Same algorithm on 64-key tiles with HALF the resources per CTA — 320 threads (TMA producer, MMA issuer, 8 softmax warps: thread =
-// query row x key half, still 32 scores per thread and tile), 96 KB of shared memory, 256 TMEM columns (S[2] x 64 + O 64) — so that
-// two CTAs share an SM. The softmax of this attention flavour is bound by the CUDA-core pipes (tanh polynomial on FMA, exp on MUFU,
+// 64-key tiles and a CTA sized at HALF an SM — 320 threads (TMA producer, MMA issuer, 8 softmax warps: thread = query row x key half,
+// 32 scores per thread and tile), 96 KB of shared memory, 256 TMEM columns (S[2] x 64 + O 64) — so that two CTAs share an SM. (Rounds 1-2
+// ran 128-key tiles with 16 softmax warps and one CTA per SM: 152.6 us at cfg2 against 121.9 us, profiles/r2s_attn_bench.txt.) The softmax of this attention flavour is bound by the CUDA-core pipes (tanh polynomial on FMA, exp on MUFU,
 // dropout hash on ALU), and inside one CTA its phases run in lockstep on all softmax warps; two independent CTAs interleave their
 // phases on the schedulers, overlap one CTA's prologue / epilogue with the other's main loop, and give the SM two MMA issuers.
 // 64-key tiles also waste less of the ragged last tile (17 x 64 = 1088 keys for N' = 1056 instead of 9 x 128 = 1152).
@@ -473,7 +230,9 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             float amax = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) { pv[i] = __uint_as_float(r[i]); amax = fmaxf(amax, fabsf(pv[i])); }
-            // clamp * log2(e) * tanh(s * scale / clamp) as an odd polynomial in the raw score (see attn_fwd_tc_kernel)
+            // clamp * log2(e) * tanh(u), u = s * scale / clamp, evaluated as an odd polynomial in the RAW score s with the constants folded
+            // in: s * (k1 + s^2 (k3 + s^2 (k5 + ...))) — 4 (degree 5, |u| <= 0.15: exact to 1e-7) or 6 (degree 9, |u| <= 0.5) packed
+            // instructions per key pair; MUFU.TANH only when a warp's tile leaves that range
             if (__all_sync(0xffffffffu, amax <= lim5)) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
@@ -935,25 +694,14 @@ extern "C" int b200_attn_fwd(const b200_attn_fwd_args* a, b200_stream_t stream) 
     p.drop_stride = (a->Np + 1) & ~1;
     CUtensorMap tq, tk, tv;
     const long long rows = (long long)a->B * a->H * a->Np;
-    static const bool fwd64 = !(getenv("B200_ATTN_FWD64") && atoi(getenv("B200_ATTN_FWD64")) == 0);   // developer A/B switch, default on
-    if (fwd64) {
-        if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows, TKV2) || make_head_map(&tv, a->v, rows, TKV2)) return -1;
-        const int smem64 = TILE16 + 2 * KV2_STAGES * TILE8 + 2 * TILE16 + 160 + 1024 + 1024;
-        static DeviceOnce once64;
-        cudaError_t e64 = set_max_smem_once(once64, attn_fwd_tc64_kernel, smem64);
-        B200_REQUIRE(e64 == cudaSuccess, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e64));
-        dim3 grid64((a->Np + TQ - 1) / TQ, a->H, a->B);
-        B200_LAUNCH(attn_fwd_tc64_kernel, grid64, 320, smem64, st, tq, tk, tv, p);
-        return check_launch("attn_fwd_tc64_kernel");
-    }
-    if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows) || make_head_map(&tv, a->v, rows)) return -1;
-    const int smem = 5 * TILE16 + 2 * PTILE + 256 + 4096 + 1024;
+    if (make_head_map(&tq, a->q, rows) || make_head_map(&tk, a->k, rows, TKV2) || make_head_map(&tv, a->v, rows, TKV2)) return -1;
+    const int smem = TILE16 + 2 * KV2_STAGES * TILE8 + 2 * TILE16 + 160 + 1024 + 1024;   // Q, K/V rings, P[2], barriers, row sums, alignment slack
     static DeviceOnce once;
-    cudaError_t e = set_max_smem_once(once, attn_fwd_tc_kernel, smem);
+    cudaError_t e = set_max_smem_once(once, attn_fwd_tc64_kernel, smem);
     B200_REQUIRE(e == cudaSuccess, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     dim3 grid((a->Np + TQ - 1) / TQ, a->H, a->B);
-    B200_LAUNCH(attn_fwd_tc_kernel, grid, 576, smem, st, tq, tk, tv, p);
-    return check_launch("attn_fwd_tc_kernel");
+    B200_LAUNCH(attn_fwd_tc64_kernel, grid, 320, smem, st, tq, tk, tv, p);
+    return check_launch("attn_fwd_tc64_kernel");
 }
 
 // dO = dOg * gate, delta = <dO, O>, d_gate — defined in attn.cu

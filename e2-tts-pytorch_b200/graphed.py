@@ -72,13 +72,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         table = self.grad_sync.new_table() if self.grad_sync is not None else None
         n0 = lib.launch_count()
-        # Captured on a HIGH-priority stream: the kernel nodes keep the priority of the stream they were captured on, and the model forks
-        # the text sub-blocks onto a default- (= lowest-) priority side stream (modules.Transformer._run_layers). When both branches have
-        # thread blocks pending, the audio branch — twice as long, i.e. the critical path of every layer — is scheduled first and the text
-        # kernels fill what is left.
-        prio = int(__import__('os').environ.get('B200_GRAPH_PRIORITY', '-1'))
-        self._capture_stream = torch.cuda.Stream(dev, priority=prio)
-        with torch.cuda.graph(self.graph, stream=self._capture_stream):
+        with torch.cuda.graph(self.graph):
             self.out = self._eager()
             if self.grad_sync is not None:
                 static_grads = self.grad_sync.gather(table)   # recorded against the (still empty) chunk table

@@ -7,8 +7,9 @@
 //   warp 1 lane 0 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction,
 //                                    accumulators double-buffered in TMEM (2 x BN columns)
 //   warps 2..9    : epilogue       — tcgen05.ld 32x32b.x32 (one accumulator row per thread; two warps share a lane quadrant and
-//                                    split the tile columns), fused
-//                                    bias / AdaLN gate / row mask / residual / GEGLU(+dropout), 16-byte stores
+//                                    split the tile columns), fused bias / AdaLN gate / row mask / residual / GEGLU(+dropout);
+//                                    bf16 tiles leave through swizzled smem staging + TMA tile stores, fp32 split-K partials through
+//                                    vector reductions (red.global.add.v4.f32)
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile loop.
 // Operands may be K-major or MN-major (transposed storage) so that the backward contractions
 // dX = dY*W and dW = dY^T*X read activations exactly as they lie in HBM — no transposes are materialised.

@@ -884,6 +884,62 @@ extern "C" int b200_rowgate_bwd(const void* dy, const void* y, const float* cs, 
     return check_launch("rowgate_bwd_kernel");
 }
 
+// LinearFourierEmbed tail (e2_tts.py:368-386, attn_fourier_embed_input — a non-default switch of Transformer.__init__ :545-546):
+//   z = linear(x) [T, df + dr]  ->  out [T, 2*df + dr] = cat(sin(z[:, :df]), cos(z[:, :df]), z[:, df:]);  the Linear itself is b200_gemm.
+// One thread per 2 output columns; sin / cos in fp32 on the bf16 GEMM output (sincosf: arguments are not range-limited).
+namespace b200 {
+__global__ void __launch_bounds__(256) fourier_feat_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long ldz, __nv_bfloat16* __restrict__ out,
+                                                               long long T, int df, int dr) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
+    const int dout = 2 * df + dr;
+    const long long total = T * dout;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long t = i / dout;
+        const int c = (int)(i % dout);
+        const __nv_bfloat16* zr = z + t * ldz;
+        float v;
+        if (c < df) v = sinf(__bfloat162float(zr[c]));
+        else if (c < 2 * df) v = cosf(__bfloat162float(zr[c - df]));
+        else v = __bfloat162float(zr[c - df]);
+        out[i] = __float2bfloat16(v);
+    }
+}
+// dz[:, :df] = d_out[:, :df] * cos(z) - d_out[:, df:2df] * sin(z);  dz[:, df:] = d_out[:, 2df:]
+__global__ void __launch_bounds__(256) fourier_feat_bwd_kernel(const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ z,
+                                                               long long ldz, __nv_bfloat16* __restrict__ dz, long long T, int df, int dr) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
+    const int dout = 2 * df + dr, dz_cols = df + dr;
+    const long long total = T * ldz;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long t = i / ldz;
+        const int c = (int)(i % ldz);
+        float v = 0.f;                      // pitch padding columns of dz are zeroed (they feed the dX / dW GEMMs as K rows)
+        const __nv_bfloat16* g = d_out + t * dout;
+        if (c < df) {
+            float sn, cs;
+            sincosf(__bfloat162float(z[i]), &sn, &cs);
+            v = __bfloat162float(g[c]) * cs - __bfloat162float(g[c + df]) * sn;
+        } else if (c < dz_cols) {
+            v = __bfloat162float(g[c + df]);
+        }
+        dz[i] = __float2bfloat16(v);
+    }
+}
+}  // namespace b200
+
+extern "C" int b200_fourier_feat_fwd(const void* z, int64_t ldz, void* out, int64_t T, int32_t df, int32_t dr, b200_stream_t stream) {
+    B200_REQUIRE(z && out && T > 0 && df >= 0 && dr >= 0 && df + dr > 0 && ldz >= df + dr, "fourier_feat_fwd: bad arguments");
+    B200_LAUNCH(fourier_feat_fwd_kernel, grid_for(T * (2 * df + dr)), 256, 0, reinterpret_cast<cudaStream_t>(stream), (const __nv_bfloat16*)z,
+                (long long)ldz, (__nv_bfloat16*)out, (long long)T, df, dr);
+    return check_launch("fourier_feat_fwd_kernel");
+}
+extern "C" int b200_fourier_feat_bwd(const void* d_out, const void* z, int64_t ldz, void* dz, int64_t T, int32_t df, int32_t dr, b200_stream_t stream) {
+    B200_REQUIRE(d_out && z && dz && T > 0 && df >= 0 && dr >= 0 && df + dr > 0 && ldz >= df + dr, "fourier_feat_bwd: bad arguments");
+    B200_LAUNCH(fourier_feat_bwd_kernel, grid_for(T * ldz), 256, 0, reinterpret_cast<cudaStream_t>(stream), (const __nv_bfloat16*)d_out,
+                (const __nv_bfloat16*)z, (long long)ldz, (__nv_bfloat16*)dz, (long long)T, df, dr);
+    return check_launch("fourier_feat_bwd_kernel");
+}
+
 extern "C" int b200_cast_rows(const float* src, void* dst, int64_t rows, int32_t cols, int32_t ld, b200_stream_t stream) {
     B200_REQUIRE(src && dst && rows > 0 && cols > 0 && ld >= cols, "cast_rows: bad arguments");
     B200_LAUNCH(cast_rows_kernel, grid_for(rows * ld), 256, 0, reinterpret_cast<cudaStream_t>(stream), src, (__nv_bfloat16*)dst, rows, cols, ld);

@@ -259,6 +259,19 @@ class _PackTable:
 # ----------------------------------------------------------------------------------------------------------------------
 
 
+class LinearFourierEmbed(Module):
+    """e2_tts.py:368-386 — parameter holder (`linear.weight`, reference state_dict key `layers.{i}.0.4.linear.weight`); the arithmetic is
+    ops.FourierLinear (tcgen05 GEMM + b200_fourier_feat_*)."""
+
+    def __init__(self, dim, p=0.5):
+        super().__init__()
+        assert p <= 1.
+        dim_fourier = int(p * dim)
+        dim_rest = dim - (dim_fourier * 2)
+        self.linear = nn.Linear(dim, dim_fourier + dim_rest, bias=False)
+        self.split_dims = (dim_fourier, dim_rest)
+
+
 class Transformer(Module):
     """Multistream flow-matching backbone — constructor and forward signature of the reference's Transformer
     (e2_tts.py:518-952). Non-default research switches raise (no kernels, no fallback)."""
@@ -276,8 +289,6 @@ class Transformer(Module):
             _unsupported('has_freq_axis', has_freq_axis, 'e2_tts.py:533')
         if attn_laser:
             _unsupported('attn_laser', attn_laser, 'e2_tts.py:543')
-        if attn_fourier_embed_input:
-            _unsupported('attn_fourier_embed_input', attn_fourier_embed_input, 'e2_tts.py:545')
         if dict(attn_kwargs) != dict(gate_value_heads=True, softclamp_logits=True):
             _unsupported('attn_kwargs', attn_kwargs, 'e2_tts.py:548-551')
         if dict(ff_kwargs):
@@ -325,7 +336,7 @@ class Transformer(Module):
                 DepthwiseConv(dim, kernel_size=kernel_size),
                 norm_klass(dim),
                 Attention(dim, heads, dim_head, not first),
-                nn.Identity(),
+                LinearFourierEmbed(dim, p=attn_fourier_embed_input_frac) if attn_fourier_embed_input else nn.Identity(),   # :639
                 post_klass(),
                 norm_klass(dim),
                 FeedForward(dim, ff_mult, dropout),
@@ -408,6 +419,10 @@ class Transformer(Module):
                 w2 = e(din, inner)
                 tab.add(ff.ff[2].weight, w2)
                 L[pre] = dict(qkv=qkv, out=out_w, w1=w1, b1=b1, w2=w2)
+            if isinstance(speech[4], LinearFourierEmbed):
+                lfe = e(*speech[4].linear.weight.shape)
+                tab.add(speech[4].linear.weight, lfe)
+                L['a']['lfe'] = lfe
             if speech[0] is not None:
                 L['skip'] = e(d, 2 * d)
                 tab.add(speech[0].weight, L['skip'])
@@ -514,8 +529,10 @@ class Transformer(Module):
             y = ops.DwConv.apply(br, conv.dw_conv1d[0].weight, conv.dw_conv1d[0].bias, mask_u8, B, Np)
             return depth(rest, y, beta)
 
-        def sub_attn(res, hcm, gain, mode, attn, pk, vf, colscale):
+        def sub_attn(res, hcm, gain, mode, attn, pk, vf, colscale, lfe=None):
             br, rest, beta = width(res, hcm, gain, mode)
+            if lfe is not None:   # attn_input_fourier_embed (:909): between the attention norm (fused into the width kernel) and the attention
+                br = ops.FourierLinear.apply(br, lfe.linear.weight, pk['lfe'], *lfe.split_dims)
             mix = attn.to_value_residual_mix
             og, v = ops.Attention.apply(br, attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_v_head_gate.weight,
                                         attn.to_v_head_gate.bias, mix[0].weight if mix is not None else None,
@@ -580,7 +597,8 @@ class Transformer(Module):
                 g_an, g_az, g_fn, g_fz = speech[2].g, None, speech[6].g, None
                 mode = 1
             xs = sub_conv(xs, shc[0], speech[1])  # :900-902
-            xs, v_first = sub_attn(xs, shc[1], g_an, mode, speech[3], pk['a'], v_first, g_az)  # :906-916
+            xs, v_first = sub_attn(xs, shc[1], g_an, mode, speech[3], pk['a'], v_first, g_az,
+                                   speech[4] if isinstance(speech[4], LinearFourierEmbed) else None)  # :906-916
             xs = sub_ff(xs, shc[2], g_fn, mode, speech[7], pk['a'], g_fz)  # :936-939
         assert not skips
         return xs

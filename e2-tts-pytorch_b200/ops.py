@@ -433,6 +433,36 @@ def _rowgate_bwd(dy, y, cs, mask, B, rpb, D, want_bias=False):
     return (dz, d_cs, d_bias) if want_bias else (dz, d_cs)
 
 
+class FourierLinear(Function):
+    """LinearFourierEmbed (e2_tts.py:368-386): cat(sin(f), cos(f), rest) of Linear(dim -> df + dr, no bias)(x) — the attention-input
+    transform of Transformer(attn_fourier_embed_input=True) (:545-546, :639, applied at :909)."""
+
+    @staticmethod
+    def forward(ctx, x, w, wpack, df, dr):
+        T, D = x.shape
+        n = df + dr
+        ld = (n + 7) // 8 * 8
+        z = gemm(x, wpack, T, n, D, ldd=ld)
+        out = torch.empty((T, 2 * df + dr), device=x.device, dtype=BF16)
+        lib.call('b200_fourier_feat_fwd', z, ld, out, T, df, dr, _stream())
+        ctx.save_for_backward(x, wpack, z)
+        ctx.meta = (df, dr, ld)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out):
+        x, wpack, z = ctx.saved_tensors
+        df, dr, ld = ctx.meta
+        T, D = x.shape
+        n = df + dr
+        dz = torch.empty((T, ld), device=x.device, dtype=BF16)
+        lib.call('b200_fourier_feat_bwd', _c(d_out), z, ld, dz, T, df, dr, _stream())
+        dx = gemm(dz, wpack, T, D, n, lda=ld, b_mn=True)
+        dW = grad_weight(dz, x, T, n, D, ldy=ld)
+        return dx, dW, None, None, None
+
+
 class OutProj(Function):
     """Attention to_out (no bias) with the fused epilogue: zero padded rows (A.4 step 6) and AdaLNZero gate (:346-351)."""
 

@@ -267,6 +267,11 @@ int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t stream);
 int b200_rowgate_bwd(const void* dy, const void* y, const float* cs, const uint8_t* mask, void* dz, float* d_cs,
                      float* d_bias, int32_t B, int32_t rows_per_batch, int32_t D, b200_stream_t stream);
 int b200_cast_rows(const float* src, void* dst, int64_t rows, int32_t cols, int32_t ld, b200_stream_t stream);
+/* LinearFourierEmbed (e2_tts.py:368-386; Transformer(attn_fourier_embed_input=True) :545-546, applied to the attention input :909):
+ * the Linear(dim -> df + dr, no bias) is b200_gemm; this is its tail, z bf16 [T, df + dr] (row pitch ldz) ->
+ * out bf16 [T, 2*df + dr] = cat(sin(z[:, :df]), cos(z[:, :df]), z[:, df:]). bwd: d_out -> dz bf16 [T, ldz] (padding columns zeroed). */
+int b200_fourier_feat_fwd(const void* z, int64_t ldz, void* out, int64_t T, int32_t df, int32_t dr, b200_stream_t stream);
+int b200_fourier_feat_bwd(const void* d_out, const void* z, int64_t ldz, void* dz, int64_t T, int32_t df, int32_t dr, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Small-batch fp32 linear (time conditioning path: time_cond_mlp e2_tts.py:621-625, all AdaptiveRMSNorm /

@@ -190,6 +190,14 @@ def hyper_depth(rest, beta, y):  # A.5 depth connection
 # '(b s) n d' layout is a pure relabelling (A.5), all cross-stream ops are per token.
 
 
+def linear_fourier_embed(sd, p, x):  # LinearFourierEmbed :368-386
+    w = sd[p + '.linear.weight']                      # (dim_fourier + dim_rest, dim), no bias :381
+    dim_fourier = x.shape[-1] - w.shape[0]            # 2 * dim_fourier + dim_rest == dim  (:378-379)
+    hiddens = _rs(x @ w.t())                          # :385
+    fourier, rest = hiddens[..., :dim_fourier], hiddens[..., dim_fourier:]
+    return _rs(torch.cat((fourier.sin(), fourier.cos(), rest), dim=-1))  # :386
+
+
 def transformer_forward(sd, cfg: TransformerCfg, x, times=None, mask=None, text_embed=None, prefix='transformer'):
     P = prefix
     b, n, d = x.shape
@@ -264,7 +272,10 @@ def transformer_forward(sd, cfg: TransformerCfg, x, times=None, mask=None, text_
         br, rest, beta = hyper_width(sd, hp + '.0.0', xs, S)  # :900-902
         xs = hyper_depth(rest, beta, depthwise_conv(sd, sp + '.1', _rs(br), mask))
         br, rest, beta = hyper_width(sd, hp + '.0.1', xs, S)  # :906-916
-        out, vals = attention(sd, sp + '.3', norm(sp + '.2', br), mask, freqs, attn_first,
+        a_in = norm(sp + '.2', br)
+        if (sp + '.4.linear.weight') in sd:  # attn_input_fourier_embed :909 (Transformer(attn_fourier_embed_input=True), :545-546, :639)
+            a_in = linear_fourier_embed(sd, sp + '.4', a_in)
+        out, vals = attention(sd, sp + '.3', a_in, mask, freqs, attn_first,
                               cfg.heads, cfg.dim_head, cfg.softclamp)
         xs = hyper_depth(rest, beta, post(sp + '.5', out))
         attn_first = vals if attn_first is None else attn_first

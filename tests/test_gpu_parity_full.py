@@ -215,9 +215,9 @@ def test_attention_core_vs_fp32_softmax(pkg, Np, H, big_logits):
 
 # ----------------------------------------------------------------------------------------------------------------------
 # (a), (e) whole model at the BASELINE widths against the oracle run on the host CPU
-def _whole_model(pkg, tkw, B, N, lens, seed, tol_pred=3e-2):
+def _whole_model(pkg, tkw, B, N, lens, seed, tol_pred=3e-2, model_kw=None):
     torch.manual_seed(seed)
-    model = pkg.E2TTS(transformer=dict(dropout=0., max_seq_len=N, **tkw), use_vocos=False)
+    model = pkg.E2TTS(transformer=dict(dropout=0., max_seq_len=N, **tkw, **(model_kw or {})), use_vocos=False)
     # dyn_scale 0.05 (5x the reference's init of the hyper-connections' dynamic scales): with the 0.5 of the 2-layer fixtures a depth-8
     # stack amplifies bf16 rounding of the residual streams ~10x — the fp32 oracle with its OWN stage outputs rounded to bf16
     # (O.STAGE_ROUND) then moves its prediction by 12.6 %, exactly what the kernels showed (gpurun_out/r2b_pytest.log). The probe below
@@ -278,6 +278,13 @@ def test_e2tts_cfg3_kernels_vs_oracle(pkg):
     """cfg3 / cfg5's width (d1024, 16 heads, dim_text 512) at N = 2048 (N' = 2080): hc_width_*<4,false>, 16-head qkv packing,
     17-tile attention; depth 2 keeps the host oracle within seconds."""
     _whole_model(pkg, dict(dim=1024, depth=2, heads=16), B=1, N=2048, lens=[1900], seed=50)
+
+
+def test_e2tts_attn_fourier_embed_input_vs_oracle(pkg):
+    """SURVEY §8f row 4, first variant: Transformer(attn_fourier_embed_input=True) (e2_tts.py:545-546; LinearFourierEmbed :368-386 on the
+    attention input, :909) — tcgen05 GEMM + b200_fourier_feat_* against the oracle, which tests/test_oracle_vs_reference.py pins to the
+    reference's own code with the switch on. Loss, prediction and every parameter gradient incl. `layers.{i}.0.4.linear.weight`."""
+    _whole_model(pkg, dict(dim=256, depth=2, heads=4), B=2, N=224, lens=[224, 170], seed=60, model_kw=dict(attn_fourier_embed_input=True))
 
 
 # ----------------------------------------------------------------------------------------------------------------------

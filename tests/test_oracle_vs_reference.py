@@ -61,6 +61,31 @@ def test_text_dropped_branch_vs_reference():
             assert (p.grad - sd[k].grad).abs().max() <= 2e-4 * p.grad.abs().max() + 1e-7, k
 
 
+def test_attn_fourier_embed_input_vs_reference():
+    """Transformer(attn_fourier_embed_input=True) (e2_tts.py:545-546, LinearFourierEmbed :368-386 applied at :909) — the reference's own
+    code, no third-party leaf involved: loss, prediction and every gradient incl. `layers.{i}.0.4.linear.weight`."""
+    ref = load_reference()
+    torch.manual_seed(23)
+    kw = dict(dim=128, depth=2, heads=2)
+    model = ref.E2TTS(transformer=dict(dropout=0., max_seq_len=128, attn_fourier_embed_input=True, **kw), use_vocos=False)
+    model.load_state_dict(O.randomize_zero_init(model.state_dict(), seed=23))
+    assert 'transformer.layers.0.0.4.linear.weight' in model.state_dict()
+    mel = torch.randn(2, 64, 100)
+    lens_t = torch.tensor([64, 45])
+    text = ['abc', 'defgh ij']
+    out, rec = run_reference_forward(ref, model, mel, text, lens=lens_t, drop_text_cond=False)
+    out.loss.backward()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    o = O.e2tts_forward(sd, O.TransformerCfg(**kw), mel, O.list_str_to_tensor(text), lens=lens_t, drop_text_cond=False, **rec)
+    o['loss'].backward()
+    assert abs(float(o['loss']) - float(out.loss)) <= 1e-5 * abs(float(out.loss))
+    assert rel_l2(o['pred'], out.pred_flow) < 1e-4
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert (p.grad - sd[k].grad).abs().max() <= 2e-4 * p.grad.abs().max() + 1e-7, k
+    assert float(sd['transformer.layers.1.0.4.linear.weight'].grad.abs().max()) > 0
+
+
 @pytest.mark.parametrize('steps,cfg_strength,duration', [(4, 1.0, 48), (3, 0.0, 40), (5, 2.5, [50, 37])])
 def test_sample_vs_reference(steps, cfg_strength, duration):
     """E2TTS.sample (:1332-1466): midpoint grid, CFG with the APG orthogonal projection (:1303-1330, :113-124), the

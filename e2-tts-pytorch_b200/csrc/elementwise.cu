@@ -940,6 +940,109 @@ extern "C" int b200_fourier_feat_bwd(const void* d_out, const void* z, int64_t l
     return check_launch("fourier_feat_bwd_kernel");
 }
 
+// InterpolatedCharacterEmbed (e2_tts.py:414-482; E2TTS(interpolated_text=True) :1135, :1233): per sample, the embeddings of its Lt valid
+// characters are stretched to its La audio frames by linear interpolation (F.interpolate 'bilinear', align_corners=False, :237-244, :459)
+// and the stretched ABSOLUTE text positions linspace(0, Lt, La) (:460) go through abs_pos_mlp = Linear(1, d) -> SiLU -> Linear(d, d)
+// (:424-429, :477). This kernel produces the two GEMM-side operands of  te = mask * (Linear2(h1) + lerp):
+//   lerp [B*N, D] bf16 (rows n >= La: 0)  and  h1 = silu(pos * w1 + b1) [B*N, D] bf16 (pos = 0 for n >= La, as the reference's padding).
+namespace b200 {
+struct InterpP {
+    const int* ids;        // [B, nt] compacted character ids (the first Lt[b] entries are valid)
+    const int *Lt, *La;    // [B]
+    const float *emb, *w1, *b1;
+    int B, N, nt, D, V;
+};
+__device__ __forceinline__ void interp_coords(int n, int Lt, int La, int& i0, int& i1, float& lam, float& pos) {
+    // area_pixel_compute_source_index(scale = Lt / La, align_corners = false): src = max((n + 0.5) * scale - 0.5, 0)
+    const float scale = (float)Lt / (float)La;
+    const float src = fmaxf(((float)n + 0.5f) * scale - 0.5f, 0.f);
+    i0 = min((int)src, Lt - 1);
+    i1 = i0 + (i0 < Lt - 1 ? 1 : 0);
+    lam = src - (float)i0;
+    // torch.linspace(0, Lt, La): step = Lt / (La - 1); first half counts up from 0, second half down from Lt
+    const float step = La > 1 ? (float)Lt / (float)(La - 1) : 0.f;
+    pos = (n < La / 2 || La == 1) ? (float)n * step : (float)Lt - (float)(La - 1 - n) * step;
+}
+__global__ void __launch_bounds__(256) interp_text_fwd_kernel(const InterpP p, __nv_bfloat16* __restrict__ lerp, __nv_bfloat16* __restrict__ h1) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
+    const long long total = (long long)p.B * p.N * p.D;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i % p.D);
+        const long long row = i / p.D;
+        const int n = (int)(row % p.N), b = (int)(row / p.N);
+        const int Lt = p.Lt[b], La = min(p.La[b], p.N);
+        float e = 0.f, pos = 0.f;
+        if (n < La && Lt > 0) {
+            int i0, i1; float lam;
+            interp_coords(n, Lt, La, i0, i1, lam, pos);
+            const int t0 = p.ids[(size_t)b * p.nt + i0], t1 = p.ids[(size_t)b * p.nt + i1];
+            e = (1.f - lam) * __ldg(p.emb + (size_t)t0 * p.D + c) + lam * __ldg(p.emb + (size_t)t1 * p.D + c);
+        }
+        const float pre = pos * __ldg(p.w1 + c) + __ldg(p.b1 + c);
+        lerp[i] = __float2bfloat16(e);
+        h1[i] = __float2bfloat16(pre / (1.f + __expf(-pre)));
+    }
+}
+// backward: d_emb[id] += weights * d_lerp (atomics into the zero-initialised table gradient); through SiLU and Linear(1, d):
+// d_pre = d_h1 * silu'(pre), dw1[c] += sum_rows d_pre * pos, db1[c] += sum_rows d_pre. One thread per channel marching ROWS rows.
+constexpr int INTERP_ROWS = 64;
+__global__ void __launch_bounds__(256) interp_text_bwd_kernel(const InterpP p, const __nv_bfloat16* __restrict__ d_lerp, const __nv_bfloat16* __restrict__ d_h1,
+                                                              float* __restrict__ d_emb, float* __restrict__ dw1, float* __restrict__ db1) {
+    pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= p.D) return;
+    const long long r0 = (long long)blockIdx.y * INTERP_ROWS, r1 = min((long long)p.B * p.N, r0 + INTERP_ROWS);
+    const float w1 = __ldg(p.w1 + c), b1 = __ldg(p.b1 + c);
+    float gw = 0.f, gb = 0.f;
+    for (long long row = r0; row < r1; ++row) {
+        const int n = (int)(row % p.N), b = (int)(row / p.N);
+        const int Lt = p.Lt[b], La = min(p.La[b], p.N);
+        float pos = 0.f;
+        if (n < La && Lt > 0) {
+            int i0, i1; float lam;
+            interp_coords(n, Lt, La, i0, i1, lam, pos);
+            const float g = __bfloat162float(d_lerp[row * p.D + c]);
+            const int t0 = p.ids[(size_t)b * p.nt + i0], t1 = p.ids[(size_t)b * p.nt + i1];
+            atomicAdd(d_emb + (size_t)t0 * p.D + c, (1.f - lam) * g);
+            atomicAdd(d_emb + (size_t)t1 * p.D + c, lam * g);
+        }
+        const float pre = pos * w1 + b1;
+        const float sg = 1.f / (1.f + __expf(-pre));
+        const float dpre = __bfloat162float(d_h1[row * p.D + c]) * sg * (1.f + pre * (1.f - sg));
+        gw += dpre * pos;
+        gb += dpre;
+    }
+    atomicAdd(dw1 + c, gw);
+    atomicAdd(db1 + c, gb);
+}
+}  // namespace b200
+
+static int fill_interp(InterpP& p, const b200_interp_text_args* a) {
+    B200_REQUIRE(a && a->ids && a->text_len && a->audio_len && a->emb && a->w1 && a->b1, "interp_text: null pointer");
+    B200_REQUIRE(a->B > 0 && a->N > 0 && a->nt > 0 && a->D > 0 && a->vocab > 0, "interp_text: bad shape");
+    p.ids = a->ids; p.Lt = a->text_len; p.La = a->audio_len; p.emb = a->emb; p.w1 = a->w1; p.b1 = a->b1;
+    p.B = a->B; p.N = a->N; p.nt = a->nt; p.D = a->D; p.V = a->vocab;
+    return 0;
+}
+extern "C" int b200_interp_text_fwd(const b200_interp_text_args* a, b200_stream_t stream) {
+    InterpP p{};
+    if (fill_interp(p, a)) return -1;
+    B200_REQUIRE(a->lerp && a->h1, "interp_text_fwd: null output");
+    B200_LAUNCH(interp_text_fwd_kernel, grid_for((long long)a->B * a->N * a->D), 256, 0, reinterpret_cast<cudaStream_t>(stream), p,
+                (__nv_bfloat16*)a->lerp, (__nv_bfloat16*)a->h1);
+    return check_launch("interp_text_fwd_kernel");
+}
+extern "C" int b200_interp_text_bwd(const b200_interp_text_args* a, b200_stream_t stream) {
+    InterpP p{};
+    if (fill_interp(p, a)) return -1;
+    B200_REQUIRE(a->d_lerp && a->d_h1 && a->d_emb && a->d_w1 && a->d_b1, "interp_text_bwd: null pointer");
+    const long long rows = (long long)a->B * a->N;
+    dim3 grid((a->D + 255) / 256, (unsigned)((rows + INTERP_ROWS - 1) / INTERP_ROWS));
+    B200_LAUNCH(interp_text_bwd_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), p, (const __nv_bfloat16*)a->d_lerp,
+                (const __nv_bfloat16*)a->d_h1, a->d_emb, a->d_w1, a->d_b1);
+    return check_launch("interp_text_bwd_kernel");
+}
+
 extern "C" int b200_cast_rows(const float* src, void* dst, int64_t rows, int32_t cols, int32_t ld, b200_stream_t stream) {
     B200_REQUIRE(src && dst && rows > 0 && cols > 0 && ld >= cols, "cast_rows: bad arguments");
     B200_LAUNCH(cast_rows_kernel, grid_for(rows * ld), 256, 0, reinterpret_cast<cudaStream_t>(stream), src, (__nv_bfloat16*)dst, rows, cols, ld);

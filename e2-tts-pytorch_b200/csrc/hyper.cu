@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
                     }
                 }
                 const float dot = warp_sum(hsum(dot2));
-                const f2 nk2 = splat(-(cn * cn * cn * invD * dot)), cn2 = splat(cn);
+                const f2 nk2 = splat(-((cn * cn * invD) * (cn * dot))), cn2 = splat(cn);   // same ordering: finite for an all-zero branch row
 #pragma unroll
                 for (int v = 0; v < VPT; ++v)
 #pragma unroll
@@ -540,7 +540,9 @@ __global__ void __launch_bounds__(256, (VPT == 1) ? 2 : 1) hc_width_bwd_kernel(c
                     Rs += __shfl_sync(0xffffffffu, term, s * HT + t);
                     cw[s][t] = __shfl_sync(0xffffffffu, cws, s * HT + t);
                 }
-                nk3[s] = -(st.inv[s] * st.inv[s] * st.inv[s] * invD * Rs);
+                // (an all-zero stream has inv = sqrt(D) / 1e-12: inv^3 overflows fp32 and inf * 0 would poison the row — keep the product
+                //  ordered so that the zero factor <u, r> is applied before the third power; x-transformers' F.normalize backward is finite too)
+                nk3[s] = -((st.inv[s] * st.inv[s] * invD) * (st.inv[s] * Rs));
             }
         }
         const float bpv[HS] = {bprev.x, bprev.y, bprev.z, bprev.w};

@@ -225,6 +225,34 @@ class CharacterEmbed(Module):  # e2_tts.py:390-412
         return text.to(torch.int32).contiguous()
 
 
+class InterpolatedCharacterEmbed(Module):  # e2_tts.py:414-482 (E2TTS(interpolated_text=True), :1135, :1233)
+    """Parameter holder with the reference's state_dict keys (`embed.weight`, `abs_pos_mlp.1.*`, `abs_pos_mlp.3.*`); the arithmetic is
+    ops.InterpText. Character ids index the table directly (no +1 shift, :446) and padding (-1) is dropped per sample (:445)."""
+
+    def __init__(self, dim, num_embeds=256):
+        super().__init__()
+        self.dim = dim
+        self.embed = nn.Embedding(num_embeds, dim)
+        self.abs_pos_mlp = nn.Sequential(nn.Identity(), nn.Linear(1, dim), nn.SiLU(), nn.Linear(dim, dim))   # index 0 = the reference's Rearrange
+
+    def embed_bf16(self, text, max_seq_len, mask=None):
+        """text (b, nt) int64 with -1 padding, mask (b, n) bool | None -> bf16 [b * n, dim] (rows of masked frames are zero)."""
+        B = text.shape[0]
+        valid = text >= 0
+        order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)        # valid characters first, original order kept (:445)
+        ids_c = torch.gather(text.clamp(min=0), 1, order).to(torch.int32).contiguous()
+        text_len = valid.sum(dim=1).to(torch.int32)
+        if exists(mask):
+            audio_len = mask.sum(dim=1).to(torch.int32)                           # :455-457
+            mask_u8 = mask.to(torch.uint8).contiguous()
+        else:
+            audio_len = torch.full((B,), max_seq_len, device=text.device, dtype=torch.int32)
+            mask_u8 = None
+        lin1, lin2 = self.abs_pos_mlp[1], self.abs_pos_mlp[3]
+        return ops.InterpText.apply(ids_c, text_len, audio_len, mask_u8, self.embed.weight, lin1.weight, lin1.bias, lin2.weight, lin2.bias,
+                                    B, max_seq_len)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # weight packing: one kernel launch per forward refreshes every bf16 GEMM operand from the fp32 parameters
 
@@ -860,8 +888,6 @@ class E2TTS(Module):
             _unsupported('num_freq_tokens', num_freq_tokens, 'e2_tts.py:1130')
         if concat_cond:
             _unsupported('concat_cond', concat_cond, 'e2_tts.py:1134')
-        if interpolated_text:
-            _unsupported('interpolated_text', interpolated_text, 'e2_tts.py:1135')
         if odeint_kwargs.get('method', 'midpoint') not in ('midpoint', 'euler'):
             _unsupported('odeint_kwargs', odeint_kwargs, 'e2_tts.py:1122-1126 (fixed-grid midpoint/euler only)')
         self.num_freq_tokens, self.has_freq_axis = 1, False
@@ -888,7 +914,8 @@ class E2TTS(Module):
         self.to_pred = nn.Linear(dim, num_channels)
         self.tokenizer, text_num_embeds = _resolve_tokenizer(tokenizer, text_num_embeds)
         self.cond_drop_prob = cond_drop_prob
-        self.embed_text = CharacterEmbed(dim_text, num_embeds=text_num_embeds, **char_embed_kwargs)
+        text_embed_klass = InterpolatedCharacterEmbed if interpolated_text else CharacterEmbed          # :1233
+        self.embed_text = text_embed_klass(dim_text, num_embeds=text_num_embeds, **char_embed_kwargs)
         self.register_buffer('zero', torch.tensor(0.), persistent=False)
         self.velocity_consistency_weight = velocity_consistency_weight
         # Vocos is a separate pretrained network fetched from the HF hub (e2_tts.py:1244): out of scope.
@@ -924,10 +951,13 @@ class E2TTS(Module):
 
     def _embed(self, A, B, N, times, mask, text, drop_text_cond, pk):
         h = ops.StemLinear.apply(A, self.proj_in.weight, self.proj_in.bias, self.cond_proj_in.weight, self.cond_proj_in.bias, pk['stem'])
-        ids = None
+        ids, te = None, None
         if exists(text) and not drop_text_cond:
-            ids = self.embed_text.ids(text, N)
-        y = self.transformer._forward_from_h(h, B, N, times, mask, text_ids=ids, text_embed_module=self.embed_text)
+            if isinstance(self.embed_text, InterpolatedCharacterEmbed):
+                te = self.embed_text.embed_bf16(text, N, mask)      # :1283 embed_text(text, seq_len, mask = mask)
+            else:
+                ids = self.embed_text.ids(text, N)
+        y = self.transformer._forward_from_h(h, B, N, times, mask, text_ids=ids, text_embed_module=self.embed_text, te_bf16=te)
         return y, pk
 
     @_on_module_device

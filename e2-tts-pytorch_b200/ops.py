@@ -692,6 +692,45 @@ class TextStem(Function):
         return None, d_emb, d_reg, None, None, None
 
 
+class InterpText(Function):
+    """InterpolatedCharacterEmbed (e2_tts.py:414-482): te = mask * (interpolate(embed(valid chars), audio_len) + abs_pos_mlp(linspace(0, Lt, La))).
+    b200_interp_text_fwd stretches the embeddings and evaluates Linear(1, d) + SiLU per token; Linear(d, d) + bias + the stretched
+    embeddings (residual) + the row mask are ONE tcgen05 GEMM with its fused epilogue. Returns bf16 [B*N, d]."""
+
+    @staticmethod
+    def forward(ctx, ids_c, text_len, audio_len, mask_u8, emb, w1, b1, w2, b2, B, N):
+        V, D = emb.shape
+        dev = emb.device
+        nt = ids_c.shape[1]
+        lerp = torch.empty((B * N, D), device=dev, dtype=BF16)
+        h1 = torch.empty((B * N, D), device=dev, dtype=BF16)
+        a = lib.make_args('b200_interp_text_args', ids=ids_c, text_len=text_len, audio_len=audio_len, emb=emb, w1=w1, b1=b1,
+                          B=B, N=N, nt=nt, D=D, vocab=V, lerp=lerp, h1=h1)
+        lib.call('b200_interp_text_fwd', a, _stream())
+        w2p = w2.detach().to(BF16).contiguous()          # a d x d operand, re-cast per call (non-default variant: not in the pack table)
+        te = gemm(h1, w2p, B * N, D, D, bias=b2, rowmask=mask_u8, resid=lerp, ldr=D)
+        ctx.save_for_backward(ids_c, text_len, audio_len, mask_u8, emb, w1, b1, w2p, h1)
+        ctx.meta = (B, N)
+        return te
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_te):
+        ids_c, text_len, audio_len, mask_u8, emb, w1, b1, w2p, h1 = ctx.saved_tensors
+        B, N = ctx.meta
+        V, D = emb.shape
+        T = B * N
+        dz, _ = _rowgate_bwd(_c(d_te), d_te, None, mask_u8, B, N, D)        # dz = d_te * mask (the epilogue's row mask)
+        d_h1 = gemm(dz, w2p, T, D, D, b_mn=True)
+        dW2 = grad_weight(dz, h1, T, D, D)
+        db2 = colsum(dz, T, D, D)
+        d_emb, dw1, db1 = _zeros((V, D), emb.device), _zeros(D, emb.device), _zeros(D, emb.device)
+        a = lib.make_args('b200_interp_text_args', ids=ids_c, text_len=text_len, audio_len=audio_len, emb=emb, w1=w1, b1=b1,
+                          B=B, N=N, nt=ids_c.shape[1], D=D, vocab=V, d_lerp=dz, d_h1=d_h1, d_emb=d_emb, d_w1=dw1, d_b1=db1)
+        lib.call('b200_interp_text_bwd', a, _stream())
+        return None, None, None, None, d_emb, dw1.view_as(w1), db1, dW2, db2, None, None
+
+
 class FinalNorm(Function):
     """drop registers -> sum residual streams -> final RMSNorm (e2_tts.py:943-952). -> bf16 [B*N, D]"""
 

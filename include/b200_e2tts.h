@@ -267,6 +267,24 @@ int b200_flow_loss_bwd(const b200_flow_loss_args* a, b200_stream_t stream);
 int b200_rowgate_bwd(const void* dy, const void* y, const float* cs, const uint8_t* mask, void* dz, float* d_cs,
                      float* d_bias, int32_t B, int32_t rows_per_batch, int32_t D, b200_stream_t stream);
 int b200_cast_rows(const float* src, void* dst, int64_t rows, int32_t cols, int32_t ld, b200_stream_t stream);
+/* InterpolatedCharacterEmbed (e2_tts.py:414-482; E2TTS(interpolated_text=True) :1135, :1233): the per-token front half of
+ *   te[b, n] = mask[b, n] * ( lerp[b, n] + Linear2( silu( pos[b, n] * w1 + b1 ) ) )
+ * ids: int32 [B, nt] COMPACTED character ids (the first text_len[b] are the valid ones, :445-447); audio_len[b] = frames of sample b
+ * (mask.sum or N, :455-457). fwd writes lerp bf16 [B*N, D] = linear interpolation of the sample's embeddings to audio_len[b] frames
+ * (F.interpolate 'bilinear', align_corners=False; rows beyond audio_len: 0) and h1 bf16 [B*N, D] = silu(pos * w1 + b1) with
+ * pos = linspace(0, text_len, audio_len) (0 beyond). Linear2 (+ bias, + lerp as residual, row mask) is b200_gemm.
+ * bwd: d_lerp, d_h1 bf16 [B*N, D] -> d_emb fp32 [vocab, D], d_w1, d_b1 fp32 [D] (all ADDED into zero-initialised buffers). */
+typedef struct {
+    const int32_t* ids; const int32_t *text_len, *audio_len;
+    const float *emb, *w1, *b1;
+    int32_t B, N, nt, D, vocab;
+    void *lerp, *h1;                       /* forward outputs */
+    const void *d_lerp, *d_h1;             /* backward inputs */
+    float *d_emb, *d_w1, *d_b1;
+} b200_interp_text_args;
+int b200_interp_text_fwd(const b200_interp_text_args* a, b200_stream_t stream);
+int b200_interp_text_bwd(const b200_interp_text_args* a, b200_stream_t stream);
+
 /* LinearFourierEmbed (e2_tts.py:368-386; Transformer(attn_fourier_embed_input=True) :545-546, applied to the attention input :909):
  * the Linear(dim -> df + dr, no bias) is b200_gemm; this is its tail, z bf16 [T, df + dr] (row pitch ldz) ->
  * out bf16 [T, 2*df + dr] = cat(sin(z[:, :df]), cos(z[:, :df]), z[:, df:]). bwd: d_out -> dz bf16 [T, ldz] (padding columns zeroed). */

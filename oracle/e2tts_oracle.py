@@ -299,12 +299,36 @@ def character_embed(sd, text, max_seq_len, prefix='embed_text'):  # :400-412
     return sd[prefix + '.embed.weight'][text]
 
 
+def interpolated_character_embed(sd, text, max_seq_len, mask=None, prefix='embed_text'):  # InterpolatedCharacterEmbed :414-482
+    embeds, positions = [], []
+    for b in range(text.shape[0]):                                   # :443 (per sample)
+        one_text = text[b][text[b] >= 0]                             # :445-446
+        e = sd[prefix + '.embed.weight'][one_text]                   # :447 (ids index the table directly)
+        text_seq_len = one_text.shape[0]
+        audio_seq_len = max_seq_len if mask is None else int(mask[b].sum())          # :455-457
+        e = F.interpolate(e.t()[None, :, :, None], (audio_seq_len, 1), mode='bilinear')[0, :, :, 0].t()   # interpolate_1d :237-244, :459
+        embeds.append(e)
+        positions.append(torch.linspace(0, text_seq_len, audio_seq_len))             # :460
+    embeds = torch.nn.utils.rnn.pad_sequence(embeds, batch_first=True)               # :469 (pad_sequence = partial(batch_first=True), :54)
+    positions = torch.nn.utils.rnn.pad_sequence(positions, batch_first=True)         # :470
+    embeds = F.pad(embeds, (0, 0, 0, max_seq_len - embeds.shape[-2]))                # :472
+    positions = F.pad(positions, (0, max_seq_len - positions.shape[-1]))[..., :max_seq_len]   # pad_to_length :473, :226-235
+    h = F.silu(positions[..., None] * sd[prefix + '.abs_pos_mlp.1.weight'][:, 0] + sd[prefix + '.abs_pos_mlp.1.bias'])   # :424-428
+    embeds = embeds + h @ sd[prefix + '.abs_pos_mlp.3.weight'].t() + sd[prefix + '.abs_pos_mlp.3.bias']   # :429, :477
+    if mask is not None:
+        embeds = torch.where(mask[..., None], embeds, torch.zeros_like(embeds))      # :479-480
+    return embeds
+
+
 def transformer_with_pred_head(sd, cfg, x, cond, times, mask, text, drop_text_cond):  # :1250-1301
     n = x.shape[1]
     h = x @ sd['proj_in.weight'].t() + sd['proj_in.bias'] + cond @ sd['cond_proj_in.weight'].t() + sd['cond_proj_in.bias']
     te = None
     if text is not None and not drop_text_cond:
-        te = character_embed(sd, text, n)
+        if 'embed_text.abs_pos_mlp.1.weight' in sd:                  # E2TTS(interpolated_text=True) :1233, :1283
+            te = interpolated_character_embed(sd, text, n, mask)
+        else:
+            te = character_embed(sd, text, n)
     emb = transformer_forward(sd, cfg, h, times=times, mask=mask, text_embed=te)
     return emb @ sd['to_pred.weight'].t() + sd['to_pred.bias']
 

@@ -215,9 +215,9 @@ def test_attention_core_vs_fp32_softmax(pkg, Np, H, big_logits):
 
 # ----------------------------------------------------------------------------------------------------------------------
 # (a), (e) whole model at the BASELINE widths against the oracle run on the host CPU
-def _whole_model(pkg, tkw, B, N, lens, seed, tol_pred=3e-2, model_kw=None):
+def _whole_model(pkg, tkw, B, N, lens, seed, tol_pred=3e-2, model_kw=None, e2tts_kw=None):
     torch.manual_seed(seed)
-    model = pkg.E2TTS(transformer=dict(dropout=0., max_seq_len=N, **tkw, **(model_kw or {})), use_vocos=False)
+    model = pkg.E2TTS(transformer=dict(dropout=0., max_seq_len=N, **tkw, **(model_kw or {})), use_vocos=False, **(e2tts_kw or {}))
     # dyn_scale 0.05 (5x the reference's init of the hyper-connections' dynamic scales): with the 0.5 of the 2-layer fixtures a depth-8
     # stack amplifies bf16 rounding of the residual streams ~10x — the fp32 oracle with its OWN stage outputs rounded to bf16
     # (O.STAGE_ROUND) then moves its prediction by 12.6 %, exactly what the kernels showed (gpurun_out/r2b_pytest.log). The probe below
@@ -285,6 +285,14 @@ def test_e2tts_attn_fourier_embed_input_vs_oracle(pkg):
     attention input, :909) — tcgen05 GEMM + b200_fourier_feat_* against the oracle, which tests/test_oracle_vs_reference.py pins to the
     reference's own code with the switch on. Loss, prediction and every parameter gradient incl. `layers.{i}.0.4.linear.weight`."""
     _whole_model(pkg, dict(dim=256, depth=2, heads=4), B=2, N=224, lens=[224, 170], seed=60, model_kw=dict(attn_fourier_embed_input=True))
+
+
+def test_e2tts_interpolated_text_vs_oracle(pkg):
+    """SURVEY §8f row 4, second variant: E2TTS(interpolated_text=True) (e2_tts.py:1135, :1233; InterpolatedCharacterEmbed :414-482) —
+    b200_interp_text_* + the abs-pos Linear as a tcgen05 GEMM with bias / residual / row-mask epilogue, against the oracle (pinned to
+    the reference's own code in tests/test_oracle_vs_reference.py): ragged text and audio lengths, gradients of the embedding table
+    and both abs_pos_mlp linears included."""
+    _whole_model(pkg, dict(dim=256, depth=2, heads=4), B=2, N=224, lens=[224, 150], seed=70, e2tts_kw=dict(interpolated_text=True))
 
 
 # ----------------------------------------------------------------------------------------------------------------------

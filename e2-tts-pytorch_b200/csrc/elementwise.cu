@@ -62,6 +62,7 @@ struct StemP {
     __nv_bfloat16* A;
     float* cond_out;
     int B, N, C, Cp;
+    int concat;   // != 0: columns [0, C) = cond, [C, 2C) = x  (cat(cond, x), e2_tts.py:1265)
 };
 __global__ void __launch_bounds__(256) stem_prepare_kernel(const StemP p) {
     pdl_wait();   // no global access before the previous kernel of the stream has completed (ptx.cuh)
@@ -69,9 +70,15 @@ __global__ void __launch_bounds__(256) stem_prepare_kernel(const StemP p) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int col = (int)(i % (2 * p.Cp));
         const long long row = i / (2 * p.Cp);
-        const int half = col / p.Cp, c = col % p.Cp;
+        int half = col / p.Cp, c = col % p.Cp;
+        bool valid = c < p.C;
+        if (p.concat) {
+            valid = col < 2 * p.C;
+            half = col < p.C ? 1 : 0;
+            c = col < p.C ? col : col - p.C;
+        }
         float v = 0.f;
-        if (c < p.C) {
+        if (valid) {
             const size_t src = (size_t)row * p.C + c;
             if (p.xin) {
                 v = half == 0 ? p.xin[src] : p.condin[src];
@@ -725,7 +732,7 @@ extern "C" int b200_pack_weights(const b200_pack_desc* descs_dev, int32_t n, b20
 extern "C" int b200_stem_prepare(const b200_stem_args* a, b200_stream_t stream) {
     B200_REQUIRE(a && a->A && ((a->x1 && a->x0 && a->times && a->span) || (a->x_in && a->cond_in)), "stem_prepare: null pointer");
     B200_REQUIRE(a->C > 0 && a->Cp >= a->C && (a->Cp % 64) == 0, "stem_prepare: Cp must be a multiple of 64 >= C");
-    StemP p{a->x1, a->x0, a->times, a->x_in, a->cond_in, a->span, (__nv_bfloat16*)a->A, a->cond_out, a->B, a->N, a->C, a->Cp};
+    StemP p{a->x1, a->x0, a->times, a->x_in, a->cond_in, a->span, (__nv_bfloat16*)a->A, a->cond_out, a->B, a->N, a->C, a->Cp, a->concat_cond};
     B200_LAUNCH(stem_prepare_kernel, grid_for((long long)a->B * a->N * a->Cp * 2), 256, 0, reinterpret_cast<cudaStream_t>(stream), p);
     return check_launch("stem_prepare_kernel");
 }

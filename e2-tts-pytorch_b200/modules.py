@@ -886,8 +886,6 @@ class E2TTS(Module):
         super().__init__()
         if num_freq_tokens != 1:
             _unsupported('num_freq_tokens', num_freq_tokens, 'e2_tts.py:1130')
-        if concat_cond:
-            _unsupported('concat_cond', concat_cond, 'e2_tts.py:1134')
         if odeint_kwargs.get('method', 'midpoint') not in ('midpoint', 'euler'):
             _unsupported('odeint_kwargs', odeint_kwargs, 'e2_tts.py:1122-1126 (fixed-grid midpoint/euler only)')
         self.num_freq_tokens, self.has_freq_axis = 1, False
@@ -908,9 +906,12 @@ class E2TTS(Module):
         num_channels = default(num_channels, self.mel_spec.n_mel_channels)
         self.num_channels = num_channels
         self.sampling_rate = default(sampling_rate, getattr(self.mel_spec, 'sampling_rate', None))
-        self.concat_cond = False
-        self.proj_in = nn.Linear(num_channels, dim)
-        self.cond_proj_in = nn.Linear(num_channels, dim)
+        self.concat_cond = concat_cond
+        if concat_cond:      # :1200-1204: one Linear on cat(cond, x) instead of two summed projections
+            self.proj_in = nn.Linear(num_channels * 2, dim)
+        else:
+            self.proj_in = nn.Linear(num_channels, dim)
+            self.cond_proj_in = nn.Linear(num_channels, dim)
         self.to_pred = nn.Linear(dim, num_channels)
         self.tokenizer, text_num_embeds = _resolve_tokenizer(tokenizer, text_num_embeds)
         self.cond_drop_prob = cond_drop_prob
@@ -942,15 +943,19 @@ class E2TTS(Module):
             stem = torch.zeros((d, 2 * Cp), device=dev, dtype=BF16)
             pred = torch.zeros((C, d), device=dev, dtype=BF16)
             tab = _PackTable()
-            tab.add(self.proj_in.weight, stem)
-            tab.add(self.cond_proj_in.weight, stem, col_off=Cp)
+            tab.add(self.proj_in.weight, stem)          # concat_cond: all 2C columns, matching stem_prepare's cat(cond, x) layout
+            if not self.concat_cond:
+                tab.add(self.cond_proj_in.weight, stem, col_off=Cp)
             tab.add(self.to_pred.weight, pred)
             self._wpack = dict(stem=stem, pred=pred, tab=tab, Cp=Cp)
         self._wpack['tab'].run()
         return self._wpack
 
     def _embed(self, A, B, N, times, mask, text, drop_text_cond, pk):
-        h = ops.StemLinear.apply(A, self.proj_in.weight, self.proj_in.bias, self.cond_proj_in.weight, self.cond_proj_in.bias, pk['stem'])
+        if self.concat_cond:
+            h = ops.StemLinear.apply(A, self.proj_in.weight, self.proj_in.bias, None, None, pk['stem'])
+        else:
+            h = ops.StemLinear.apply(A, self.proj_in.weight, self.proj_in.bias, self.cond_proj_in.weight, self.cond_proj_in.bias, pk['stem'])
         ids, te = None, None
         if exists(text) and not drop_text_cond:
             if isinstance(self.embed_text, InterpolatedCharacterEmbed):
@@ -966,7 +971,7 @@ class E2TTS(Module):
         B, N, C = x.shape
         drop_text_cond = default(drop_text_cond, self.training and pyrandom.random() < self.cond_drop_prob)
         pk = self._packed()
-        A, _ = ops.stem_prepare(B, N, C, pk['Cp'], x_in=x.to(F32).contiguous(), cond_in=cond.to(F32).contiguous())
+        A, _ = ops.stem_prepare(B, N, C, pk['Cp'], x_in=x.to(F32).contiguous(), cond_in=cond.to(F32).contiguous(), concat=self.concat_cond)
         if not torch.is_tensor(times):
             times = torch.tensor(times, device=x.device)
         y, pk = self._embed(A, B, N, times.to(x.device), mask, text, drop_text_cond, pk)
@@ -1090,11 +1095,11 @@ class E2TTS(Module):
             with torch.no_grad():
                 t_d = times + velocity_consistency_delta
                 vpk = vcm._packed()
-                A_d, _ = ops.stem_prepare(B, N, C, vpk['Cp'], x1=x1, x0=x0, times=t_d, span=span_u8)
+                A_d, _ = ops.stem_prepare(B, N, C, vpk['Cp'], x1=x1, x0=x0, times=t_d, span=span_u8, concat=velocity_consistency_model.concat_cond)
                 y_d, vpk = vcm._embed(A_d, B, N, t_d, mask, text, drop_text_cond, vpk)
                 vel_target = ops.PredHead.apply(y_d, vcm.to_pred.weight, vcm.to_pred.bias, vpk['pred'])
         pk = self._packed()
-        A, cond = ops.stem_prepare(B, N, C, pk['Cp'], x1=x1, x0=x0, times=times, span=span_u8, want_cond=True)
+        A, cond = ops.stem_prepare(B, N, C, pk['Cp'], x1=x1, x0=x0, times=times, span=span_u8, want_cond=True, concat=self.concat_cond)
         y, pk = self._embed(A, B, N, times, mask, text, drop_text_cond, pk)
         loss, pred, pred_data, parts = ops.FlowLossHead.apply(y, self.to_pred.weight, self.to_pred.bias, pk['pred'], x1, x0, span_u8, vel_target,
                                                               float(self.velocity_consistency_weight) if need_velocity_loss else 0.0)

@@ -895,13 +895,14 @@ class MaskedMean(Function):
         return dx, None, None, None
 
 
-def stem_prepare(B, N, C, Cp, *, x1=None, x0=None, times=None, span=None, x_in=None, cond_in=None, want_cond=False):
-    """Flow-matching input stage (e2_tts.py:1519-1543): builds the bf16 GEMM operand [w | cond] (2*Cp columns)."""
+def stem_prepare(B, N, C, Cp, *, x1=None, x0=None, times=None, span=None, x_in=None, cond_in=None, want_cond=False, concat=False):
+    """Flow-matching input stage (e2_tts.py:1519-1543): builds the bf16 GEMM operand [w | cond] (2*Cp columns); concat=True lays it out
+    as cat(cond, w) for the single proj_in of E2TTS(concat_cond=True) (:1263-1265)."""
     dev = (x1 if x1 is not None else x_in).device
     A = torch.empty((B * N, 2 * Cp), device=dev, dtype=BF16)
     cond_out = torch.empty((B, N, C), device=dev, dtype=F32) if want_cond else None
     a = lib.make_args('b200_stem_args', x1=x1, x0=x0, times=times, span=span, x_in=x_in, cond_in=cond_in, A=A, cond_out=cond_out,
-                      B=B, N=N, C=C, Cp=Cp)
+                      B=B, N=N, C=C, Cp=Cp, concat_cond=int(concat))
     lib.call('b200_stem_prepare', a, _stream())
     return A, cond_out
 

@@ -186,12 +186,15 @@ int b200_pack_weights(const b200_pack_desc* descs_dev, int32_t n, b200_stream_t 
 
 /* Flow-matching stem (e2_tts.py:1519-1543 and the operand of proj_in/cond_proj_in :1267-1277):
  *   training: A[row] = [ (1-t) x0 + t x1 | pad | where(span, 0, x1) | pad ] (bf16, 2*Cp columns), cond_out fp32
- *   direct  : x_in / cond_in given (sampling, transformer_with_pred_head).  Cp = C rounded up to 64. */
+ *   direct  : x_in / cond_in given (sampling, transformer_with_pred_head).  Cp = C rounded up to 64.
+ *   concat_cond != 0 (E2TTS(concat_cond=True), :1263-1265): A[row] = [ cond (C) | x (C) | pad ] = cat(cond, x), the operand of the
+ *   single Linear(2C -> dim) proj_in of that variant (:1201). */
 typedef struct {
     const float *x1, *x0, *times; const uint8_t* span;   /* training mode */
     const float *x_in, *cond_in;                          /* direct mode (x1 == NULL) */
     void* A; float* cond_out;
     int32_t B, N, C, Cp;
+    int32_t concat_cond;
 } b200_stem_args;
 int b200_stem_prepare(const b200_stem_args* a, b200_stream_t stream);
 

@@ -322,7 +322,10 @@ def interpolated_character_embed(sd, text, max_seq_len, mask=None, prefix='embed
 
 def transformer_with_pred_head(sd, cfg, x, cond, times, mask, text, drop_text_cond):  # :1250-1301
     n = x.shape[1]
-    h = x @ sd['proj_in.weight'].t() + sd['proj_in.bias'] + cond @ sd['cond_proj_in.weight'].t() + sd['cond_proj_in.bias']
+    if 'cond_proj_in.weight' in sd:   # :1270-1277
+        h = x @ sd['proj_in.weight'].t() + sd['proj_in.bias'] + cond @ sd['cond_proj_in.weight'].t() + sd['cond_proj_in.bias']
+    else:                              # E2TTS(concat_cond=True) :1263-1267
+        h = torch.cat((cond, x), dim=-1) @ sd['proj_in.weight'].t() + sd['proj_in.bias']
     te = None
     if text is not None and not drop_text_cond:
         if 'embed_text.abs_pos_mlp.1.weight' in sd:                  # E2TTS(interpolated_text=True) :1233, :1283

@@ -59,7 +59,14 @@ def test_unsupported_switches_raise(pkg):
     with pytest.raises(NotImplementedError):
         pkg.Transformer(dim=128, depth=2, heads=2, attn_laser=True)
     with pytest.raises(NotImplementedError):
-        pkg.E2TTS(transformer=dict(dim=128, depth=2, heads=2), concat_cond=True, use_vocos=False)
+        pkg.Transformer(dim=128, depth=2, heads=2, has_freq_axis=True)
+    with pytest.raises(NotImplementedError):
+        pkg.E2TTS(transformer=dict(dim=128, depth=2, heads=2), num_freq_tokens=2, use_vocos=False)
+    # the variants that ARE built construct with the reference's parameter layout
+    m = pkg.E2TTS(transformer=dict(dim=128, depth=2, heads=2, attn_fourier_embed_input=True), concat_cond=True, interpolated_text=True, use_vocos=False)
+    sd = m.state_dict()
+    assert sd['proj_in.weight'].shape == (128, 200) and 'cond_proj_in.weight' not in sd
+    assert sd['embed_text.abs_pos_mlp.3.weight'].shape == (64, 64) and sd['transformer.layers.0.0.4.linear.weight'].shape == (96, 128)
 
 
 def test_tokenizer_and_mask_helpers(pkg):

@@ -287,6 +287,12 @@ def test_e2tts_attn_fourier_embed_input_vs_oracle(pkg):
     _whole_model(pkg, dict(dim=256, depth=2, heads=4), B=2, N=224, lens=[224, 170], seed=60, model_kw=dict(attn_fourier_embed_input=True))
 
 
+def test_e2tts_concat_cond_vs_oracle(pkg):
+    """SURVEY §8f row 4, third variant: E2TTS(concat_cond=True) (e2_tts.py:1134, :1200-1201, :1263-1267): the stem GEMM reads
+    cat(cond, x) (b200_stem_prepare concat layout) against ONE packed Linear(2C -> dim); oracle pinned to the reference's own code."""
+    _whole_model(pkg, dict(dim=256, depth=2, heads=4), B=2, N=224, lens=[224, 190], seed=80, e2tts_kw=dict(concat_cond=True))
+
+
 def test_e2tts_interpolated_text_vs_oracle(pkg):
     """SURVEY §8f row 4, second variant: E2TTS(interpolated_text=True) (e2_tts.py:1135, :1233; InterpolatedCharacterEmbed :414-482) —
     b200_interp_text_* + the abs-pos Linear as a tcgen05 GEMM with bias / residual / row-mask epilogue, against the oracle (pinned to

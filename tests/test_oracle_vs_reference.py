@@ -62,15 +62,40 @@ def test_text_dropped_branch_vs_reference():
 
 
 def test_variant_state_dicts_match_reference():
-    """The two non-default switches that are built (attn_fourier_embed_input, interpolated_text) keep the reference's parameter names
+    """The non-default switches that are built (attn_fourier_embed_input, interpolated_text, concat_cond) keep the reference's parameter names
     and shapes, so reference checkpoints of those variants load."""
     ref = load_reference()
     import e2_tts_pytorch_b200 as pkg
-    kw = dict(transformer=dict(dim=128, depth=2, heads=2, attn_fourier_embed_input=True), use_vocos=False, interpolated_text=True)
+    kw = dict(transformer=dict(dim=128, depth=2, heads=2, attn_fourier_embed_input=True), use_vocos=False, interpolated_text=True,
+              concat_cond=True)
     a, b = ref.E2TTS(**kw).state_dict(), pkg.E2TTS(**kw).state_dict()
     assert set(a) == set(b), (sorted(set(a) - set(b))[:5], sorted(set(b) - set(a))[:5])
     for k in a:
         assert a[k].shape == b[k].shape, k
+
+
+def test_concat_cond_vs_reference():
+    """E2TTS(concat_cond=True) (e2_tts.py:1134, :1200-1201, :1263-1267): one Linear(2C -> dim) on cat(cond, x) instead of two summed
+    projections — the reference's own code."""
+    ref = load_reference()
+    torch.manual_seed(29)
+    kw = dict(dim=128, depth=2, heads=2)
+    model = ref.E2TTS(transformer=dict(dropout=0., max_seq_len=128, **kw), use_vocos=False, concat_cond=True)
+    model.load_state_dict(O.randomize_zero_init(model.state_dict(), seed=29))
+    assert 'cond_proj_in.weight' not in model.state_dict() and model.state_dict()['proj_in.weight'].shape == (128, 200)
+    mel = torch.randn(2, 64, 100)
+    lens_t = torch.tensor([64, 41])
+    text = ['abc', 'defgh ij']
+    out, rec = run_reference_forward(ref, model, mel, text, lens=lens_t, drop_text_cond=False)
+    out.loss.backward()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    o = O.e2tts_forward(sd, O.TransformerCfg(**kw), mel, O.list_str_to_tensor(text), lens=lens_t, drop_text_cond=False, **rec)
+    o['loss'].backward()
+    assert abs(float(o['loss']) - float(out.loss)) <= 1e-5 * abs(float(out.loss))
+    assert rel_l2(o['pred'], out.pred_flow) < 1e-4
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert (p.grad - sd[k].grad).abs().max() <= 2e-4 * p.grad.abs().max() + 1e-7, k
 
 
 def test_interpolated_text_vs_reference():

@@ -1,4 +1,4 @@
-"""Developer tool (GPU): device time of the hyper-connection width kernels at a BASELINE shape (B200_HC16=0/1 selects the backward variant)."""
+"""Developer tool (GPU): device time of the hyper-connection width kernels (unfused path) at the BASELINE shapes."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -32,5 +32,5 @@ for (B, Np, D) in ((16, 1056, 512), (16, 1056, 256), (8, 2080, 1024)):
             tf.append(e[0].elapsed_time(e[1]) * 1e3); tb.append(e[2].elapsed_time(e[3]) * 1e3)
     tf.sort(); tb.sort()
     fb, bb = 9 * D * 2 * T, 13 * D * 2 * T
-    print(f'HC16={os.environ.get("B200_HC16", "1")} B{B} Np{Np} D{D}: width fwd {tf[len(tf)//2]:.1f} us = {fb / tf[len(tf)//2] * 1e-3:.0f} GB/s, '
+    print(f'B{B} Np{Np} D{D}: width fwd {tf[len(tf)//2]:.1f} us = {fb / tf[len(tf)//2] * 1e-3:.0f} GB/s, '
           f'bwd (token kernel + param GEMM + finalize + zero slab) {tb[len(tb)//2]:.1f} us = {bb / tb[len(tb)//2] * 1e-3:.0f} GB/s')

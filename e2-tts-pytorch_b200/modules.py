@@ -235,13 +235,19 @@ class InterpolatedCharacterEmbed(Module):  # e2_tts.py:414-482 (E2TTS(interpolat
         self.embed = nn.Embedding(num_embeds, dim)
         self.abs_pos_mlp = nn.Sequential(nn.Identity(), nn.Linear(1, dim), nn.SiLU(), nn.Linear(dim, dim))   # index 0 = the reference's Rearrange
 
+    @staticmethod
+    def compact(text):
+        """(b, nt) int64 with -1 padding anywhere -> (ids int32 (b, nt) with each row's valid characters first, in their original order;
+        text_len int32 (b,)) — `one_text[one_text >= 0]` of e2_tts.py:445-446 for the whole batch."""
+        valid = text >= 0
+        order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
+        ids_c = torch.gather(text.clamp(min=0), 1, order).to(torch.int32).contiguous()
+        return ids_c, valid.sum(dim=1).to(torch.int32)
+
     def embed_bf16(self, text, max_seq_len, mask=None):
         """text (b, nt) int64 with -1 padding, mask (b, n) bool | None -> bf16 [b * n, dim] (rows of masked frames are zero)."""
         B = text.shape[0]
-        valid = text >= 0
-        order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)        # valid characters first, original order kept (:445)
-        ids_c = torch.gather(text.clamp(min=0), 1, order).to(torch.int32).contiguous()
-        text_len = valid.sum(dim=1).to(torch.int32)
+        ids_c, text_len = self.compact(text)
         if exists(mask):
             audio_len = mask.sum(dim=1).to(torch.int32)                           # :455-457
             mask_u8 = mask.to(torch.uint8).contiguous()

@@ -101,3 +101,14 @@ def test_positional_struct_marshalling_checks_the_header_order(pkg):
     assert s.lda == 8 and s.force_tile == 0
     with pytest.raises(RuntimeError, match='field order'):
         lib.make_args_positional('b200_gemm_args', ('lda', 'A'), (8, None))
+
+
+def test_host_helpers_of_the_round2_paths(pkg):
+    """Host-side pieces of the fused hyper-connection path and of InterpolatedCharacterEmbed (no kernel calls)."""
+    import torch
+    from e2_tts_pytorch_b200 import ops
+    assert ops.hc_can_fuse(16 * 1056, 4) and ops.hc_can_fuse(2 * 1312, 4) and not ops.hc_can_fuse(2 * 150, 4)
+    text = torch.tensor([[5, -1, 7, 9, -1], [-1, -1, -1, -1, -1], [1, 2, 3, 4, 5]])
+    ids, n = pkg.modules.InterpolatedCharacterEmbed.compact(text)
+    assert n.tolist() == [3, 0, 5] and ids.dtype == torch.int32
+    assert ids[0, :3].tolist() == [5, 7, 9] and ids[2].tolist() == [1, 2, 3, 4, 5]
